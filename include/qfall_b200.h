@@ -1,0 +1,155 @@
+/* qfall_b200.h -- C ABI of the B200 (sm_100a) backend for the batched PSF /
+ * FIPS 203 hot path of qfall/tools.
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the
+ * reference's `PSF` trait (src/primitive/psf.rs:39-81) or of its
+ * `LossyCompressionFIPS203` trait (src/compression/lossy_compression_fips203.rs:20-59)
+ * for a BATCH of B targets.  A Rust shim converts qfall-math values to the
+ * fixed-width buffers below (see INTEGRATION.md for the extern "C" block).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all matrices row-major;
+ *  - Range values (u, A, a_bar, tags ...) are residues in [0,q), q < 2^62, stored
+ *    as int64 (the FLINT small-word form qfall-math holds them in);
+ *  - Domain values (sigma, e, samp_d output) are int32 (|entry| <= s*r*sqrt(m));
+ *  - a batch is "one row per target": sigma/e are B x m, u is B x n;
+ *    ring values are B x (k+2) x n coefficients (coefficient embedding order,
+ *    gpv_ring.rs:172-178);
+ *  - every function returns a qf_status, never aborts; qf_last_error() gives text;
+ *  - functions without a suffix take HOST pointers and synchronise before
+ *    returning; `_dev` variants take DEVICE pointers, enqueue on the context's
+ *    stream and do not synchronise;
+ *  - one context per thread (or external locking): the reference types are
+ *    neither Send nor Sync (gadget_parameters.rs:51).
+ *  - samplers are keyed by (seed, first_index + row): a batch split across calls,
+ *    chunks or GPUs yields the same preimages as one call.
+ */
+#ifndef QFALL_B200_H
+#define QFALL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QF_OK = 0,
+    QF_ERR_INVALID = 1,       /* bad argument / shape (reference: panic or MathError) */
+    QF_ERR_CUDA = 2,          /* CUDA runtime failure */
+    QF_ERR_NOT_IN_DOMAIN = 3, /* f_a: some sigma fails check_domain (reference: assert!, gpv.rs:191) */
+    QF_ERR_NO_KEY = 4,        /* key / trapdoor not installed */
+    QF_ERR_UNSUPPORTED = 5,   /* parameter range outside this backend */
+    QF_ERR_NUMERIC = 6        /* internal range check tripped (value did not fit) */
+} qf_status;
+
+typedef enum {
+    QF_PSF_GPV = 0,          /* src/primitive/psf/gpv.rs */
+    QF_PSF_PERTURBATION = 1, /* src/primitive/psf/mp_perturbation.rs */
+    QF_PSF_GPV_RING = 2      /* src/primitive/psf/gpv_ring.rs */
+} qf_psf_kind;
+
+/* GadgetParameters / GadgetParametersRing (gadget_parameters.rs:44-52, 73-81) plus the
+ * Gaussian parameters of the PSF struct (gpv.rs:54-57, mp_perturbation.rs:58-62,
+ * gpv_ring.rs:63-67). */
+typedef struct {
+    int32_t kind;       /* qf_psf_kind */
+    int64_t n;          /* security parameter / ring degree */
+    int64_t k;          /* gadget length ceil(log_base q) */
+    int64_t m_bar;      /* classical: columns of A_bar; ring: k + 2 */
+    int64_t base;       /* gadget base */
+    uint64_t q;         /* modulus, < 2^62 */
+    double s;           /* Gaussian parameter s */
+    double r;           /* rounding parameter r (perturbation only; 1 otherwise) */
+    uint64_t norm_bound; /* floor of the check_domain bound (s^2 m [r^2]); 0 = derive from s, r */
+} qf_params;
+
+typedef struct qf_ctx qf_ctx;
+
+/* ---- context ----------------------------------------------------------- */
+qf_status qf_ctx_create(const qf_params* params, int device, qf_ctx** out);
+void qf_ctx_destroy(qf_ctx* ctx);
+const char* qf_last_error(const qf_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t); NULL = the context's own stream */
+qf_status qf_set_stream(qf_ctx* ctx, void* cuda_stream);
+/* targets processed per internal chunk (bounds the workspace); 0 = default */
+qf_status qf_set_chunk(qf_ctx* ctx, int64_t targets_per_chunk);
+qf_status qf_synchronize(qf_ctx* ctx);
+/* number of kernels this context has launched so far */
+uint64_t qf_launch_count(const qf_ctx* ctx);
+
+/* ---- key material -------------------------------------------------------- */
+/* A: n x m residues (PSFGPV / PSFPerturbation `A`, gpv.rs:60, mp_perturbation.rs:194) */
+qf_status qf_set_a(qf_ctx* ctx, const int64_t* a);
+/* PSFPerturbation trapdoor (mp_perturbation.rs:195): R m_bar x nk in {-1,0,1} (any small ints),
+ * sqrt_sigma_2 m x m lower-triangular, and ONE k x k diagonal block of the gadget short basis
+ * I_n (x) S_k with its GSO (gadget_classical.rs:248-287; the shim checks block-diagonality). */
+qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const double* sqrt_sigma_2,
+                                       const int64_t* s_block, const double* s_block_gso);
+/* PSFGPV trapdoor (gpv.rs:61): short basis S (dim x dim, columns are basis vectors) and its
+ * GSO.  dim = m for QF_PSF_GPV, n*(k+2) (coefficient embedding) for QF_PSF_GPV_RING. */
+qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* s_gso);
+/* ring key: (k+2) polynomials of n coefficients (gpv_ring.rs:70) */
+qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a);
+
+/* ---- TrapGen (gadget_classical.rs:56-68, gadget_ring.rs:62-81) ------------ */
+/* A = [A_bar | tag*G - A_bar*R] mod q from supplied A_bar (n x m_bar), R (m_bar x nk) and
+ * tag (n x n, NULL = identity).  Bit-exact against the reference given the same inputs.
+ * Writes A (n x m) and installs it as the context key. */
+qf_status qf_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int8_t* r, const int64_t* tag, int64_t* a_out);
+/* Samples A_bar uniform (gpv.rs:84) and R from PlusMinusOneZero (trapdoor_distribution.rs:82-86)
+ * on the device (Philox, `seed`), then as qf_trap_gen_from with tag = I. */
+qf_status qf_trap_gen(qf_ctx* ctx, uint64_t seed, int64_t* a_out, int8_t* r_out);
+/* Ring: A = [1 | a_bar | g^t - (a_bar*r + e)] mod (X^n+1, q); r, e: k x n small coefficients. */
+qf_status qf_ring_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int32_t* r, const int32_t* e,
+                                int64_t* a_out);
+
+/* ---- PSF::f_a / check_domain ------------------------------------------------ */
+/* u[b] = A * sigma[b] mod q and in_domain[b] = check_domain(sigma[b])
+ * (gpv.rs:190-193,219-224; mp_perturbation.rs:366-369,396-402; gpv_ring.rs:243-247,274-283).
+ * Returns QF_ERR_NOT_IN_DOMAIN if any flag is 0 (u rows of such targets are unspecified),
+ * the shim turns that into the reference's panic.  in_domain may be NULL. */
+qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain);
+qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain);
+qf_status qf_check_domain(qf_ctx* ctx, const int32_t* sigma, int64_t batch, uint8_t* in_domain);
+
+/* ---- PSF::samp_d (gpv.rs:113-116, mp_perturbation.rs:264-267, gpv_ring.rs:118-122) --- */
+qf_status qf_samp_d(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first_index, int32_t* out);
+qf_status qf_samp_d_dev(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first_index, int32_t* out);
+
+/* ---- PSF::samp_p (gpv.rs:152-161, mp_perturbation.rs:304-336, gpv_ring.rs:160-212) --- */
+/* e[b] with A e[b] = u[b] mod q, distributed as the reference's sampler. */
+qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first_index,
+                    int32_t* e_out);
+qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first_index,
+                        int32_t* e_out);
+
+/* ---- LossyCompressionFIPS203 (lossy_compression_fips203.rs:89-114, 143-172) ----------- */
+/* Flat coefficient streams (a polynomial / matrix of polynomials is just `count` coefficients).
+ * u16 variants: q < 2^16, 1 <= d <= 16; device_ptrs != 0 -> in/out are device pointers and the
+ * call is asynchronous on `cuda_stream` (may be NULL = default stream). */
+qf_status qf_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
+                          int device_ptrs, void* cuda_stream);
+qf_status qf_decompress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
+                            int device_ptrs, void* cuda_stream);
+/* FLINT-word variants, any q < 2^62, 1 <= d <= 62. */
+qf_status qf_compress_i64(const int64_t* in, int64_t* out, size_t count, uint64_t q, uint32_t d,
+                          int device_ptrs, void* cuda_stream);
+qf_status qf_decompress_i64(const int64_t* in, int64_t* out, size_t count, uint64_t q, uint32_t d,
+                            int device_ptrs, void* cuda_stream);
+
+/* ---- Z::sample_discrete_gauss for a batch of (centre) values (qfall-math SampleZ as used at
+ * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers. */
+qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out);
+
+/* ---- synthetic inputs for benchmarks (Philox, on device) -------------------------------- */
+qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* cuda_stream);
+
+/* library / build identification */
+const char* qf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QFALL_B200_H */

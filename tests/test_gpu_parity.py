@@ -1,0 +1,513 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for every deterministic function; for the samplers: A e = u exactly,
+check_domain, and chi-square / moment tests against the exact law D_{Z,s,c}
+(rho(x) = exp(-pi (x-c)^2 / s^2), CONTRIBUTING.md:35-45) and the oracle's reference sampler."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import qfall_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tools_b200
+
+    return tools_b200
+
+
+def _chi2_ok(counts, probs, n):
+    keep = probs * n >= 8
+    exp = probs[keep] * n
+    chi = ((counts[keep] - exp) ** 2 / exp).sum()
+    # lump the rest
+    rest_e = n - exp.sum()
+    rest_o = n - counts[keep].sum()
+    dof = keep.sum() - 1
+    if rest_e >= 8:
+        chi += (rest_o - rest_e) ** 2 / rest_e
+        dof += 1
+    return chi < dof + 5.0 * np.sqrt(2.0 * dof), chi, dof
+
+
+# ----------------------------------------------------------------------------------
+# FIPS 203 compression: bit-exact (lossy_compression_fips203.rs:101-111, 159-169)
+# ----------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("q", [257, 3329])
+def test_compress_exhaustive(T, q):
+    x = np.arange(q, dtype=np.uint16)
+    for d in range(1, 13):
+        c = T.lossy_compress(x, d, q)
+        assert c.dtype == np.uint16
+        assert np.array_equal(c.astype(np.uint64), O.lossy_compress_np(x, d, q))
+        back = T.lossy_decompress(c, d, q)
+        assert np.array_equal(back.astype(np.uint64), O.lossy_decompress_np(c, d, q))
+        # int64 (FLINT word) path
+        c64 = T.lossy_compress(x.astype(np.int64), d, q)
+        assert np.array_equal(c64.astype(np.uint64), O.lossy_compress_np(x, d, q))
+        assert np.array_equal(T.lossy_decompress(c64, d, q).astype(np.uint64), O.lossy_decompress_np(c, d, q))
+        # round-trip bound (lossy_compression_fips203.rs:281-326)
+        dist = np.abs(back.astype(np.int64) - x.astype(np.int64))
+        dist = np.minimum(dist, q - dist)
+        assert dist.max() <= 2 ** max(O.ceil_log(q, 2) - d - 1, 0)
+
+
+@pytest.mark.parametrize("count", [0, 1, 7, 8, 9, 255, 256 * 16 + 3, 1_000_003])
+def test_compress_ragged_sizes(T, count):
+    rng = np.random.default_rng(count)
+    x = rng.integers(0, 3329, count).astype(np.uint16)
+    for d in (1, 4, 10, 11):
+        c = T.lossy_compress(x, d, 3329)
+        assert np.array_equal(c.astype(np.uint64), O.lossy_compress_np(x, d, 3329))
+        assert np.array_equal(T.lossy_decompress(c, d, 3329).astype(np.uint64), O.lossy_decompress_np(c, d, 3329))
+
+
+def test_compress_matrix_shape_and_d0(T):
+    rng = np.random.default_rng(2)
+    mat = rng.integers(0, 3329, (2, 3, 16)).astype(np.uint16)  # MatPolynomialRingZq 2x3, degree 16
+    c = T.lossy_compress(mat, 11, 3329)
+    assert c.shape == mat.shape
+    with pytest.raises(AssertionError):
+        T.lossy_compress(mat, 0, 3329)  # lossy_compression_fips203.rs:329-338 should_panic
+    with pytest.raises(AssertionError):
+        T.lossy_decompress(mat, 0, 3329)
+
+
+def test_compress_wide_modulus(T):
+    rng = np.random.default_rng(9)
+    q = 2**61 - 1
+    x = rng.integers(0, q, 5000, dtype=np.int64)
+    for d in (1, 13, 40, 61):
+        want = np.array([O.compress_coeff(int(v), d, q) for v in x], dtype=np.int64)
+        got = T.lossy_compress(x, d, q)
+        assert np.array_equal(got, want)
+        wantd = np.array([O.decompress_coeff(int(v), d, q) for v in want], dtype=np.int64)
+        assert np.array_equal(T.lossy_decompress(got, d, q), wantd)
+
+
+# ----------------------------------------------------------------------------------
+# TrapGen: bit-exact (gadget_classical.rs:56-68)
+# ----------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,q,with_tag", [(5, 32, False), (8, 64, False), (42, 32, True), (16, 2**24 - 3, False),
+                                          (12, 2**31 - 1, True), (6, 2**40 + 15, False)])
+def test_trap_gen_from_bit_exact(T, n, q, with_tag):
+    from tools_b200.psf import gen_trapdoor
+
+    rng = np.random.default_rng(n)
+    gp, po = T.GadgetParameters.init_default(n, q), O.GadgetParameters.init_default(n, q)
+    a_bar = rng.integers(0, q, (n, gp.m_bar), dtype=np.int64)
+    r = np.array(O.sample_pm_one_zero(rng, gp.m_bar, n * gp.k), dtype=np.int8)
+    tag = O.mat_identity(n)
+    if with_tag:
+        for i in range(n):
+            for j in range(i + 1, n):
+                tag[i][j] = int(rng.integers(0, q))
+    want = O.gen_trapdoor(po, a_bar.tolist(), tag, r.tolist())
+    got = gen_trapdoor(gp, a_bar, r, np.array(tag, dtype=np.int64) if with_tag else None)
+    assert got.tolist() == want
+    # A [R; I] = H G   (gadget_classical.rs:362-414)
+    td = np.vstack([r.astype(object), np.eye(n * gp.k, dtype=object)])
+    lhs = (got.astype(object).dot(td)) % q
+    rhs = np.array(O.mat_mul(tag, O.gen_gadget_mat(n, gp.k, 2), q), dtype=object)
+    assert np.array_equal(lhs, rhs)
+
+
+# ----------------------------------------------------------------------------------
+# f_a / check_domain: bit-exact
+# ----------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,q,s,r", [(8, 64, 25.0, 3.0), (5, 256, 25.0, 2.3219280948873622), (24, 2**24 - 3, 300.0, 4.0),
+                                     (16, 2**31 - 1, 4000.0, 2.0), (3, 2**45 + 59, 50.0, 1.5)])
+def test_f_a_classical_bit_exact(T, n, q, s, r):
+    rng = np.random.default_rng(n + 1)
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, r, s)
+    a = rng.integers(0, q, (n, gp.m), dtype=np.int64)
+    B = 300
+    sig = psf.samp_d_batch(B, seed=5)
+    assert sig.shape == (B, gp.m) and sig.dtype == np.int32
+    u, flags = psf.f_a_batch(a, sig)
+    assert flags.all()
+    want = O.f_a_classical_batch(a, sig, q)
+    assert np.array_equal(u, want)
+    # single-target trait call == A * sigma (mp_perturbation.rs:451-464)
+    assert psf.f_a(a, sig[0]).tolist() == O.f_a_classical(a, sig[0], q)
+    # extreme in-domain vector: one huge entry (norm exactly at the bound)
+    big = np.zeros((2, gp.m), dtype=np.int32)
+    big[0, 3] = int(np.floor(s * r * np.sqrt(gp.m)))
+    big[1, gp.m - 1] = -int(np.floor(s * r * np.sqrt(gp.m)))
+    u2, f2 = psf.f_a_batch(a, big)
+    assert f2.all() and np.array_equal(u2, O.f_a_classical_batch(a, big, q))
+
+
+def test_f_a_domain_errors(T):
+    # gpv.rs:287-368 / mp_perturbation.rs:466-554
+    gp = T.GadgetParameters.init_default(8, 128)
+    psf = T.PSFGPV(gp, 10.0)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 128, (8, gp.m), dtype=np.int64)
+    m = gp.m
+    with pytest.raises(AssertionError):
+        psf.f_a(a, np.zeros((m, 2), dtype=np.int64))  # matrix
+    with pytest.raises(AssertionError):
+        psf.f_a(a, np.zeros(m - 1, dtype=np.int64))  # wrong length
+    too_long = np.zeros(m, dtype=np.int64)
+    too_long[0] = round(10.0) * m
+    with pytest.raises(AssertionError):
+        psf.f_a(a, too_long)
+    value = round(10.0)
+    assert psf.check_domain(np.zeros(m, dtype=np.int64))
+    assert psf.check_domain(np.full(m, value, dtype=np.int64))
+    assert psf.check_domain(np.full((m, 1), value, dtype=np.int64))
+    assert not psf.check_domain(np.zeros((m, 2), dtype=np.int64))
+    assert not psf.check_domain(np.zeros(m + 1, dtype=np.int64))
+    assert not psf.check_domain(np.zeros(m - 1, dtype=np.int64))
+    assert not psf.check_domain(too_long)
+    # oracle agrees on random vectors around the boundary
+    for scale in (5, 9, 10, 11, 14):
+        v = rng.integers(-scale, scale + 1, m)
+        assert psf.check_domain(v) == O.check_domain_gpv(v.tolist(), m, 10.0)
+    # batch flags: mixed
+    sig = np.zeros((3, m), dtype=np.int32)
+    sig[1, 0] = value * m
+    u, flags = psf.f_a_batch(a, sig, strict=False)
+    assert flags.tolist() == [True, False, True]
+    with pytest.raises(AssertionError):
+        psf.f_a_batch(a, sig)
+
+
+# ----------------------------------------------------------------------------------
+# samplers: exact law
+# ----------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("s,c", [(3.0, 0.0), (3.0, 0.37), (7.5, -12.5), (1.8, 1e6 + 0.25), (20.0, 3.999),
+                                 (4.0 * np.sqrt(5), -0.5), (1000.0, 7.3), (60000.0, 123456.789)])
+def test_sample_z_law(T, s, c):
+    from tools_b200 import _ffi
+
+    n = 400_000
+    centers = np.full(n, c, dtype=np.float64)
+    out = np.empty(n, dtype=np.int64)
+    st = _ffi.lib().qf_sample_z(_ffi.ptr(centers), n, s, 1234, _ffi.ptr(out))
+    assert st == 0
+    if s < 100:
+        xs, pm = O.dgauss_pmf(s, c)
+        cnt = np.array([(out == x).sum() for x in xs])
+        assert cnt.sum() == n, "sample outside the 6 s tail cut"
+        ok, chi, dof = _chi2_ok(cnt, pm, n)
+        assert ok, (chi, dof)
+    sigma = s / np.sqrt(2 * np.pi)
+    xs, pm = O.dgauss_pmf(s, c)
+    mean = (xs * pm).sum()
+    var = ((xs - mean) ** 2 * pm).sum()
+    assert abs(out.mean() - mean) < 5 * sigma / np.sqrt(n)
+    assert abs(out.var() - var) < 6 * var * np.sqrt(2.0 / n)
+    # fourth moment (kurtosis of a Gaussian is 3)
+    m4 = ((out - out.mean()) ** 4).mean() / out.var() ** 2
+    assert abs(m4 - ((xs - mean) ** 4 * pm).sum() / var**2) < 0.06
+
+
+def test_sample_z_matches_reference_sampler(T):
+    """Two-sample chi-square between the CUDA sampler and the oracle's restatement of the
+    reference SampleZ (uniform proposal + rejection) at the same (s, c)."""
+    from tools_b200 import _ffi
+
+    s, c, n = 3.0 * np.sqrt(5), 0.3, 200_000
+    out = np.empty(n, dtype=np.int64)
+    assert _ffi.lib().qf_sample_z(_ffi.ptr(np.full(n, c)), n, s, 99, _ffi.ptr(out)) == 0
+    rng = np.random.default_rng(5)
+    # vectorised restatement of O.sample_z (same proposal / acceptance rule)
+    lo, hi = int(np.ceil(c - np.ceil(6 * s))), int(np.floor(c + np.floor(6 * s)))
+    ref = []
+    while len(ref) < n:
+        x = rng.integers(lo, hi + 1, 4 * n)
+        acc = rng.random(4 * n) < np.exp(-np.pi * (x - c) ** 2 / (s * s))
+        ref.extend(x[acc].tolist())
+    ref = np.array(ref[:n])
+    xs = np.arange(lo, hi + 1)
+    a = np.array([(out == x).sum() for x in xs], dtype=np.float64)
+    b = np.array([(ref == x).sum() for x in xs], dtype=np.float64)
+    keep = (a + b) >= 20
+    chi = (((a - b) ** 2) / (a + b))[keep].sum()
+    dof = keep.sum() - 1
+    assert chi < dof + 5 * np.sqrt(2 * dof), (chi, dof)
+
+
+def test_samp_d(T):
+    # gpv.rs:238-249, mp_perturbation.rs:416-428, gpv_ring.rs:302-313
+    for n, q in [(5, 256), (10, 128), (15, 157)]:
+        gp = T.GadgetParameters.init_default(n, q)
+        psf = T.PSFGPV(gp, 10.0)
+        d = psf.samp_d_batch(50, seed=n)
+        assert psf.check_domain_batch(d).all()
+        assert psf.check_domain(psf.samp_d())
+        pp = T.PSFPerturbation(gp, float(np.log2(n)), 25.0)
+        assert pp.check_domain_batch(pp.samp_d_batch(50, seed=n)).all()
+    gr = T.GadgetParametersRing.init_default(5, 123456789)
+    pr = T.PSFGPVRing(gr, 1000.0, 1.005)
+    d = pr.samp_d_batch(20, seed=3)
+    assert d.shape == (20, gr.k + 2, 5)
+    assert pr.check_domain_batch(d).all() and pr.check_domain(pr.samp_d())
+    # law of the coordinates: D_{Z, s} with s = 10
+    gp = T.GadgetParameters.init_default(8, 64)
+    psf = T.PSFGPV(gp, 10.0)
+    flat = psf.samp_d_batch(4000, seed=1).reshape(-1)
+    xs, pm = O.dgauss_pmf(10.0, 0.0)
+    cnt = np.array([(flat == x).sum() for x in xs])
+    ok, chi, dof = _chi2_ok(cnt, pm, flat.size)
+    assert ok, (chi, dof)
+    # determinism and batch splitting
+    a = psf.samp_d_batch(64, seed=7)
+    b = np.concatenate([psf.samp_d_batch(40, seed=7), psf.samp_d_batch(24, seed=7, first_index=40)])
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, psf.samp_d_batch(64, seed=8))
+
+
+# ----------------------------------------------------------------------------------
+# PSFPerturbation::samp_p (mp_perturbation.rs:304-336)
+# ----------------------------------------------------------------------------------
+
+
+def _pert_setup(T, n, q, r, s, seed=1):
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, r, s)
+    a, td = psf.trap_gen(seed=seed)
+    return gp, psf, a, td
+
+
+@pytest.mark.parametrize("n,q,r,s", [(8, 64, 3.0, 25.0), (5, 256, float(np.log2(5)), 25.0), (6, 128, float(np.log2(6)), 25.0),
+                                     (8, 127, 3.0, 30.0), (16, 2**20 - 3, 4.0, 80.0)])
+def test_samp_p_perturbation_preimage_and_domain(T, n, q, r, s):
+    gp, psf, a, td = _pert_setup(T, n, q, r, s)
+    # the generated key really is a G-trapdoor
+    rmat = td[0]
+    tdm = np.vstack([rmat.astype(object), np.eye(n * gp.k, dtype=object)])
+    assert np.array_equal(a.astype(object).dot(tdm) % q, np.array(O.gen_gadget_mat(n, gp.k, 2), dtype=object) % q)
+    rng = np.random.default_rng(3)
+    B = 2000
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=11)
+    assert e.shape == (B, gp.m)
+    assert np.array_equal(O.f_a_classical_batch(a, e, q), u)  # A e = u exactly, every target
+    assert psf.check_domain_batch(e).all()
+    u2, flags = psf.f_a_batch(a, e)
+    assert np.array_equal(u2, u) and flags.all()
+    # README flow (mp_perturbation.rs:432-448): trait-shaped single calls
+    ds = psf.samp_d(seed=4)
+    rng_fa = psf.f_a(a, ds)
+    pre = psf.samp_p(a, td, rng_fa, seed=5)
+    assert psf.check_domain(pre) and psf.f_a(a, pre).tolist() == rng_fa.tolist()
+    # determinism / batch splitting / seed sensitivity
+    e_again = psf.samp_p_batch(a, td, u, seed=11)
+    assert np.array_equal(e, e_again)
+    e_split = np.concatenate([psf.samp_p_batch(a, td, u[:700], seed=11),
+                              psf.samp_p_batch(a, td, u[700:], seed=11, first_index=700)])
+    assert np.array_equal(e, e_split)
+    assert not np.array_equal(e, psf.samp_p_batch(a, td, u, seed=12))
+
+
+def test_samp_p_perturbation_distribution(T):
+    """Marginals against the reference algorithm (oracle restatement) at the same s, and against
+    the spherical law the construction targets: each coordinate ~ D_{Z, s r}-like with
+    variance (s r)^2 / (2 pi)."""
+    n, q, r, s = 8, 64, 3.0, 25.0
+    gp, psf, a, td = _pert_setup(T, n, q, r, s)
+    rmat, l, (sb, sg) = td
+    rng = np.random.default_rng(8)
+    B = 20000
+    u = np.tile(rng.integers(0, q, (1, n), dtype=np.int64), (B, 1))  # one fixed syndrome
+    e = psf.samp_p_batch(a, td, u, seed=21).astype(np.float64)
+    sigma2 = (s * r) ** 2 / (2 * np.pi)
+    var = e.var(axis=0)
+    assert np.all(np.abs(var / sigma2 - 1) < 0.08), (var.min() / sigma2, var.max() / sigma2)
+    assert np.all(np.abs(e.mean(axis=0)) < 5 * np.sqrt(sigma2 / B) + 0.6)
+    # covariance is spherical: off-diagonal correlations vanish
+    corr = np.corrcoef(e.T)
+    off = corr - np.eye(gp.m)
+    assert np.abs(off).max() < 0.05
+    # reference sampler on the same key: compare ||e||^2 and a few coordinate variances
+    po = O.GadgetParameters.init_default(n, q)
+    rr = np.random.default_rng(9)
+    ref = np.array([O.samp_p_perturbation(rr, po, a, rmat.tolist(), l, sb.tolist(), sg, u[0].tolist(), r)
+                    for _ in range(300)], dtype=np.float64)
+    n_ref, n_gpu = (ref**2).sum(1), (e**2).sum(1)
+    se = np.sqrt(n_ref.var() / len(n_ref) + n_gpu.var() / len(n_gpu))
+    assert abs(n_ref.mean() - n_gpu.mean()) < 5 * se
+    assert abs(ref.var() / e.var() - 1) < 0.06
+
+
+def test_gadget_sampler_distribution(T):
+    """The gadget part alone: z = e[m_bar:] - p[m_bar:] is not observable, but G z' = v structure
+    is: with R = 0 the lower block of e is p_low + z; check A e = u and the conditional law of the
+    lower block's parity: for q = 2^k the first digit of each block satisfies z_0 = v_0 mod 2."""
+    # covered structurally by the preimage tests; here: many different syndromes, tiny modulus
+    n, q, r, s = 4, 16, 3.0, 30.0
+    gp, psf, a, td = _pert_setup(T, n, q, r, s, seed=5)
+    rng = np.random.default_rng(1)
+    u = rng.integers(0, q, (5000, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=2)
+    assert np.array_equal(O.f_a_classical_batch(a, e, q), u)
+    assert psf.check_domain_batch(e).all()
+
+
+# ----------------------------------------------------------------------------------
+# PSFGPV::samp_p (gpv.rs:152-161)
+# ----------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,q,s", [(5, 256, 10.0), (6, 128, 10.0), (8, 128, 90.0), (10, 127, 40.0), (24, 2**16, 60.0)])
+def test_samp_p_gpv_preimage_and_domain(T, n, q, s):
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFGPV(gp, s)
+    a, td = psf.trap_gen(seed=n)
+    sb, sg = td
+    assert not (a.astype(object).dot(sb.astype(object)) % q).any()  # basis of the kernel lattice
+    rng = np.random.default_rng(4)
+    B = 1000
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=3)
+    assert np.array_equal(O.f_a_classical_batch(a, e, q), u)
+    assert psf.check_domain_batch(e).all()
+    ds = psf.samp_d(seed=1)
+    fa = psf.f_a(a, ds)
+    pre = psf.samp_p(a, td, fa, seed=2)
+    assert psf.f_a(a, pre).tolist() == fa.tolist() and psf.check_domain(pre)
+    assert np.array_equal(e, psf.samp_p_batch(a, td, u, seed=3))
+    e_split = np.concatenate([psf.samp_p_batch(a, td, u[:300], seed=3), psf.samp_p_batch(a, td, u[300:], seed=3, first_index=300)])
+    assert np.array_equal(e, e_split)
+
+
+def test_samp_p_gpv_distribution(T):
+    """GPV08 SampleD outputs D_{Lambda_u^perp(A), s}: spherical, variance s^2/(2 pi) per coordinate;
+    compared with the oracle's restatement of the reference loop on the same key."""
+    n, q, s = 5, 32, 10.0
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFGPV(gp, s)
+    a, td = psf.trap_gen(seed=2)
+    sb, sg = td
+    rng = np.random.default_rng(6)
+    B = 20000
+    u = np.tile(rng.integers(0, q, (1, n), dtype=np.int64), (B, 1))
+    e = psf.samp_p_batch(a, td, u, seed=4).astype(np.float64)
+    sigma2 = s * s / (2 * np.pi)
+    var = e.var(axis=0)
+    assert np.all(np.abs(var / sigma2 - 1) < 0.15), (var.min() / sigma2, var.max() / sigma2)
+    rr = np.random.default_rng(1)
+    ref = np.array([O.samp_p_gpv(rr, a.tolist(), q, sb.tolist(), sg, u[0].tolist(), s) for _ in range(400)], dtype=np.float64)
+    n_ref, n_gpu = (ref**2).sum(1), (e**2).sum(1)
+    se = np.sqrt(n_ref.var() / len(n_ref) + n_gpu.var() / len(n_gpu))
+    assert abs(n_ref.mean() - n_gpu.mean()) < 5 * se
+
+
+# ----------------------------------------------------------------------------------
+# PSFGPVRing (gpv_ring.rs)
+# ----------------------------------------------------------------------------------
+
+
+def _ring_s(n):
+    return ((2 * 2 * 1.005 * np.sqrt(n) + 1) * 2) * 4  # gpv_ring.rs:296-298
+
+
+@pytest.mark.parametrize("n,q", [(64, 3329), (256, 3329), (128, 7681), (64, 2**31 - 1), (8, 1024), (5, 256), (6, 128)])
+def test_ring_f_a_bit_exact(T, n, q):
+    rng = np.random.default_rng(n)
+    gp = T.GadgetParametersRing.init_default(n, q)
+    psf = T.PSFGPVRing(gp, float(_ring_s(n)), 1.005)
+    a = rng.integers(0, q, (gp.k + 2, n), dtype=np.int64)
+    B = 40
+    sig = psf.samp_d_batch(B, seed=1)
+    u, flags = psf.f_a_batch(a, sig)
+    assert flags.all()
+    for b in range(0, B, 7):
+        assert u[b].tolist() == O.f_a_ring(a.tolist(), sig[b].tolist(), n, q)
+    # == rot^-(a) sigma (rotation_matrix.rs): first polynomial only
+    rot = np.array(O.rot_minus(a[1].tolist()), dtype=object)
+    one = np.zeros((1, gp.k + 2, n), dtype=np.int32)
+    one[0, 1] = sig[0, 1]
+    u1, _ = psf.f_a_batch(a, one)
+    assert u1[0].tolist() == [int(x) % q for x in rot.dot(sig[0, 1].astype(object))]
+    # domain edge cases (gpv_ring.rs:355-445)
+    assert psf.check_domain(np.zeros((gp.k + 2, n), dtype=np.int64))
+    assert not psf.check_domain(np.zeros((gp.k + 1, n), dtype=np.int64))
+    assert not psf.check_domain(np.zeros((gp.k + 3, n), dtype=np.int64))
+    big = np.zeros((gp.k + 2, n), dtype=np.int64)
+    big[0, 0] = round(psf.s) * (gp.k + 2) * 8
+    assert not psf.check_domain(big)
+    with pytest.raises(AssertionError):
+        psf.f_a(a, big)
+
+
+@pytest.mark.parametrize("n,q", [(6, 32), (64, 3329), (8, 2**31 - 1)])
+def test_ring_trap_gen_bit_exact(T, n, q):
+    rng = np.random.default_rng(q % 1000)
+    gp, po = T.GadgetParametersRing.init_default(n, q), O.GadgetParametersRing.init_default(n, q)
+    psf = T.PSFGPVRing(gp, float(_ring_s(n)), 1.005)
+    a_bar = rng.integers(0, q, n, dtype=np.int64)
+    r = rng.integers(-10, 11, (gp.k, n)).astype(np.int32)
+    e = rng.integers(-10, 11, (gp.k, n)).astype(np.int32)
+    got = psf.gen_trapdoor_ring_lwe(a_bar, r, e)
+    want = O.gen_trapdoor_ring_lwe(po, a_bar.tolist(), r.tolist(), e.tolist())
+    assert got.tolist() == want
+
+
+@pytest.mark.parametrize("n,q", [(5, 2**31 - 1 - 57), (6, 2**31 - 1), (8, 1024), (64, 3329)])
+def test_ring_samp_p_preimage_and_domain(T, n, q):
+    gp = T.GadgetParametersRing.init_default(n, q)
+    psf = T.PSFGPVRing(gp, float(_ring_s(n)), 1.005)
+    a, td = psf.trap_gen(seed=n)
+    rng = np.random.default_rng(1)
+    B = 200
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=9)
+    assert e.shape == (B, gp.k + 2, n)
+    for b in range(0, B, 9):
+        assert O.f_a_ring(a.tolist(), e[b].tolist(), n, q) == u[b].tolist()
+    u2, flags = psf.f_a_batch(a, e)
+    assert np.array_equal(u2, u) and flags.all()
+    ds = psf.samp_d(seed=2)
+    fa = psf.f_a(a, ds)
+    pre = psf.samp_p(a, td, fa, seed=3)
+    assert psf.f_a(a, pre).tolist() == fa.tolist() and psf.check_domain(pre)
+
+
+# ----------------------------------------------------------------------------------
+# device-resident entry points and a mid-size configuration
+# ----------------------------------------------------------------------------------
+
+
+def test_device_entry_points_and_midsize(T):
+    import torch
+    from tools_b200 import _ffi
+
+    n, q, r, s = 32, 2**24, 5.0, 120.0
+    gp, psf, a, td = _pert_setup(T, n, q, r, s, seed=3)
+    B = 3000
+    dev = torch.device("cuda:0")
+    u = torch.empty((B, n), dtype=torch.int64, device=dev)
+    assert _ffi.lib().qf_fill_uniform_modq_dev(_ffi.ptr(u.data_ptr()), u.numel(), q, 77, None) == 0
+    torch.cuda.synchronize()
+    psf._install_a(a)
+    psf._install_td(a, td)
+    e = torch.empty((B, gp.m), dtype=torch.int32, device=dev)
+    psf.ctx.call("qf_set_stream", _ffi.ptr(torch.cuda.current_stream().cuda_stream))
+    psf.ctx.call("qf_samp_p_dev", _ffi.ptr(u.data_ptr()), B, 5, 0, _ffi.ptr(e.data_ptr()))
+    uo = torch.empty((B, n), dtype=torch.int64, device=dev)
+    fl = torch.empty(B, dtype=torch.uint8, device=dev)
+    psf.ctx.call("qf_f_a_dev", _ffi.ptr(e.data_ptr()), B, _ffi.ptr(uo.data_ptr()), _ffi.ptr(fl.data_ptr()))
+    psf.ctx.call("qf_synchronize")
+    assert torch.equal(uo, u) and bool(fl.all())
+    assert np.array_equal(O.f_a_classical_batch(a, e.cpu().numpy()[:50], q), u.cpu().numpy()[:50])
+    assert (u.cpu().numpy() < q).all() and u.cpu().numpy().std() > q / 8
+    # host path gives the same preimages as the device path (same seed)
+    e_host = psf.samp_p_batch(a, td, u.cpu().numpy(), seed=5)
+    assert np.array_equal(e_host, e.cpu().numpy())
+    assert psf.ctx.launch_count() > 0

@@ -1,0 +1,1000 @@
+// C ABI (include/qfall_b200.h) and the host-side pipelines that compose the kernels.
+//
+// Data layout in HBM (everything "one row per target", row length padded to 16 elements):
+//   Domain batch   int32  B x dim          (sigma, e, samp_d)           -- caller visible
+//   Range batch    int64  B x n            (u, f_a output)              -- caller visible
+//   work matrices  fp64   Bc x ld          (exact integers or reals)    -- per chunk of Bc targets
+//   key matrices   fp64   rows x ld        W[coord][k], K-major         -- A chunks, sqrt(Sigma_2), R, S, U, Mt_P
+// A batch is processed in chunks of `chunk` targets so that the workspace is bounded;
+// the key material is resident for the lifetime of the context.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qfall_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+
+struct Dev {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    ~Dev() { release(); }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline long pad16(long x) { return (x + 15) / 16 * 16; }
+inline int bitlen_u64(unsigned long long v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+uint64_t inv_mod(uint64_t a, uint64_t q) {  // a^{-1} mod q, gcd(a,q)=1
+    i128 t = 0, nt = 1, r = q, nr = a % q;
+    while (nr != 0) {
+        i128 qu = r / nr;
+        i128 tmp = t - qu * nt; t = nt; nt = tmp;
+        tmp = r - qu * nr; r = nr; nr = tmp;
+    }
+    if (t < 0) t += q;
+    return (uint64_t)t;
+}
+uint64_t gcd_u64(uint64_t a, uint64_t b) {
+    while (b) { uint64_t t = a % b; a = b; b = t; }
+    return a;
+}
+inline uint64_t mulmod_h(uint64_t a, uint64_t b, uint64_t q) { return (uint64_t)((u128)a * b % q); }
+
+}  // namespace
+
+struct qf_ctx {
+    qf_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    long n = 0, k = 0, m_bar = 0, nk = 0, m = 0;
+    long dim = 0;        // Domain length: m (classical) or n*(k+2) (ring)
+    long ld_dim = 0, ld_n = 0, ld_nk = 0;
+    unsigned long long bound = 0;
+    double s_samp_d = 0;
+    long chunk = 0;
+
+    // classical key
+    bool has_a = false;
+    int a_nchunks = 0, a_bits = 0;
+    Dev dA[4];
+    std::vector<int64_t> hA;
+    // perturbation trapdoor
+    bool has_pert = false;
+    Dev dR, dL, dSk, dSkGso;
+    // nearest-plane engine (GPV, ring)
+    bool has_np = false;
+    int npiv = 0;
+    bool ainv_identity = false;
+    long ld_piv = 0;
+    int ainv_nchunks = 0, ainv_bits = 0;
+    Dev dPiv, dAinv[4], dMtP, dU, dS, dDg;
+    int z_nchunks = 1, z_bits = 0;
+    double zlimit = 0;
+    // ring key
+    bool has_ring = false, ring_ntt = false;
+    Dev dAhat, dTw, dAraw;
+    std::vector<int64_t> hAring;
+    // workspace
+    Dev w[12];
+    Dev dNorm, dFlag, io_a, io_b, io_c;
+
+    qf_status fail(qf_status st, const std::string& msg) {
+        err = msg;
+        return st;
+    }
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf__[256];                                                                       \
+            snprintf(buf__, sizeof buf__, "CUDA error %s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return ctx->fail(QF_ERR_CUDA, buf__);                                                  \
+        }                                                                                          \
+    } while (0)
+#define LAUNCH(call)          \
+    do {                      \
+        CK(call);             \
+        ctx->launches += 1;   \
+    } while (0)
+#define QF_TRY(call)                     \
+    do {                                 \
+        qf_status s__ = (call);          \
+        if (s__ != QF_OK) return s__;    \
+    } while (0)
+
+namespace {
+
+// largest chunk width wb such that sum_k x_k w_k stays an exact fp64 integer:
+// |partial sums| <= ||x|| * 2^wb * sqrt(K) < 2^53   (Cauchy-Schwarz)
+int exact_bits(double x_norm, long K) {
+    double b = 52.9 - std::log2(std::max(1.0, x_norm)) - 0.5 * std::log2((double)std::max(1L, K));
+    return (int)std::floor(b);
+}
+
+// Upload a non-negative integer matrix (host int64, rows x cols) as `nchunks` fp64 matrices of
+// `bits`-bit digits, each rows x ld.
+qf_status upload_chunks(qf_ctx* ctx, const int64_t* h, long rows, long cols, long ld, int nchunks, int bits, Dev* dst) {
+    std::vector<double> tmp((size_t)rows * ld, 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+        const unsigned long long mask = (bits >= 64) ? ~0ull : ((1ull << bits) - 1);
+        for (long i = 0; i < rows; ++i)
+            for (long j = 0; j < cols; ++j) {
+                unsigned long long v = (unsigned long long)h[i * cols + j];
+                tmp[(size_t)i * ld + j] = (double)((v >> (c * bits)) & mask);
+            }
+        CK(dst[c].ensure(tmp.size() * sizeof(double)));
+        CK(cudaMemcpyAsync(dst[c].p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return QF_OK;
+}
+
+template <typename T>
+qf_status upload_as_f64(qf_ctx* ctx, const T* h, long rows, long cols, long ld, Dev& dst) {
+    CK(dst.ensure((size_t)rows * ld * sizeof(double)));
+    const long rows_per = std::max(1L, (long)((64L << 20) / (ld * (long)sizeof(double))));
+    std::vector<double> tmp((size_t)rows_per * ld, 0.0);
+    for (long r0 = 0; r0 < rows; r0 += rows_per) {
+        long rr = std::min(rows_per, rows - r0);
+        for (long i = 0; i < rr; ++i)
+            for (long j = 0; j < cols; ++j) tmp[(size_t)i * ld + j] = (double)h[(r0 + i) * cols + j];
+        CK(cudaMemcpyAsync(dst.as<double>() + (size_t)r0 * ld, tmp.data(), (size_t)rr * ld * sizeof(double),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return QF_OK;
+}
+
+qf_status check_flag(qf_ctx* ctx) {
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->dFlag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h) {
+        CK(cudaMemsetAsync(ctx->dFlag.p, 0, sizeof(int), ctx->stream));
+        char buf[128];
+        snprintf(buf, sizeof buf, "internal range check tripped (flag=%d): a value left its exact-integer range", h);
+        return ctx->fail(QF_ERR_NUMERIC, buf);
+    }
+    return QF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// exact  out = X * W^t  with W given as non-negative fp64 digit matrices
+// ---------------------------------------------------------------------------
+qf_status gemm_chunks(qf_ctx* ctx, const double* X, long ldx, Dev* W, int nchunks, long ldw, double** acc, long ldacc,
+                      int B, int N, int K) {
+    for (int c = 0; c < nchunks; ++c)
+        LAUNCH(qf_launch_gemm_f64(X, ldx, W[c].as<double>(), ldw, acc[c], ldacc, B, N, K, 1.0, 0.0, 0, ctx->stream));
+    return QF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// f_a / check_domain on one chunk (classical)
+// ---------------------------------------------------------------------------
+qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uint8_t* dFlags) {
+    const long ldm = ctx->ld_dim, ldn = ctx->ld_n;
+    CK(ctx->w[0].ensure((size_t)ctx->chunk * ldm * 8));
+    CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+    double* X = ctx->w[0].as<double>();
+    LAUNCH(qf_launch_i32_to_f64(dSigma, ctx->dim, X, ldm, Bc, (int)ctx->dim, ctx->dNorm.as<unsigned long long>(),
+                                ctx->stream));
+    if (dFlags)
+        LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, dFlags, Bc, ctx->stream));
+    if (dU) {
+        double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+        CombineArgs ca{};
+        for (int c = 0; c < ctx->a_nchunks; ++c) {
+            CK(ctx->w[1 + c].ensure((size_t)ctx->chunk * ldn * 8));
+            acc[c] = ctx->w[1 + c].as<double>();
+            ca.acc[c] = acc[c];
+            ca.shift[c] = c * ctx->a_bits;
+        }
+        QF_TRY(gemm_chunks(ctx, X, ldm, ctx->dA, ctx->a_nchunks, ldm, acc, ldn, Bc, (int)ctx->n, (int)ctx->m));
+        ca.nacc = ctx->a_nchunks; ca.acc_sign = 1; ca.ldacc = ldn; ca.base = nullptr; ca.ldbase = 0; ca.q = ctx->prm.q;
+        LAUNCH(qf_launch_combine_i64(ca, dU, ctx->n, Bc, (int)ctx->n, ctx->stream));
+    }
+    return QF_OK;
+}
+
+qf_status ring_f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uint8_t* dFlags) {
+    CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+    const int npoly = (int)(ctx->k + 2);
+    int64_t* out = dU;
+    if (!out) {
+        CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
+        out = ctx->w[1].as<int64_t>();
+    }
+    if (ctx->ring_ntt)
+        LAUNCH(qf_launch_ring_f_a(dSigma, ctx->dAhat.as<uint64_t>(), out, ctx->dNorm.as<unsigned long long>(), Bc, npoly,
+                                  (int)ctx->n, ctx->prm.q, ctx->dTw.as<uint64_t>(), ctx->stream));
+    else
+        LAUNCH(qf_launch_ring_f_a_schoolbook(dSigma, ctx->dAraw.as<int64_t>(), out, ctx->dNorm.as<unsigned long long>(),
+                                             Bc, npoly, (int)ctx->n, ctx->prm.q, ctx->stream));
+    if (dFlags)
+        LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, dFlags, Bc, ctx->stream));
+    return QF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PSFPerturbation::samp_p on one chunk (mp_perturbation.rs:304-336)
+// ---------------------------------------------------------------------------
+qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
+    const long ldm = ctx->ld_dim, ldn = ctx->ld_n, ldnk = ctx->ld_nk;
+    const long C = ctx->chunk;
+    CK(ctx->w[0].ensure((size_t)C * ldm * 8));   // g, later reused
+    CK(ctx->w[1].ensure((size_t)C * ldm * 8));   // x2 = sqrt(Sigma2) g
+    CK(ctx->w[2].ensure((size_t)C * ldm * 8));   // p
+    CK(ctx->w[3].ensure((size_t)C * ldnk * 8));  // z
+    CK(ctx->w[4].ensure((size_t)C * ctx->n * 8));  // v (int64)
+    double* G = ctx->w[0].as<double>();
+    double* X2 = ctx->w[1].as<double>();
+    double* P = ctx->w[2].as<double>();
+    double* Z = ctx->w[3].as<double>();
+    int64_t* V = ctx->w[4].as<int64_t>();
+    // p <- D_{Z^m, r sqrt(Sigma_2)} : x2 = sqrt(Sigma_2) * N(0,I), p_i <- D_{Z, r, x2_i}   (:315)
+    LAUNCH(qf_launch_normal_fill(G, ldm, Bc, (int)ctx->m, seed, first, QF_STREAM_PERT_NORMAL, ctx->stream));
+    LAUNCH(qf_launch_gemm_f64(G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, 1,
+                              ctx->stream));
+    LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
+                            ctx->stream));
+    // v = u - A p   (:318)
+    {
+        double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+        CombineArgs ca{};
+        for (int c = 0; c < ctx->a_nchunks; ++c) {
+            CK(ctx->w[5 + c].ensure((size_t)C * ldn * 8));
+            acc[c] = ctx->w[5 + c].as<double>();
+            ca.acc[c] = acc[c];
+            ca.shift[c] = c * ctx->a_bits;
+        }
+        QF_TRY(gemm_chunks(ctx, P, ldm, ctx->dA, ctx->a_nchunks, ldm, acc, ldn, Bc, (int)ctx->n, (int)ctx->m));
+        ca.nacc = ctx->a_nchunks; ca.acc_sign = -1; ca.ldacc = ldn; ca.base = dUin; ca.ldbase = ctx->n; ca.q = ctx->prm.q;
+        LAUNCH(qf_launch_combine_i64(ca, V, ctx->n, Bc, (int)ctx->n, ctx->stream));
+    }
+    // z <- D_{Lambda_v^perp(G), r sqrt(b^2+1)}   (:321-326 -> :173-191)
+    const double s_g = ctx->prm.r * std::sqrt((double)(ctx->prm.base * ctx->prm.base + 1));
+    LAUNCH(qf_launch_gadget_sample(V, ctx->n, Z, ldnk, Bc, (int)ctx->n, (int)ctx->k, (int)ctx->prm.base, ctx->prm.q,
+                                   ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed, first, ctx->stream));
+    // e = p + [R; I] z   (:328-335): top block accumulates R z into p in place (exact small integers)
+    LAUNCH(qf_launch_gemm_f64(Z, ldnk, ctx->dR.as<double>(), ldnk, P, ldm, Bc, (int)ctx->m_bar, (int)ctx->nk, 1.0, 1.0, 0,
+                              ctx->stream));
+    LAUNCH(qf_launch_finalize_pert(P, ldm, Z, ldnk, dE, ctx->m, Bc, (int)ctx->m, (int)ctx->m_bar, ctx->dFlag.as<int>(),
+                                   ctx->stream));
+    return QF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// GPV / ring samp_p on one chunk: GPV08 SampleD in GSO coordinates (gpv.rs:152-161,
+// gpv_ring.rs:160-212)
+// ---------------------------------------------------------------------------
+constexpr int NP_NB = 32;
+constexpr int NP_BIG = 1024;
+
+qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
+    const long D = ctx->dim, ldD = ctx->ld_dim, ldp = ctx->ld_piv, C = ctx->chunk;
+    const int np = ctx->npiv;
+    CK(ctx->w[0].ensure((size_t)C * ldp * 8));  // u as fp64
+    CK(ctx->w[1].ensure((size_t)C * ldp * 8));  // sol_P
+    CK(ctx->w[2].ensure((size_t)C * ldD * 8));  // T
+    CK(ctx->w[3].ensure((size_t)C * ldD * 8));  // Z
+    double* Uf = ctx->w[0].as<double>();
+    double* Sol = ctx->w[1].as<double>();
+    double* T = ctx->w[2].as<double>();
+    double* Z = ctx->w[3].as<double>();
+    // particular solution on the pivot columns: sol_P = A_P^{-1} u mod q   (gpv.rs:153-156)
+    if (ctx->ainv_identity) {
+        LAUNCH(qf_launch_i64_to_f64(dUin, ctx->n, Sol, ldp, Bc, np, 1.0, ctx->stream));
+    } else {
+        LAUNCH(qf_launch_i64_to_f64(dUin, ctx->n, Uf, ldp, Bc, np, 1.0, ctx->stream));
+        double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+        CombineArgs ca{};
+        for (int c = 0; c < ctx->ainv_nchunks; ++c) {
+            CK(ctx->w[4 + c].ensure((size_t)C * ldD * 8));
+            acc[c] = ctx->w[4 + c].as<double>();
+            ca.acc[c] = acc[c];
+            ca.shift[c] = c * ctx->ainv_bits;
+        }
+        QF_TRY(gemm_chunks(ctx, Uf, ldp, ctx->dAinv, ctx->ainv_nchunks, ldp, acc, ldp, Bc, np, np));
+        ca.nacc = ctx->ainv_nchunks; ca.acc_sign = 1; ca.ldacc = ldp; ca.base = nullptr; ca.ldbase = 0; ca.q = ctx->prm.q;
+        LAUNCH(qf_launch_combine_f64(ca, Sol, ldp, Bc, np, ctx->stream));
+    }
+    // centre c = -sol in GSO coordinates: T = -(B~^t D^-1)[:,P] sol_P   (gpv.rs:158)
+    LAUNCH(qf_launch_gemm_f64(Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0, ctx->stream));
+    // randomized nearest plane, i = D-1 .. 0, blocked (gpv.rs:160)
+    const double* U = ctx->dU.as<double>();
+    for (long jb0 = ((D - 1) / NP_BIG) * NP_BIG; jb0 >= 0; jb0 -= NP_BIG) {
+        const long jb1 = std::min(D, jb0 + NP_BIG);
+        for (long j0 = ((jb1 - 1 - jb0) / NP_NB) * NP_NB + jb0; j0 >= jb0; j0 -= NP_NB) {
+            const int nbe = (int)std::min((long)NP_NB, D - j0);
+            LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(), Bc, (int)j0, NP_NB, (int)D, seed,
+                                     first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
+            if (j0 > jb0)
+                LAUNCH(qf_launch_gemm_f64(Z + j0, ldD, U + jb0 * ldD + j0, ldD, T + jb0, ldD, Bc, (int)(j0 - jb0), nbe,
+                                          -1.0, 1.0, 0, ctx->stream));
+        }
+        if (jb0 > 0)
+            LAUNCH(qf_launch_gemm_f64(Z + jb0, ldD, U + jb0, ldD, T, ldD, Bc, (int)jb0, (int)(jb1 - jb0), -1.0, 1.0, 0,
+                                      ctx->stream));
+    }
+    // e = sol + S z   (exact integers; z split into z_bits-wide balanced chunks)
+    {
+        double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+        double* zc[4] = {nullptr, nullptr, nullptr, nullptr};
+        CombineArgs ca{};
+        const int nc = ctx->z_nchunks;
+        for (int c = 0; c < nc; ++c) {
+            CK(ctx->w[4 + c].ensure((size_t)C * ldD * 8));
+            acc[c] = ctx->w[4 + c].as<double>();
+            ca.acc[c] = acc[c];
+            ca.shift[c] = c * ctx->z_bits;
+        }
+        if (nc > 1) {
+            zc[0] = T;  // T is dead now
+            for (int c = 1; c < nc; ++c) {
+                CK(ctx->w[7 + c].ensure((size_t)C * ldD * 8));
+                zc[c] = ctx->w[7 + c].as<double>();
+            }
+            LAUNCH(qf_launch_split_chunks(Z, ldD, zc, nc, ctx->z_bits, ldD, Bc, (int)D, ctx->stream));
+        } else {
+            zc[0] = Z;
+        }
+        // acc_0 starts as the particular solution scattered to its pivot columns
+        CK(cudaMemsetAsync(acc[0], 0, (size_t)Bc * ldD * 8, ctx->stream));
+        LAUNCH(qf_launch_scatter_cols_f64(Sol, ldp, ctx->dPiv.as<int>(), np, acc[0], ldD, Bc, 1.0, ctx->stream));
+        for (int c = 0; c < nc; ++c)
+            LAUNCH(qf_launch_gemm_f64(zc[c], ldD, ctx->dS.as<double>(), ldD, acc[c], ldD, Bc, (int)D, (int)D, 1.0,
+                                      c == 0 ? 1.0 : 0.0, 0, ctx->stream));
+        ca.nacc = nc; ca.acc_sign = 1; ca.ldacc = ldD; ca.base = nullptr; ca.ldbase = 0; ca.q = 0;
+        LAUNCH(qf_launch_combine_i32(ca, dE, D, Bc, (int)D, ctx->dFlag.as<int>(), ctx->stream));
+    }
+    return QF_OK;
+}
+
+// find n columns of A (n x m) that form a matrix invertible over Z_q by unit pivoting and return
+// Ainv (row k maps u to the coefficient of pivot column k):  sol[piv[k]] = sum_j Ainv[k][j] u_j
+bool find_unit_pivots(const int64_t* A, long n, long m, uint64_t q, std::vector<int>& piv, std::vector<int64_t>& Ainv) {
+    std::vector<uint64_t> T((size_t)n * n, 0);
+    for (long i = 0; i < n; ++i) T[i * n + i] = 1;
+    std::vector<char> used(n, 0);
+    std::vector<long> pivrow;
+    std::vector<uint64_t> w(n);
+    piv.clear();
+    for (long c = 0; c < m && (long)piv.size() < n; ++c) {
+        for (long i = 0; i < n; ++i) {
+            u128 acc = 0;
+            for (long j = 0; j < n; ++j) {
+                acc += (u128)T[i * n + j] * (uint64_t)A[j * m + c];
+                if ((j & 3) == 3) acc %= q;
+            }
+            w[i] = (uint64_t)(acc % q);
+        }
+        long r = -1;
+        for (long i = 0; i < n; ++i)
+            if (!used[i] && w[i] && gcd_u64(w[i], q) == 1) { r = i; break; }
+        if (r < 0) continue;
+        uint64_t inv = inv_mod(w[r], q);
+        for (long j = 0; j < n; ++j) T[r * n + j] = mulmod_h(T[r * n + j], inv, q);
+        for (long i = 0; i < n; ++i) {
+            if (i == r || w[i] == 0) continue;
+            uint64_t f = w[i];
+            for (long j = 0; j < n; ++j) {
+                uint64_t sub = mulmod_h(f, T[r * n + j], q);
+                T[i * n + j] = (T[i * n + j] + q - sub) % q;
+            }
+        }
+        used[r] = 1;
+        piv.push_back((int)c);
+        pivrow.push_back(r);
+    }
+    if ((long)piv.size() < n) return false;
+    Ainv.assign((size_t)n * n, 0);
+    for (long kk = 0; kk < n; ++kk)
+        for (long j = 0; j < n; ++j) Ainv[kk * n + j] = (int64_t)T[pivrow[kk] * n + j];
+    return true;
+}
+
+template <typename F>
+qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
+    for (int64_t b0 = 0; b0 < batch; b0 += ctx->chunk) {
+        int Bc = (int)std::min<int64_t>(ctx->chunk, batch - b0);
+        QF_TRY(f(b0, Bc));
+    }
+    return QF_OK;
+}
+
+qf_status install_a(qf_ctx* ctx, const int64_t* a) {
+    if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "qf_set_a on a ring context; use qf_ring_set_a");
+    const long n = ctx->n, m = ctx->m;
+    for (long i = 0; i < n * m; ++i)
+        if (a[i] < 0 || (uint64_t)a[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "A entry outside [0,q)");
+    ctx->hA.assign(a, a + n * m);
+    const int qbits = bitlen_u64(ctx->prm.q - 1);
+    int wb = exact_bits(std::sqrt((double)ctx->bound), m);
+    if (wb < 4) return ctx->fail(QF_ERR_UNSUPPORTED, "domain bound too large for the exact fp64 contraction");
+    wb = std::min(wb, std::max(qbits, 1));
+    int nch = (qbits + wb - 1) / wb;
+    if (nch < 1) nch = 1;
+    if (nch > 4) return ctx->fail(QF_ERR_UNSUPPORTED, "modulus needs more than 4 digit matrices at this domain bound");
+    ctx->a_bits = wb;
+    ctx->a_nchunks = nch;
+    QF_TRY(upload_chunks(ctx, a, n, m, ctx->ld_dim, nch, wb, ctx->dA));
+    ctx->has_a = true;
+    return QF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qf_version(void) { return "qfall_b200 0.1 (sm_100a)"; }
+
+qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
+    if (!p || !out) return QF_ERR_INVALID;
+    *out = nullptr;
+    if (p->n < 1 || p->k < 1 || p->base < 2 || p->q < 2 || p->q >= (1ull << 62) || !(p->s > 0)) return QF_ERR_INVALID;
+    if (p->kind < 0 || p->kind > 2) return QF_ERR_INVALID;
+    qf_ctx* ctx = new qf_ctx();
+    ctx->prm = *p;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return QF_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->n = p->n; ctx->k = p->k; ctx->m_bar = p->m_bar; ctx->nk = p->n * p->k;
+    if (p->kind == QF_PSF_GPV_RING) {
+        ctx->m = p->k + 2;
+        ctx->dim = p->n * (p->k + 2);
+    } else {
+        ctx->m = p->m_bar + ctx->nk;
+        ctx->dim = ctx->m;
+    }
+    ctx->ld_dim = pad16(ctx->dim); ctx->ld_n = pad16(ctx->n); ctx->ld_nk = pad16(ctx->nk);
+    const double r = (p->kind == QF_PSF_PERTURBATION) ? p->r : 1.0;
+    ctx->s_samp_d = p->s * r;
+    if (p->norm_bound) {
+        ctx->bound = p->norm_bound;
+    } else {
+        long double b = (long double)p->s * p->s * (long double)ctx->dim * (long double)r * r;
+        ctx->bound = (unsigned long long)floorl(b);
+    }
+    // default chunk: keep ~6 fp64 work matrices within ~12 GB
+    long per_target = ctx->ld_dim * 8 * 8;
+    long c = (long)((12LL << 30) / std::max(1L, per_target));
+    c = std::max(128L, std::min(65536L, c / 128 * 128));
+    ctx->chunk = c;
+    if (ctx->dFlag.ensure(sizeof(int)) != cudaSuccess || cudaMemset(ctx->dFlag.p, 0, sizeof(int)) != cudaSuccess) {
+        delete ctx;
+        return QF_ERR_CUDA;
+    }
+    *out = ctx;
+    return QF_OK;
+}
+
+void qf_ctx_destroy(qf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaStream_t s = ctx->own_stream;
+    delete ctx;
+    if (s) cudaStreamDestroy(s);
+}
+
+const char* qf_last_error(const qf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t qf_launch_count(const qf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+qf_status qf_set_stream(qf_ctx* ctx, void* s) {
+    if (!ctx) return QF_ERR_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return QF_OK;
+}
+qf_status qf_set_chunk(qf_ctx* ctx, int64_t c) {
+    if (!ctx || c < 0) return QF_ERR_INVALID;
+    if (c == 0) return QF_OK;
+    ctx->chunk = std::max<int64_t>(1, c);
+    return QF_OK;
+}
+qf_status qf_synchronize(qf_ctx* ctx) {
+    if (!ctx) return QF_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return check_flag(ctx);
+}
+
+qf_status qf_set_a(qf_ctx* ctx, const int64_t* a) {
+    if (!ctx || !a) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return install_a(ctx, a);
+}
+
+qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const double* l, const int64_t* sk,
+                                       const double* skg) {
+    if (!ctx || !r || !l || !sk || !skg) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");
+    CK(cudaSetDevice(ctx->device));
+    QF_TRY(upload_as_f64(ctx, r, ctx->m_bar, ctx->nk, ctx->ld_nk, ctx->dR));
+    QF_TRY(upload_as_f64(ctx, l, ctx->m, ctx->m, ctx->ld_dim, ctx->dL));
+    QF_TRY(upload_as_f64(ctx, sk, ctx->k, ctx->k, ctx->k, ctx->dSk));
+    QF_TRY(upload_as_f64(ctx, skg, ctx->k, ctx->k, ctx->k, ctx->dSkGso));
+    ctx->has_pert = true;
+    return QF_OK;
+}
+
+qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
+    if (!ctx || !s || !sg) return QF_ERR_INVALID;
+    if (ctx->prm.kind == QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a GPV context");
+    CK(cudaSetDevice(ctx->device));
+    const long D = ctx->dim, ld = ctx->ld_dim;
+    const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
+    // particular-solution map
+    std::vector<int> piv;
+    if (ring) {
+        if (!ctx->has_ring) return ctx->fail(QF_ERR_NO_KEY, "install the ring key first (qf_ring_set_a)");
+        // a_0 must be the constant polynomial 1 (gadget_ring.rs:75): then x = (u, 0, ..., 0) solves a x = u
+        if (ctx->hAring[0] != 1) return ctx->fail(QF_ERR_UNSUPPORTED, "ring key: a_0 != 1");
+        for (long i = 1; i < ctx->n; ++i)
+            if (ctx->hAring[i] != 0) return ctx->fail(QF_ERR_UNSUPPORTED, "ring key: a_0 != 1");
+        ctx->npiv = (int)ctx->n;
+        ctx->ainv_identity = true;
+        for (int i = 0; i < ctx->npiv; ++i) piv.push_back(i);
+    } else {
+        if (!ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "install A first (qf_set_a)");
+        std::vector<int64_t> ainv;
+        if (!find_unit_pivots(ctx->hA.data(), ctx->n, ctx->m, ctx->prm.q, piv, ainv))
+            return ctx->fail(QF_ERR_UNSUPPORTED, "A has no n columns invertible over Z_q by unit pivoting");
+        ctx->npiv = (int)ctx->n;
+        ctx->ainv_identity = false;
+        const int qbits = bitlen_u64(ctx->prm.q - 1);
+        int wb = exact_bits((double)ctx->prm.q * std::sqrt((double)ctx->n), ctx->n);
+        if (wb < 2) return ctx->fail(QF_ERR_UNSUPPORTED, "modulus too large for the exact particular-solution product");
+        wb = std::min(wb, qbits);
+        int nch = (qbits + wb - 1) / wb;
+        if (nch > 4) return ctx->fail(QF_ERR_UNSUPPORTED, "modulus needs more than 4 digit matrices (GPV)");
+        ctx->ainv_bits = wb; ctx->ainv_nchunks = nch;
+        ctx->ld_piv = pad16(ctx->npiv);
+        QF_TRY(upload_chunks(ctx, ainv.data(), ctx->n, ctx->n, ctx->ld_piv, nch, wb, ctx->dAinv));
+    }
+    ctx->ld_piv = pad16(ctx->npiv);
+    CK(ctx->dPiv.ensure(piv.size() * sizeof(int)));
+    CK(cudaMemcpy(ctx->dPiv.p, piv.data(), piv.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // S (row-major, S[t][j] = coordinate t of b_j) as fp64; GSO likewise
+    int64_t smax = 0;
+    for (long i = 0; i < D * D; ++i) smax = std::max<int64_t>(smax, s[i] < 0 ? -s[i] : s[i]);
+    QF_TRY(upload_as_f64(ctx, s, D, D, ld, ctx->dS));
+    Dev dG, dMt, dSt, dD;
+    QF_TRY(upload_as_f64(ctx, sg, D, D, ld, dG));
+    CK(dD.ensure((size_t)D * 8));
+    CK(dMt.ensure((size_t)D * ld * 8));
+    CK(dSt.ensure((size_t)D * ld * 8));
+    CK(ctx->dU.ensure((size_t)D * ld * 8));
+    CK(ctx->dMtP.ensure((size_t)D * ctx->ld_piv * 8));
+    CK(ctx->dDg.ensure((size_t)D * sizeof(DGaussParams)));
+    LAUNCH(qf_launch_colnorm2(dG.as<double>(), ld, (int)D, (int)D, dD.as<double>(), ctx->stream));
+    LAUNCH(qf_launch_transpose_scale(dG.as<double>(), ld, dMt.as<double>(), ld, (int)D, (int)D, dD.as<double>(), ctx->stream));
+    LAUNCH(qf_launch_transpose_scale(ctx->dS.as<double>(), ld, dSt.as<double>(), ld, (int)D, (int)D, nullptr, ctx->stream));
+    LAUNCH(qf_launch_gemm_f64(dMt.as<double>(), ld, dSt.as<double>(), ld, ctx->dU.as<double>(), ld, (int)D, (int)D, (int)D,
+                              1.0, 0.0, 0, ctx->stream));
+    LAUNCH(qf_launch_gather_cols(dMt.as<double>(), ld, ctx->dPiv.as<int>(), ctx->npiv, ctx->dMtP.as<double>(), ctx->ld_piv,
+                                 (int)D, ctx->stream));
+    LAUNCH(qf_launch_make_dg(dD.as<double>(), (int)D, ctx->prm.s, ctx->dDg.as<DGaussParams>(), ctx->stream));
+    std::vector<double> hd(D);
+    CK(cudaMemcpyAsync(hd.data(), dD.p, (size_t)D * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double dmin = hd[0], dmax = hd[0];
+    for (long i = 0; i < D; ++i) {
+        if (!(hd[i] > 0)) return ctx->fail(QF_ERR_INVALID, "GSO has a zero / non-finite column");
+        dmin = std::min(dmin, hd[i]);
+        dmax = std::max(dmax, hd[i]);
+    }
+    if (ctx->prm.s / std::sqrt(dmin) > 2.0e6)
+        return ctx->fail(QF_ERR_UNSUPPORTED, "s / min||b~_i|| exceeds the fp32 range of the integer sampler");
+    // exact e = sol + S z : z digits of z_bits bits
+    int zb = exact_bits(std::sqrt((double)D) * 0.5, D) - bitlen_u64((unsigned long long)smax) ;
+    // (||z_c|| <= 2^(zb-1) sqrt(D); rows of S bounded entrywise by smax)
+    zb = std::min(zb, 40);
+    if (zb < 4) return ctx->fail(QF_ERR_UNSUPPORTED, "basis entries too large for the exact S*z product");
+    const double z_est = 8.0 * ((double)ctx->prm.q * std::sqrt((double)ctx->npiv) + 8.0 * ctx->prm.s) / std::sqrt(dmin);
+    int nch = 1;
+    while (nch < 4 && z_est >= std::ldexp(1.0, nch * zb - 1)) ++nch;
+    ctx->z_bits = zb; ctx->z_nchunks = nch;
+    ctx->zlimit = std::min(std::ldexp(1.0, nch * zb - 1), std::ldexp(1.0, 52));
+    ctx->has_np = true;
+    return QF_OK;
+}
+
+qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a) {
+    if (!ctx || !a) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "not a ring context");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, np = ctx->k + 2;
+    for (long i = 0; i < n * np; ++i)
+        if (a[i] < 0 || (uint64_t)a[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "ring key coefficient outside [0,q)");
+    ctx->hAring.assign(a, a + n * np);
+    CK(ctx->dAraw.ensure((size_t)n * np * 8));
+    CK(cudaMemcpy(ctx->dAraw.p, a, (size_t)n * np * 8, cudaMemcpyHostToDevice));
+    ctx->ring_ntt = (n >= 64) && ((n & (n - 1)) == 0) && n <= 2048;
+    if (ctx->ring_ntt) {
+        // exactness of the integer product: npoly * n * (q/2) * max|sigma| < 2^63
+        double mag = (double)np * (double)n * ((double)ctx->prm.q / 2) * std::sqrt((double)ctx->bound);
+        if (mag >= 9.0e18) ctx->ring_ntt = false;
+    }
+    if (ctx->ring_ntt) {
+        std::vector<uint64_t> tw(2 * n + 1);
+        qf_ring_make_tables((int)n, tw.data());
+        CK(ctx->dTw.ensure(tw.size() * 8));
+        CK(cudaMemcpy(ctx->dTw.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
+        CK(ctx->dAhat.ensure((size_t)n * np * 8));
+        LAUNCH(qf_launch_ring_prepare(ctx->dAraw.as<int64_t>(), ctx->dAhat.as<uint64_t>(), (int)np, (int)n, ctx->prm.q,
+                                      ctx->dTw.as<uint64_t>(), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->has_ring = true;
+    return QF_OK;
+}
+
+qf_status qf_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int8_t* r, const int64_t* tag, int64_t* a_out) {
+    if (!ctx || !a_bar || !r || !a_out) return QF_ERR_INVALID;
+    if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "ring context: use qf_ring_trap_gen_from");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, mb = ctx->m_bar, nk = ctx->nk, m = ctx->m, k = ctx->k;
+    const uint64_t q = ctx->prm.q;
+    {
+        // base^k must reach q (find_solution_gadget_vec panics otherwise, gadget_classical.rs:170)
+        u128 pw = 1;
+        for (long i = 0; i < k && pw < q; ++i) pw *= (uint64_t)ctx->prm.base;
+        if (pw < q) return ctx->fail(QF_ERR_INVALID, "base^k < q");
+    }
+    for (long i = 0; i < n * mb; ++i)
+        if (a_bar[i] < 0 || (uint64_t)a_bar[i] >= q) return ctx->fail(QF_ERR_INVALID, "A_bar entry outside [0,q)");
+    // (A_bar R)^t = R^t A_bar^t : "targets" are the nk columns of R, key matrix is A_bar (n x m_bar)
+    const long ldmb = pad16(mb), ldn = ctx->ld_n;
+    int rmax = 1;
+    for (long i = 0; i < mb * nk; ++i) rmax = std::max(rmax, (int)std::abs((int)r[i]));
+    const int qbits = bitlen_u64(q - 1);
+    int wb = exact_bits((double)rmax * std::sqrt((double)mb), mb);
+    if (wb < 4) return ctx->fail(QF_ERR_UNSUPPORTED, "R too large for the exact A_bar*R product");
+    wb = std::min(wb, qbits);
+    int nch = (qbits + wb - 1) / wb;
+    if (nch > 4) return ctx->fail(QF_ERR_UNSUPPORTED, "modulus needs more than 4 digit matrices (TrapGen)");
+    Dev dW[4], dX, dAcc[4], dOut;
+    QF_TRY(upload_chunks(ctx, a_bar, n, mb, ldmb, nch, wb, dW));
+    {
+        std::vector<double> rt((size_t)nk * ldmb, 0.0);
+        for (long i = 0; i < mb; ++i)
+            for (long j = 0; j < nk; ++j) rt[(size_t)j * ldmb + i] = (double)r[i * nk + j];
+        CK(dX.ensure(rt.size() * 8));
+        CK(cudaMemcpy(dX.p, rt.data(), rt.size() * 8, cudaMemcpyHostToDevice));
+    }
+    double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+    CombineArgs ca{};
+    for (int c = 0; c < nch; ++c) {
+        CK(dAcc[c].ensure((size_t)nk * ldn * 8));
+        acc[c] = dAcc[c].as<double>();
+        ca.acc[c] = acc[c];
+        ca.shift[c] = c * wb;
+    }
+    QF_TRY(gemm_chunks(ctx, dX.as<double>(), ldmb, dW, nch, ldmb, acc, ldn, (int)nk, (int)n, (int)mb));
+    ca.nacc = nch; ca.acc_sign = 1; ca.ldacc = ldn; ca.base = nullptr; ca.ldbase = 0; ca.q = q;
+    CK(dOut.ensure((size_t)nk * n * 8));
+    LAUNCH(qf_launch_combine_i64(ca, dOut.as<int64_t>(), n, (int)nk, (int)n, ctx->stream));
+    std::vector<int64_t> art((size_t)nk * n);
+    CK(cudaMemcpyAsync(art.data(), dOut.p, art.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // A = [A_bar | tag*G - A_bar R]
+    std::vector<uint64_t> gpow(k);
+    {
+        u128 pw = 1;
+        for (long t = 0; t < k; ++t) { gpow[t] = (uint64_t)(pw % q); pw = pw * (uint64_t)ctx->prm.base; }
+    }
+    for (long i = 0; i < n; ++i) {
+        for (long j = 0; j < mb; ++j) a_out[i * m + j] = a_bar[i * mb + j];
+        for (long j = 0; j < nk; ++j) {
+            long blk = j / k, t = j % k;
+            uint64_t h = tag ? ((uint64_t)tag[i * n + blk] % q) : (i == blk ? 1 : 0);
+            uint64_t hg = mulmod_h(h, gpow[t], q);
+            uint64_t ar = (uint64_t)art[(size_t)j * n + i];
+            a_out[i * m + mb + j] = (int64_t)((hg + q - ar) % q);
+        }
+    }
+    return install_a(ctx, a_out);
+}
+
+qf_status qf_trap_gen(qf_ctx* ctx, uint64_t seed, int64_t* a_out, int8_t* r_out) {
+    if (!ctx || !a_out || !r_out) return QF_ERR_INVALID;
+    if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "ring context");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, mb = ctx->m_bar, nk = ctx->nk;
+    Dev dAb, dR;
+    CK(dAb.ensure((size_t)n * mb * 8));
+    CK(dR.ensure((size_t)mb * nk));
+    LAUNCH(qf_launch_uniform_modq(dAb.as<int64_t>(), n * mb, ctx->prm.q, seed, 0, ctx->stream));
+    LAUNCH(qf_launch_ternary(dR.as<int8_t>(), mb * nk, seed, ctx->stream));
+    std::vector<int64_t> ab((size_t)n * mb);
+    CK(cudaMemcpyAsync(ab.data(), dAb.p, ab.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(r_out, dR.p, (size_t)mb * nk, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return qf_trap_gen_from(ctx, ab.data(), r_out, nullptr, a_out);
+}
+
+qf_status qf_ring_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int32_t* r, const int32_t* e, int64_t* a_out) {
+    if (!ctx || !a_bar || !r || !e || !a_out) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "not a ring context");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, k = ctx->k;
+    const uint64_t q = ctx->prm.q;
+    // a_bar * r_j for j < k : the ring kernel with a one-polynomial "key" a_bar and k "targets" r_j
+    Dev dA, dAh, dTw, dR, dOut;
+    CK(dA.ensure((size_t)n * 8));
+    CK(cudaMemcpy(dA.p, a_bar, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(dR.ensure((size_t)k * n * 4));
+    CK(cudaMemcpy(dR.p, r, (size_t)k * n * 4, cudaMemcpyHostToDevice));
+    CK(dOut.ensure((size_t)k * n * 8));
+    int rmax = 1;
+    for (long i = 0; i < k * n; ++i) rmax = std::max(rmax, std::abs(r[i]));
+    bool ntt = (n >= 64) && ((n & (n - 1)) == 0) && n <= 2048 && ((double)n * ((double)q / 2) * rmax < 9.0e18);
+    if (ntt) {
+        std::vector<uint64_t> tw(2 * n + 1);
+        qf_ring_make_tables((int)n, tw.data());
+        CK(dTw.ensure(tw.size() * 8));
+        CK(cudaMemcpy(dTw.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
+        CK(dAh.ensure((size_t)n * 8));
+        LAUNCH(qf_launch_ring_prepare(dA.as<int64_t>(), dAh.as<uint64_t>(), 1, (int)n, q, dTw.as<uint64_t>(), ctx->stream));
+        LAUNCH(qf_launch_ring_f_a(dR.as<int32_t>(), dAh.as<uint64_t>(), dOut.as<int64_t>(), nullptr, (int)k, 1, (int)n, q,
+                                  dTw.as<uint64_t>(), ctx->stream));
+    } else {
+        LAUNCH(qf_launch_ring_f_a_schoolbook(dR.as<int32_t>(), dA.as<int64_t>(), dOut.as<int64_t>(), nullptr, (int)k, 1,
+                                             (int)n, q, ctx->stream));
+    }
+    std::vector<int64_t> ar((size_t)k * n);
+    CK(cudaMemcpyAsync(ar.data(), dOut.p, ar.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // A = [1 | a_bar | g^t - (a_bar r + e)]   (gadget_ring.rs:74-78)
+    for (long t = 0; t < n; ++t) {
+        a_out[t] = (t == 0) ? (int64_t)(1 % q) : 0;
+        a_out[n + t] = (int64_t)((uint64_t)a_bar[t] % q);
+    }
+    u128 pw = 1;
+    for (long j = 0; j < k; ++j) {
+        for (long t = 0; t < n; ++t) {
+            i128 v = -(i128)ar[j * n + t] - (i128)e[j * n + t];
+            if (t == 0) v += (i128)(uint64_t)(pw % q);
+            i128 mm = v % (i128)q;
+            if (mm < 0) mm += q;
+            a_out[(2 + j) * n + t] = (int64_t)mm;
+        }
+        pw = (pw * (uint64_t)ctx->prm.base) % q;
+    }
+    return qf_ring_set_a(ctx, a_out);
+}
+
+// ---- f_a / check_domain ------------------------------------------------------
+qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
+    if (!ctx || !sigma || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
+    if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
+    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) {
+        const int32_t* s = sigma + b0 * ctx->dim;
+        int64_t* u = u_out ? u_out + b0 * ctx->n : nullptr;
+        uint8_t* f = in_domain ? in_domain + b0 : nullptr;
+        return ring ? ring_f_a_chunk(ctx, s, Bc, u, f) : f_a_chunk(ctx, s, Bc, u, f);
+    });
+}
+
+qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
+    if (!ctx || !sigma || !u_out || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
+    if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
+    const long C = ctx->chunk;
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
+    CK(ctx->io_c.ensure((size_t)C));
+    std::vector<uint8_t> flags((size_t)std::max<int64_t>(batch, 1));
+    QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        CK(cudaMemcpyAsync(ctx->io_a.p, sigma + b0 * ctx->dim, (size_t)Bc * ctx->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+        QF_TRY(ring ? ring_f_a_chunk(ctx, ctx->io_a.as<int32_t>(), Bc, ctx->io_b.as<int64_t>(), ctx->io_c.as<uint8_t>())
+                    : f_a_chunk(ctx, ctx->io_a.as<int32_t>(), Bc, ctx->io_b.as<int64_t>(), ctx->io_c.as<uint8_t>()));
+        CK(cudaMemcpyAsync(u_out + b0 * ctx->n, ctx->io_b.p, (size_t)Bc * ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(flags.data() + b0, ctx->io_c.p, (size_t)Bc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    }));
+    bool all = true;
+    for (int64_t b = 0; b < batch; ++b) all = all && flags[b];
+    if (in_domain && batch) memcpy(in_domain, flags.data(), (size_t)batch);
+    if (!all) return ctx->fail(QF_ERR_NOT_IN_DOMAIN, "f_a: sigma not in the domain D_n (check_domain failed)");
+    return QF_OK;
+}
+
+qf_status qf_check_domain(qf_ctx* ctx, const int32_t* sigma, int64_t batch, uint8_t* in_domain) {
+    if (!ctx || !sigma || !in_domain || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const long C = ctx->chunk;
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    CK(ctx->io_c.ensure((size_t)C));
+    CK(ctx->w[0].ensure((size_t)C * ctx->ld_dim * 8));
+    CK(ctx->dNorm.ensure((size_t)C * 8));
+    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        CK(cudaMemcpyAsync(ctx->io_a.p, sigma + b0 * ctx->dim, (size_t)Bc * ctx->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(qf_launch_i32_to_f64(ctx->io_a.as<int32_t>(), ctx->dim, ctx->w[0].as<double>(), ctx->ld_dim, Bc, (int)ctx->dim,
+                                    ctx->dNorm.as<unsigned long long>(), ctx->stream));
+        LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, ctx->io_c.as<uint8_t>(), Bc, ctx->stream));
+        CK(cudaMemcpyAsync(in_domain + b0, ctx->io_c.p, (size_t)Bc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    });
+}
+
+// ---- samp_d ------------------------------------------------------------------
+qf_status qf_samp_d_dev(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first, int32_t* out) {
+    if (!ctx || !out || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        LAUNCH(qf_launch_dgauss(nullptr, 0, nullptr, 0, out + b0 * ctx->dim, ctx->dim, Bc, (int)ctx->dim, ctx->s_samp_d, seed,
+                                first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->stream));
+        return QF_OK;
+    });
+}
+
+qf_status qf_samp_d(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first, int32_t* out) {
+    if (!ctx || !out || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const long C = ctx->chunk;
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        LAUNCH(qf_launch_dgauss(nullptr, 0, nullptr, 0, ctx->io_a.as<int32_t>(), ctx->dim, Bc, (int)ctx->dim, ctx->s_samp_d,
+                                seed, first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->stream));
+        CK(cudaMemcpyAsync(out + b0 * ctx->dim, ctx->io_a.p, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    });
+}
+
+// ---- samp_p ------------------------------------------------------------------
+static qf_status samp_p_ready(qf_ctx* ctx) {
+    if (ctx->prm.kind == QF_PSF_PERTURBATION) {
+        if (!ctx->has_a || !ctx->has_pert) return ctx->fail(QF_ERR_NO_KEY, "PSFPerturbation: key or trapdoor missing");
+    } else {
+        if (!ctx->has_np) return ctx->fail(QF_ERR_NO_KEY, "GPV: trapdoor missing (qf_set_trapdoor_gpv)");
+    }
+    return QF_OK;
+}
+
+qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
+    if (!ctx || !u || !e_out || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    QF_TRY(samp_p_ready(ctx));
+    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        const int64_t* uu = u + b0 * ctx->n;
+        int32_t* ee = e_out + b0 * ctx->dim;
+        return ctx->prm.kind == QF_PSF_PERTURBATION ? samp_p_pert_chunk(ctx, uu, Bc, seed, first + (uint64_t)b0, ee)
+                                                    : samp_p_np_chunk(ctx, uu, Bc, seed, first + (uint64_t)b0, ee);
+    });
+}
+
+qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
+    if (!ctx || !u || !e_out || batch < 0) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    QF_TRY(samp_p_ready(ctx));
+    for (int64_t i = 0; i < batch * ctx->n; ++i)
+        if (u[i] < 0 || (uint64_t)u[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "target entry outside [0,q)");
+    const long C = ctx->chunk;
+    CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        CK(cudaMemcpyAsync(ctx->io_b.p, u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        QF_TRY(ctx->prm.kind == QF_PSF_PERTURBATION
+                   ? samp_p_pert_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, ctx->io_a.as<int32_t>())
+                   : samp_p_np_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, ctx->io_a.as<int32_t>()));
+        CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, ctx->io_a.p, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    }));
+    return check_flag(ctx);
+}
+
+// ---- compression -----------------------------------------------------------------
+static qf_status compress_any(const void* in, void* out, size_t count, uint64_t q, uint32_t d, int dev, void* stream,
+                              int dec, int wide) {
+    if ((!in || !out) && count) return QF_ERR_INVALID;
+    if (d < 1) return QF_ERR_INVALID;  // reference: assert!(d >= 1), lossy_compression_fips203.rs:91-94
+    if (count == 0) return QF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = wide ? 8 : 2;
+    auto run = [&](const void* di, void* dout) -> cudaError_t {
+        return wide ? qf_launch_compress_i64((const int64_t*)di, (int64_t*)dout, count, q, d, dec, st)
+                    : qf_launch_compress_u16((const uint16_t*)di, (uint16_t*)dout, count, (uint32_t)q, d, dec, st);
+    };
+    if (!wide && (q > 65535 || d > 16)) return QF_ERR_UNSUPPORTED;
+    if (wide && (q >= (1ull << 62) || d > 62)) return QF_ERR_UNSUPPORTED;
+    if (dev) {
+        cudaError_t e = run(in, out);
+        return e == cudaSuccess ? QF_OK : (e == cudaErrorInvalidValue ? QF_ERR_INVALID : QF_ERR_CUDA);
+    }
+    void *di = nullptr, *dout = nullptr;
+    if (cudaMalloc(&di, count * esz) != cudaSuccess) return QF_ERR_CUDA;
+    if (cudaMalloc(&dout, count * esz) != cudaSuccess) { cudaFree(di); return QF_ERR_CUDA; }
+    qf_status rc = QF_OK;
+    if (cudaMemcpyAsync(di, in, count * esz, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (rc == QF_OK) {
+        cudaError_t e = run(di, dout);
+        if (e != cudaSuccess) rc = (e == cudaErrorInvalidValue ? QF_ERR_INVALID : QF_ERR_CUDA);
+    }
+    if (rc == QF_OK && cudaMemcpyAsync(out, dout, count * esz, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == QF_OK) rc = QF_ERR_CUDA;
+    cudaFree(di);
+    cudaFree(dout);
+    return rc;
+}
+
+qf_status qf_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d, int dev, void* st) {
+    return compress_any(in, out, count, q, d, dev, st, 0, 0);
+}
+qf_status qf_decompress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d, int dev, void* st) {
+    return compress_any(in, out, count, q, d, dev, st, 1, 0);
+}
+qf_status qf_compress_i64(const int64_t* in, int64_t* out, size_t count, uint64_t q, uint32_t d, int dev, void* st) {
+    return compress_any(in, out, count, q, d, dev, st, 0, 1);
+}
+qf_status qf_decompress_i64(const int64_t* in, int64_t* out, size_t count, uint64_t q, uint32_t d, int dev, void* st) {
+    return compress_any(in, out, count, q, d, dev, st, 1, 1);
+}
+
+qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out) {
+    if (!centers || !out || !(s > 0)) return QF_ERR_INVALID;
+    if (count == 0) return QF_OK;
+    double *dc = nullptr, *dz = nullptr;
+    if (cudaMalloc(&dc, count * 8) != cudaSuccess) return QF_ERR_CUDA;
+    if (cudaMalloc(&dz, count * 8) != cudaSuccess) { cudaFree(dc); return QF_ERR_CUDA; }
+    qf_status rc = QF_OK;
+    std::vector<double> hz(count);
+    if (cudaMemcpy(dc, centers, count * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = QF_ERR_CUDA;
+    // one "target" per value so that every value owns its Philox stream
+    if (rc == QF_OK && qf_launch_dgauss(dc, 1, dz, 1, nullptr, 0, (int)count, 1, s, seed, 0, QF_STREAM_SAMP_D, nullptr) != cudaSuccess)
+        rc = QF_ERR_CUDA;
+    if (rc == QF_OK && cudaMemcpy(hz.data(), dz, count * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (rc == QF_OK)
+        for (size_t i = 0; i < count; ++i) out[i] = (int64_t)hz[i];
+    cudaFree(dc);
+    cudaFree(dz);
+    return rc;
+}
+
+qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* st) {
+    if (!out || q < 2) return QF_ERR_INVALID;
+    return qf_launch_uniform_modq(out, (long)count, q, seed, 0, (cudaStream_t)st) == cudaSuccess ? QF_OK : QF_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// FIPS 203 Compress_d / Decompress_d over a flat coefficient stream
+// (lossy_compression_fips203.rs:101-111 and :159-169).
+//
+//   compress  : y = floor((x * 2^d + floor(q/2)) / q) mod 2^d        x in [0,q)
+//   decompress: x = floor((y * q + 2^(d-1)) / 2^d)                    (written unreduced)
+//
+// HBM-streaming kernel: u16 in, u16 out (4 algorithmic bytes per coefficient),
+// 128-bit loads/stores (8 coefficients per access, 2 accesses in flight per
+// thread), grid = 148 SMs x 8 resident CTAs, no shared memory.  The division by
+// q is an exact multiply-high by ceil(2^64 / q) (numerator < 2^33, q < 2^16).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+struct CParams {
+    uint32_t q, d, half_q, mask, round;
+    unsigned long long magic;  // ceil(2^64 / q)
+};
+
+__device__ __forceinline__ uint32_t comp1(uint32_t x, const CParams& p) {
+    unsigned long long num = ((unsigned long long)x << p.d) + p.half_q;
+    return (uint32_t)__umul64hi(num, p.magic) & p.mask;
+}
+__device__ __forceinline__ uint32_t decomp1(uint32_t y, const CParams& p) {
+    return (uint32_t)(((unsigned long long)y * p.q + p.round) >> p.d);
+}
+
+template <bool DEC>
+__device__ __forceinline__ uint32_t map2(uint32_t w, const CParams& p) {
+    uint32_t lo = w & 0xffffu, hi = w >> 16;
+    if (DEC) {
+        lo = decomp1(lo, p);
+        hi = decomp1(hi, p);
+    } else {
+        lo = comp1(lo, p);
+        hi = comp1(hi, p);
+    }
+    return (lo & 0xffffu) | (hi << 16);
+}
+
+template <bool DEC>
+__global__ void __launch_bounds__(256)
+compress_u16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, size_t count, CParams p) {
+    const size_t nvec = count / 8;
+    const uint4* vin = reinterpret_cast<const uint4*>(in);
+    uint4* vout = reinterpret_cast<uint4*>(out);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {
+        uint4 a = __ldcs(vin + i), b = __ldcs(vin + i + stride);
+        a.x = map2<DEC>(a.x, p); a.y = map2<DEC>(a.y, p); a.z = map2<DEC>(a.z, p); a.w = map2<DEC>(a.w, p);
+        b.x = map2<DEC>(b.x, p); b.y = map2<DEC>(b.y, p); b.z = map2<DEC>(b.z, p); b.w = map2<DEC>(b.w, p);
+        __stcs(vout + i, a);
+        __stcs(vout + i + stride, b);
+    }
+    if (i < nvec) {
+        uint4 a = __ldcs(vin + i);
+        a.x = map2<DEC>(a.x, p); a.y = map2<DEC>(a.y, p); a.z = map2<DEC>(a.z, p); a.w = map2<DEC>(a.w, p);
+        __stcs(vout + i, a);
+    }
+    // ragged tail (count not a multiple of 8)
+    size_t t = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) out[t] = (uint16_t)(DEC ? decomp1(in[t], p) : comp1(in[t], p));
+}
+
+// General path on FLINT words (int64 in/out), any q < 2^62, 1 <= d <= 62.
+__global__ void compress_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, size_t count,
+                                    unsigned long long q, uint32_t d, int dec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned __int128 x = (unsigned __int128)(unsigned long long)in[i];
+        if (dec) {
+            unsigned __int128 v = x * q + ((unsigned __int128)1 << (d - 1));
+            out[i] = (int64_t)(unsigned long long)(v >> d);
+        } else {
+            unsigned __int128 v = (x << d) + (q >> 1);
+            unsigned __int128 y = v / q;
+            out[i] = (int64_t)((unsigned long long)y & ((d >= 64) ? ~0ull : ((1ull << d) - 1)));
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
+                                   int decompress, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if (q < 2 || q > 65535 || d < 1 || d > 16) return cudaErrorInvalidValue;
+    if ((((uintptr_t)in) & 15) || (((uintptr_t)out) & 15)) return cudaErrorMisalignedAddress;
+    CParams p;
+    p.q = q; p.d = d; p.half_q = q / 2; p.mask = (d >= 32) ? 0xffffffffu : ((1u << d) - 1);
+    p.round = 1u << (d - 1);
+    p.magic = ~0ull / q + 1;  // ceil(2^64/q) for q not a power of two; exact quotient otherwise as well
+    size_t nvec = count / 8;
+    size_t want = (nvec + 2 * 256 - 1) / (2 * 256);
+    int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    if (decompress)
+        compress_u16_kernel<true><<<grid, 256, 0, stream>>>(in, out, count, p);
+    else
+        compress_u16_kernel<false><<<grid, 256, 0, stream>>>(in, out, count, p);
+    return cudaGetLastError();
+}
+
+cudaError_t qf_launch_compress_i64(const int64_t* in, int64_t* out, size_t count, unsigned long long q, uint32_t d,
+                                   int decompress, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if (q < 2 || q >= (1ull << 62) || d < 1 || d > 62) return cudaErrorInvalidValue;
+    size_t want = (count + 255) / 256;
+    int grid = (int)(want > 148 * 16 ? 148 * 16 : want);
+    compress_i64_kernel<<<grid, 256, 0, stream>>>(in, out, count, q, d, decompress);
+    return cudaGetLastError();
+}

@@ -1,0 +1,332 @@
+// Conversion, recombination and elementwise sampler kernels.
+// All are HBM-streaming: flat grid-stride loops, lanes on the contiguous
+// (coordinate) dimension, one warp per target row where a row reduction is needed.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TPB = 256;
+
+inline int grid_for(long long work, int per_block, int max_blocks = 148 * 16) {
+    long long g = (work + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// ---- conversions -----------------------------------------------------------
+__global__ void i32_to_f64_kernel(const int32_t* __restrict__ in, long ldin, double* __restrict__ out, long ldout,
+                                  int B, int M, unsigned long long* __restrict__ norm2) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long b = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B;
+         b += (long)gridDim.x * warps_per_block) {
+        const int32_t* src = in + b * ldin;
+        double* dst = out + b * ldout;
+        unsigned long long acc = 0;
+        for (int j = lane; j < M; j += 32) {
+            int32_t v = src[j];
+            dst[j] = (double)v;
+            long long w = v;
+            acc += (unsigned long long)(w * w);
+        }
+        if (norm2) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) norm2[b] = acc;
+        }
+    }
+}
+
+__global__ void i64_to_f64_kernel(const int64_t* __restrict__ in, long ldin, double* __restrict__ out, long ldout,
+                                  int B, int M, double scale) {
+    long total = (long)B * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        out[b * ldout + j] = scale * (double)in[b * ldin + j];
+    }
+}
+
+__global__ void f64_to_i32_kernel(const double* __restrict__ in, long ldin, int32_t* __restrict__ out, long ldout,
+                                  int B, int M, int* flag) {
+    long total = (long)B * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        double v = in[b * ldin + j];
+        double r = rint(v);
+        if (r != v || fabs(r) > 2147483647.0) {
+            if (flag) atomicOr(flag, 1);
+            r = fmax(fmin(r, 2147483647.0), -2147483647.0);
+        }
+        out[b * ldout + j] = (int32_t)r;
+    }
+}
+
+__global__ void domain_flags_kernel(const unsigned long long* __restrict__ norm2, unsigned long long bound,
+                                    uint8_t* __restrict__ flags, int B) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x)
+        flags[b] = norm2[b] <= bound ? 1 : 0;
+}
+
+// ---- recombination of exact fp64 partial products --------------------------
+template <typename OutT>
+__global__ void combine_kernel(CombineArgs a, OutT* __restrict__ out, long ldout, int B, int N) {
+    long total = (long)B * N;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / N;
+        int n = (int)(i - b * N);
+        __int128 v = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < a.nacc) {
+                long long t = __double2ll_rn(a.acc[c][b * a.ldacc + n]);
+                v += ((__int128)t) << a.shift[c];
+            }
+        }
+        if (a.acc_sign < 0) v = -v;
+        if (a.base) v += (__int128)a.base[b * a.ldbase + n];
+        if (a.q) {
+            out[b * ldout + n] = (OutT)mod_i128(v, a.q);
+        } else {
+            out[b * ldout + n] = (OutT)(long long)v;
+        }
+    }
+}
+
+__global__ void combine_i32_kernel(CombineArgs a, int32_t* __restrict__ out, long ldout, int B, int N, int* flag) {
+    long total = (long)B * N;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / N;
+        int n = (int)(i - b * N);
+        __int128 v = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < a.nacc) {
+                long long t = __double2ll_rn(a.acc[c][b * a.ldacc + n]);
+                v += ((__int128)t) << a.shift[c];
+            }
+        }
+        if (a.acc_sign < 0) v = -v;
+        if (a.base) v += (__int128)a.base[b * a.ldbase + n];
+        if (v > 2147483647 || v < -2147483647) {
+            if (flag) atomicOr(flag, 1);
+            v = 0;
+        }
+        out[b * ldout + n] = (int32_t)(long long)v;
+    }
+}
+
+__global__ void finalize_pert_kernel(const double* __restrict__ P, long ldp, const double* __restrict__ Zb, long ldz,
+                                     int32_t* __restrict__ out, long ldo, int B, int M, int split, int* flag) {
+    long total = (long)B * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        double v = P[b * ldp + j];
+        if (j >= split) v += Zb[b * ldz + (j - split)];
+        double r = rint(v);
+        if (r != v || fabs(r) > 2147483647.0) {
+            if (flag) atomicOr(flag, 1);
+            r = 0;
+        }
+        out[b * ldo + j] = (int32_t)r;
+    }
+}
+
+__global__ void split_chunks_kernel(const double* __restrict__ in, long ldin, double* o0, double* o1, double* o2,
+                                    double* o3, int nchunks, int bits, long ldout, int B, int M) {
+    long total = (long)B * M;
+    const double scale = ldexp(1.0, bits), inv = ldexp(1.0, -bits);
+    double* outs[4] = {o0, o1, o2, o3};
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        double rem = in[b * ldin + j];
+        for (int c = 0; c < nchunks; ++c) {
+            if (c == nchunks - 1) {
+                outs[c][b * ldout + j] = rem;
+            } else {
+                double hi = rint(rem * inv);
+                outs[c][b * ldout + j] = rem - hi * scale;
+                rem = hi;
+            }
+        }
+    }
+}
+
+__global__ void scatter_cols_kernel(const double* __restrict__ src, long ldsrc, const int* __restrict__ cols,
+                                    int ncols, double* __restrict__ dst, long lddst, int B, double scale) {
+    long total = (long)B * ncols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / ncols;
+        int j = (int)(i - b * ncols);
+        dst[b * lddst + cols[j]] = scale * src[b * ldsrc + j];
+    }
+}
+
+// ---- samplers --------------------------------------------------------------
+__global__ void normal_fill_kernel(double* __restrict__ out, long ld, int B, int M, uint64_t seed,
+                                   uint64_t first_target, uint32_t tag) {
+    const int half = (M + 1) >> 1;
+    long total = (long)B * half;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / half;
+        int p = (int)(i - b * half);
+        Philox rng;
+        rng.init(seed, (first_target + (uint64_t)b) * (uint64_t)half + (uint64_t)p, tag);
+        float n0, n1;
+        rng.normal2(n0, n1);
+        double* row = out + b * ld;
+        row[2 * p] = (double)n0;
+        if (2 * p + 1 < M) row[2 * p + 1] = (double)n1;
+    }
+}
+
+__global__ void dgauss_kernel(const double* __restrict__ center, long ldc, double* __restrict__ out_f64, long ldo,
+                              int32_t* __restrict__ out_i32, long ldoi, int B, int M, DGaussParams dg,
+                              uint64_t seed, uint64_t first_target, uint32_t tag) {
+    long total = (long)B * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        Philox rng;
+        rng.init(seed, (first_target + (uint64_t)b) * (uint64_t)M + (uint64_t)j, tag);
+        double c = center ? center[b * ldc + j] : 0.0;
+        double z = sample_dgauss(dg, c, rng);
+        if (out_f64) out_f64[b * ldo + j] = z;
+        if (out_i32) out_i32[b * ldoi + j] = (int32_t)z;
+    }
+}
+
+__global__ void uniform_modq_kernel(int64_t* __restrict__ out, long count, unsigned long long q, uint64_t seed,
+                                    uint64_t first_index) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        Philox rng;
+        rng.init(seed, first_index + (uint64_t)i, QF_STREAM_UNIFORM);
+        uint64_t rh = ((uint64_t)rng.next() << 32) | rng.next();
+        uint64_t rl = ((uint64_t)rng.next() << 32) | rng.next();
+        // floor((rh*2^64 + rl) * q / 2^128): bias < q / 2^128
+        uint64_t hi = __umul64hi(rh, q);
+        uint64_t lo = rh * q;
+        uint64_t carry = __umul64hi(rl, q);
+        uint64_t s = lo + carry;
+        if (s < lo) hi += 1;
+        out[i] = (int64_t)hi;
+    }
+}
+
+// R = U{0,1} - U{0,1} entrywise (trapdoor_distribution.rs:82-86): P(-1)=P(1)=1/4, P(0)=1/2.
+// 16 entries per thread (one 128-bit Philox block gives 2 bits per entry for 64 entries;
+// we use one block per 16 entries to keep the counter <-> entry map trivial).
+__global__ void ternary_kernel(int8_t* __restrict__ out, long count, uint64_t seed) {
+    long groups = (count + 15) / 16;
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+        Philox rng;
+        rng.init(seed, (uint64_t)g, QF_STREAM_TERNARY);
+        uint32_t bits = rng.next();
+        long base = g * 16;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            if (base + t < count) {
+                int a = (bits >> (2 * t)) & 1, b = (bits >> (2 * t + 1)) & 1;
+                out[base + t] = (int8_t)(a - b);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_i32_to_f64(const int32_t* in, long ldin, double* out, long ldout, int B, int M,
+                                 unsigned long long* norm2, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    i32_to_f64_kernel<<<grid_for(B, TPB / 32), TPB, 0, stream>>>(in, ldin, out, ldout, B, M, norm2);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_i64_to_f64(const int64_t* in, long ldin, double* out, long ldout, int B, int M, double scale,
+                                 cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    i64_to_f64_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(in, ldin, out, ldout, B, M, scale);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_f64_to_i32(const double* in, long ldin, int32_t* out, long ldout, int B, int M, int* flag,
+                                 cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    f64_to_i32_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(in, ldin, out, ldout, B, M, flag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_domain_flags(const unsigned long long* norm2, unsigned long long bound, uint8_t* flags, int B,
+                                   cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    domain_flags_kernel<<<grid_for(B, TPB), TPB, 0, stream>>>(norm2, bound, flags, B);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_combine_i64(const CombineArgs& a, int64_t* out, long ldout, int B, int N, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    combine_kernel<int64_t><<<grid_for((long long)B * N, TPB), TPB, 0, stream>>>(a, out, ldout, B, N);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_combine_f64(const CombineArgs& a, double* out, long ldout, int B, int N, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    combine_kernel<double><<<grid_for((long long)B * N, TPB), TPB, 0, stream>>>(a, out, ldout, B, N);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_combine_i32(const CombineArgs& a, int32_t* out, long ldout, int B, int N, int* flag,
+                                  cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    combine_i32_kernel<<<grid_for((long long)B * N, TPB), TPB, 0, stream>>>(a, out, ldout, B, N, flag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_finalize_pert(const double* P, long ldp, const double* Zb, long ldz, int32_t* out, long ldo,
+                                    int B, int M, int split, int* flag, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    finalize_pert_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(P, ldp, Zb, ldz, out, ldo, B, M, split,
+                                                                            flag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_split_chunks(const double* in, long ldin, double* const* out, int nchunks, int bits, long ldout,
+                                   int B, int M, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    double* o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int c = 0; c < nchunks && c < 4; ++c) o[c] = out[c];
+    split_chunks_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(in, ldin, o[0], o[1], o[2], o[3], nchunks,
+                                                                              bits, ldout, B, M);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_scatter_cols_f64(const double* src, long ldsrc, const int* cols, int ncols, double* dst,
+                                       long lddst, int B, double scale, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    scatter_cols_kernel<<<grid_for((long long)B * ncols, TPB), TPB, 0, stream>>>(src, ldsrc, cols, ncols, dst, lddst, B,
+                                                                                scale);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t seed, uint64_t first_target,
+                                  uint32_t tag, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    normal_fill_kernel<<<grid_for((long long)B * ((M + 1) / 2), TPB), TPB, 0, stream>>>(out, ld, B, M, seed,
+                                                                                       first_target, tag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32, long ldoi,
+                             int B, int M, double s, uint64_t seed, uint64_t first_target, uint32_t tag,
+                             cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    DGaussParams dg = make_dgauss(s);
+    dgauss_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(center, ldc, out_f64, ldo, out_i32, ldoi, B, M,
+                                                                      dg, seed, first_target, tag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_uniform_modq(int64_t* out, long count, unsigned long long q, uint64_t seed,
+                                   uint64_t first_index, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    uniform_modq_kernel<<<grid_for(count, TPB), TPB, 0, stream>>>(out, count, q, seed, first_index);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    ternary_kernel<<<grid_for((count + 15) / 16, TPB), TPB, 0, stream>>>(out, count, seed);
+    return cudaGetLastError();
+}

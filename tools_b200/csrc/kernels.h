@@ -1,0 +1,105 @@
+// Internal launcher declarations (device pointers everywhere).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+// ---- gemm_f64.cu ----------------------------------------------------------
+cudaError_t qf_launch_gemm_f64(const double* X, long ldx, const double* W, long ldw, double* C, long ldc,
+                               int B, int N, int K, double alpha, double beta, int tri_lower,
+                               cudaStream_t stream);
+
+// ---- elementwise.cu -------------------------------------------------------
+// out[b][j] = (double) in[b][j]; optionally norm2[b] = sum_j in[b][j]^2 (exact, u64 saturating)
+cudaError_t qf_launch_i32_to_f64(const int32_t* in, long ldin, double* out, long ldout, int B, int M,
+                                 unsigned long long* norm2, cudaStream_t stream);
+cudaError_t qf_launch_i64_to_f64(const int64_t* in, long ldin, double* out, long ldout, int B, int M,
+                                 double scale, cudaStream_t stream);
+// out[b][j] = (int32) in[b][j]; sets *flag if a value does not fit / is not an integer
+cudaError_t qf_launch_f64_to_i32(const double* in, long ldin, int32_t* out, long ldout, int B, int M,
+                                 int* flag, cudaStream_t stream);
+// in_domain[b] = norm2[b] <= bound
+cudaError_t qf_launch_domain_flags(const unsigned long long* norm2, unsigned long long bound, uint8_t* flags,
+                                   int B, cudaStream_t stream);
+
+struct CombineArgs {
+    const double* acc[4];   // exact-integer fp64 partial products, B x N each, leading dim ldacc
+    int shift[4];           // value = sum_c acc_c * 2^shift_c
+    int nacc;
+    int acc_sign;           // +1 or -1
+    long ldacc;
+    const int64_t* base;    // optional B x N (ld ldbase): out = base + acc_sign * value
+    long ldbase;
+    unsigned long long q;   // 0: plain integer result, else reduce into [0,q)
+};
+cudaError_t qf_launch_combine_i64(const CombineArgs& a, int64_t* out, long ldout, int B, int N, cudaStream_t stream);
+cudaError_t qf_launch_combine_f64(const CombineArgs& a, double* out, long ldout, int B, int N, cudaStream_t stream);
+// int32 output; sets *flag when a value does not fit
+cudaError_t qf_launch_combine_i32(const CombineArgs& a, int32_t* out, long ldout, int B, int N, int* flag,
+                                  cudaStream_t stream);
+// out[b][j] = (int32)(P[b][j] + (j >= split ? Zb[b][j-split] : 0))   (e = p + [R;I] z, lower part)
+cudaError_t qf_launch_finalize_pert(const double* P, long ldp, const double* Zb, long ldz, int32_t* out, long ldo,
+                                    int B, int M, int split, int* flag, cudaStream_t stream);
+
+// split an exact-integer fp64 matrix into balanced chunks of `bits` bits: in = sum_c out_c * 2^(c*bits)
+cudaError_t qf_launch_split_chunks(const double* in, long ldin, double* const* out, int nchunks, int bits,
+                                   long ldout, int B, int M, cudaStream_t stream);
+// dst[b][cols[j]] = src[b][j]  (dst pre-zeroed by the caller)
+cudaError_t qf_launch_scatter_cols_f64(const double* src, long ldsrc, const int* cols, int ncols, double* dst,
+                                       long lddst, int B, double scale, cudaStream_t stream);
+
+// ---- samplers (elementwise.cu) -------------------------------------------
+cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t seed, uint64_t first_target,
+                                  uint32_t tag, cudaStream_t stream);
+// out[b][j] <- D_{Z, s, center[b][j]} (center == nullptr: centred at 0)
+cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32,
+                             long ldoi, int B, int M, double s, uint64_t seed, uint64_t first_target,
+                             uint32_t tag, cudaStream_t stream);
+cudaError_t qf_launch_uniform_modq(int64_t* out, long count, unsigned long long q, uint64_t seed,
+                                   uint64_t first_index, cudaStream_t stream);
+cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream_t stream);
+
+// ---- lattice.cu -------------------------------------------------------------
+// Gadget-lattice preimage (mp_perturbation.rs:173-191) for every (target, row):
+// V: B x n residues, Z: B x (n*k) exact-integer doubles.
+// sk: k x k block basis (row-major), gso: k x k GSO (columns are b~_i), both in device memory.
+cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long ldz, int B, int n, int k,
+                                    int base, unsigned long long q, const double* sk, const double* gso,
+                                    double s_g, uint64_t seed, uint64_t first_target, cudaStream_t stream);
+// One diagonal block of the randomized nearest-plane recursion in GSO coordinates:
+// for i = j0+nb-1 .. j0:  c' = T[b][i] - sum_{j>i in block} U[i][j] z_j ;  z_i <- D_{Z, s/||b~_i||, c'}
+// writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).
+// *flag is set when |z| >= zlimit (exact-integer range check).
+cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
+                              const DGaussParams* dg, int B, int j0, int nb, int dim, uint64_t seed,
+                              uint64_t first_target, double zlimit, int* flag, cudaStream_t stream);
+
+// ---- compress.cu -----------------------------------------------------------
+cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
+                                   int decompress, cudaStream_t stream);
+cudaError_t qf_launch_compress_i64(const int64_t* in, int64_t* out, size_t count, unsigned long long q,
+                                   uint32_t d, int decompress, cudaStream_t stream);
+
+// ---- ring_ntt.cu -----------------------------------------------------------
+// Negacyclic products over Z_q[X]/(X^n+1) through an exact NTT over the Goldilocks prime.
+// a_hat: npoly x n precomputed transforms of the key polynomials (centred lift of a mod q).
+// tw: device table of 2n+1 words (psi powers bit-reversed, inverse powers, 1/n) from qf_ring_make_tables.
+void qf_ring_make_tables(int n, uint64_t* host_out);
+cudaError_t qf_launch_ring_prepare(const int64_t* a, uint64_t* a_hat, int npoly, int n, unsigned long long q,
+                                   const uint64_t* tw, cudaStream_t stream);
+// out[b] = sum_j a_j * sigma[b][j] mod (X^n+1, q);  sigma: B x npoly x n (int32), out: B x n
+cudaError_t qf_launch_ring_f_a(const int32_t* sigma, const uint64_t* a_hat, int64_t* out, unsigned long long* norm2,
+                               int B, int npoly, int n, unsigned long long q, const uint64_t* tw,
+                               cudaStream_t stream);
+// Schoolbook fallback for degrees that are not a power of two (or < 64): a is the raw key, npoly x n in [0,q).
+cudaError_t qf_launch_ring_f_a_schoolbook(const int32_t* sigma, const int64_t* a, int64_t* out,
+                                          unsigned long long* norm2, int B, int npoly, int n, unsigned long long q,
+                                          cudaStream_t stream);
+
+// ---- setup.cu (per-key, not per-target) --------------------------------------
+cudaError_t qf_launch_colnorm2(const double* G, long ld, int rows, int cols, double* d, cudaStream_t stream);
+cudaError_t qf_launch_transpose_scale(const double* in, long ldin, double* out, long ldout, int rows, int cols,
+                                      const double* scale, cudaStream_t stream);
+cudaError_t qf_launch_gather_cols(const double* in, long ldin, const int* cols, int ncols, double* out, long ldout,
+                                  int rows, cudaStream_t stream);
+cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams* dg, cudaStream_t stream);
