@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- samp_p preimages/s (+ f_a evals/s) of the B200 backend on BASELINE.json configs[1]:
+PSFGPV, n = 256, q = 2^24, classical gadget, synthetic targets (the 1M-target workload is
+consumed in steps of --batch targets per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, q, description)
+    "c2": (256, 2**24, "C2 PSFGPV n=256 q=2^24 classical gadget (m=12352), uniform synthetic targets"),
+    "c2small": (64, 2**24, "reduced PSFGPV n=64 q=2^24 (m=3108) -- smoke-size variant, not the headline"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def gpv_s(gp):
+    # s = ceil((sqrt(m_bar)+1) * sqrt(5) * log2 n)   (bound from short_basis_classical.rs:233-235)
+    return float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(gp.n)))
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.cmd = ["nvidia-smi", f"--id={gpu_index}",
+                    "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                    "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                    "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"]
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def exact_abar_r(a_bar, r, q):
+    """(A_bar R) mod q in float64 BLAS, exact: A_bar split into 12-bit limbs."""
+    rf = r.astype(np.float64)
+    acc = np.zeros((a_bar.shape[0], r.shape[1]), dtype=object)
+    shift = 0
+    rem = a_bar.astype(np.int64)
+    while rem.any():
+        limb = (rem & 0xFFF).astype(np.float64)
+        part = np.rint(limb @ rf).astype(np.int64)
+        acc = (acc + (part.astype(object) << shift)) % q
+        rem >>= 12
+        shift += 12
+    return acc.astype(np.int64)
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's own algorithm (oracle/oracle_c.c,
+    the reference crate cannot be built in this image) on all host threads, on a bounded sample
+    of the same workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle_c as OC
+    from tools_b200 import gadget, linalg  # host-side numpy key setup only (untimed)
+
+    n, q, desc = WORKLOADS[args.workload]
+    gp = gadget.GadgetParameters.init_default(n, q)
+    s = gpv_s(gp)
+    rng = np.random.default_rng(2)
+    t0 = time.time()
+    a_bar = rng.integers(0, q, (n, gp.m_bar), dtype=np.int64)
+    r = (rng.integers(0, 2, (gp.m_bar, n * gp.k)) - rng.integers(0, 2, (gp.m_bar, n * gp.k))).astype(np.int8)
+    ar = exact_abar_r(a_bar, r, q)
+    g = np.zeros((n, n * gp.k), dtype=np.int64)
+    for j in range(n):
+        g[j, j * gp.k:(j + 1) * gp.k] = [(2**t) % q for t in range(gp.k)]
+    a = np.concatenate([a_bar, (g - ar) % q], axis=1)
+    basis = gadget.gen_short_basis_for_trapdoor(gp, a, r)
+    gso = np.linalg.qr(basis.astype(np.float64))
+    gso = gso[0] * np.diag(gso[1])[None, :]
+    piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
+    log(f"[reference] key setup {time.time() - t0:.1f}s (untimed)")
+    threads = OC.threads()
+    per_step = max(threads, args.ref_targets or threads)
+    bt = np.ascontiguousarray(basis.astype(np.float64).T)
+    gt = np.ascontiguousarray(gso.T)
+    import ctypes as C
+
+    lib = OC.lib()
+
+    def step(seed):
+        u = rng.integers(0, q, (per_step, n), dtype=np.int64)
+        e = np.empty((per_step, gp.m), dtype=np.int32)
+        lib.orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
+                           C.c_void_p(ainv.ctypes.data), C.c_long(len(piv)), C.c_void_p(u.ctypes.data),
+                           C.c_void_p(e.ctypes.data), C.c_long(per_step), C.c_long(n), C.c_long(gp.m), C.c_uint64(q),
+                           C.c_double(s), C.c_uint64(seed), C.c_int(threads))
+        return u, e
+
+    for w in range(args.warmup):
+        step(w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        u, e = step(100 + k)
+    dt = time.perf_counter() - t0
+    # the timed output is a valid preimage set
+    from oracle import qfall_oracle as O
+
+    assert np.array_equal(O.f_a_classical_batch(a, e[:2], q), u[:2])
+    val = args.steps * per_step / dt
+    line = {
+        "impl": "reference", "metric": "samp_p_preimages_per_s", "value": val, "unit": "preimages/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "targets_per_step": per_step, "s": s},
+        "cpu_baseline": {"value": val, "unit": "preimages/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} targets/step x {args.steps} steps, one independent instance per thread; "
+                                   "reference loop structure in fp64 (gpv.rs:152-161) with the per-call Gaussian "
+                                   "elimination hoisted out"},
+        "e2e": {"value": val, "unit": "preimages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=0, help="targets per step per GPU (0 = workload default)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-targets", type=int, default=0, help="reference arm: targets per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import tools_b200 as T
+    from tools_b200 import _ffi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, q, desc = WORKLOADS[args.workload]
+    gp = T.GadgetParameters.init_default(n, q)
+    s = gpv_s(gp)
+    batch = args.batch or (32768 if args.workload == "c2" else 65536)
+    t0 = time.time()
+    psf = T.PSFGPV(gp, s, device=local)
+    a, td = psf.trap_gen(seed=2)  # same seed on every rank: the key is replicated, not communicated
+    psf._install_a(a)
+    psf._install_td(a, td)
+    ctx = psf.ctx
+    log(f"[rank {rank}] key setup {time.time() - t0:.1f}s  m={gp.m} s={s} batch/step/gpu={batch}")
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.call("qf_set_stream", _ffi.ptr(stream))
+    lib = _ffi.lib()
+
+    total_steps = args.warmup + args.steps
+    u = torch.empty((batch, n), dtype=torch.int64, device=dev)
+    e = torch.empty((batch, gp.m), dtype=torch.int32, device=dev)
+
+    def fill_targets(step_idx):
+        # Philox-seeded uniform targets, distinct per (rank, step)
+        st = lib.qf_fill_uniform_modq_dev(_ffi.ptr(u.data_ptr()), u.numel(), q, 1000 + rank * 100003 + step_idx,
+                                          _ffi.ptr(stream))
+        assert st == 0
+
+    def step(step_idx):
+        first = (rank * total_steps + step_idx) * batch
+        ctx.call("qf_samp_p_dev", _ffi.ptr(u.data_ptr()), batch, 2, first, _ffi.ptr(e.data_ptr()))
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for w in range(args.warmup):
+        fill_targets(w)
+        step(w)
+    ctx.call("qf_synchronize")
+    fill_targets(args.warmup)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ctx.call("qf_profile", 1)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    gms, gfl, gln = _ffi.C.c_double(), _ffi.C.c_double(), _ffi.C.c_uint64()
+    ctx.call("qf_profile_read", _ffi.C.byref(gms), _ffi.C.byref(gfl), _ffi.C.byref(gln))
+    ctx.call("qf_profile", 0)
+    clock_info = clocks.stop() if rank == 0 else None
+    ctx.call("qf_synchronize")
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * batch / (ms * 1e-3)
+
+    # correctness of what was just timed: A e = u for the last step (oracle-free, through f_a_dev)
+    uo = torch.empty_like(u)
+    fl = torch.empty(batch, dtype=torch.uint8, device=dev)
+    ctx.call("qf_f_a_dev", _ffi.ptr(e.data_ptr()), batch, _ffi.ptr(uo.data_ptr()), _ffi.ptr(fl.data_ptr()))
+    ctx.call("qf_synchronize")
+    assert torch.equal(uo, u), "A e != u in the timed output"
+    assert bool(fl.all()), "a timed preimage fails check_domain"
+
+    # ---- f_a evals/s (device resident; sigma = the preimages, in domain) ---------------------------------
+    for _ in range(3):
+        ctx.call("qf_f_a_dev", _ffi.ptr(e.data_ptr()), batch, _ffi.ptr(uo.data_ptr()), _ffi.ptr(fl.data_ptr()))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    fa_steps = max(args.steps, 4)
+    for _ in range(fa_steps):
+        ctx.call("qf_f_a_dev", _ffi.ptr(e.data_ptr()), batch, _ffi.ptr(uo.data_ptr()), _ffi.ptr(fl.data_ptr()))
+    f1.record()
+    barrier()
+    fa_ms = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([fa_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fa_ms = float(t.item())
+    fa_value = world * fa_steps * batch / (fa_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ----------------
+    e2e_batch = batch
+    hu = torch.empty((e2e_batch, n), dtype=torch.int64).pin_memory()
+    he = torch.empty((e2e_batch, gp.m), dtype=torch.int32).pin_memory()
+    hu.copy_(u.cpu())
+    hu_np, he_np = hu.numpy(), he.numpy()
+
+    def e2e_step(i):
+        ctx.call("qf_samp_p", _ffi.ptr(hu_np), e2e_batch, 2, (rank * 1000 + i) * e2e_batch, _ffi.ptr(he_np))
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 4))
+    for i in range(e2e_steps):
+        e2e_step(1 + i)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = world * e2e_steps * e2e_batch / e2e_dt
+    assert np.array_equal(he_np[:4].astype(np.int64) @ a.T % q, hu_np[:4])
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (gemm_f64: fp64 tensor-pipe DMMA) -------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # MEASURED_PEAKS.json has no fp64 entry: measure the cuBLAS DGEMM burst the same way the driver
+    # measured bf16 (torch.matmul 8192^3, best of 5) and use it as the denominator.
+    x = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    y = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    best = 1e9
+    for _ in range(6):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        torch.matmul(x, y)
+        p1.record()
+        torch.cuda.synchronize()
+        best = min(best, p0.elapsed_time(p1))
+    dgemm_tf = 2 * 8192**3 / (best * 1e-3) / 1e12
+    del x, y
+    achieved = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else None
+    roofline = {
+        "kernel": "gemm_f64_kernel (mma.sync.m8n8k4.f64, fp64 tensor pipe)",
+        "bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
+        "frac": (achieved / dgemm_tf) if achieved else None, "traffic": None,
+        "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json holds only bf16 "
+                       f"{peaks.get('bf16_tflops')} TF/s and HBM {peaks.get('hbm_gbs')} GB/s); nominal fp64 is ~37 TF/s",
+        "kernel_ms_per_step": gms.value / args.steps, "kernel_share_of_step": gms.value / ms,
+        "launches": int(gln.value),
+    }
+
+    # ---- CPU baseline: the oracle's C restatement on a bounded sample ----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle_c as OC
+
+            threads = OC.threads()
+            sample = threads  # one target per thread: ~ one pass over the 2.4 GB of basis + GSO each
+            sb, sg = td
+            t1 = time.time()
+            piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
+            us = hu_np[:sample]
+            tc = time.perf_counter()
+            ec = OC.samp_p_gpv(sb, sg, piv, ainv, us, q, s, 1, threads)
+            dtc = time.perf_counter() - tc
+            assert np.array_equal(ec[:2].astype(np.int64) @ a.T % q, us[:2])
+            cpu = {"value": sample / dtc, "unit": "preimages/s", "cores": threads, "kind": "port",
+                   "sample": f"{sample} targets of the same workload, one per host thread ({dtc:.1f}s); reference "
+                             "loop structure in fp64 with the per-call Gaussian elimination hoisted out "
+                             f"(setup {tc - t1:.1f}s untimed, transposes included in the timed call)"}
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = {"value": None, "error": repr(ex)}
+
+    line = {
+        "metric": "samp_p_preimages_per_s", "value": value, "unit": "preimages/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "targets_per_step_per_gpu": batch, "total_targets_timed": world * args.steps * batch,
+                   "s": s, "l2": "per-step working set (T, Z: batch x m fp64 = %.1f GB each) exceeds L2" % (batch * gp.m * 8 / 1e9),
+                   "sharding": "targets split across ranks, key replicated, no collective on the data path"},
+        "e2e": {"value": e2e_value, "unit": "preimages/s", "h2d_bytes_per_step": e2e_batch * n * 8,
+                "d2h_bytes_per_step": e2e_batch * gp.m * 4, "steps": e2e_steps},
+        "f_a": {"value": fa_value, "unit": "evals/s", "ms_per_step": fa_ms / fa_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clock_info,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

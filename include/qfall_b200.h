@@ -79,6 +79,12 @@ qf_status qf_synchronize(qf_ctx* ctx);
 /* number of kernels this context has launched so far */
 uint64_t qf_launch_count(const qf_ctx* ctx);
 
+/* Per-launch CUDA-event timing of the dominant kernel (the fp64 tensor contraction) on the
+ * context's stream.  qf_profile_read synchronises, returns the summed kernel time, the
+ * algorithmic flops those launches performed and their count, and resets the counters. */
+qf_status qf_profile(qf_ctx* ctx, int enable);
+qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches);
+
 /* ---- key material -------------------------------------------------------- */
 /* A: n x m residues (PSFGPV / PSFPerturbation `A`, gpv.rs:60, mp_perturbation.rs:194) */
 qf_status qf_set_a(qf_ctx* ctx, const int64_t* a);

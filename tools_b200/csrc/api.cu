@@ -107,6 +107,11 @@ struct qf_ctx {
     // workspace
     Dev w[12];
     Dev dNorm, dFlag, io_a, io_b, io_c;
+    // optional per-launch timing of the dominant kernel (gemm_f64), CUDA events on ctx->stream
+    bool prof = false;
+    struct ProfRec { cudaEvent_t a, b; double flops; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
 
     qf_status fail(qf_status st, const std::string& msg) {
         err = msg;
@@ -190,13 +195,33 @@ qf_status check_flag(qf_ctx* ctx) {
     return QF_OK;
 }
 
+// gemm_f64 launch with optional event timing (algorithmic flops: 2 B N K, triangular: B N (N+1))
+cudaError_t ctx_gemm(qf_ctx* ctx, const double* X, long ldx, const double* W, long ldw, double* C, long ldc, int B, int N,
+                     int K, double alpha, double beta, int tri) {
+    qf_ctx::ProfRec rec{};
+    if (ctx->prof) {
+        for (cudaEvent_t* e : {&rec.a, &rec.b}) {
+            if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) return cudaErrorUnknown;
+        }
+        rec.flops = tri ? (double)B * N * (double)(std::min(N, K) + 1) : 2.0 * B * (double)N * K;
+        cudaEventRecord(rec.a, ctx->stream);
+    }
+    cudaError_t e = qf_launch_gemm_f64(X, ldx, W, ldw, C, ldc, B, N, K, alpha, beta, tri, ctx->stream);
+    if (ctx->prof) {
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof_recs.push_back(rec);
+    }
+    return e;
+}
+
 // ---------------------------------------------------------------------------
 // exact  out = X * W^t  with W given as non-negative fp64 digit matrices
 // ---------------------------------------------------------------------------
 qf_status gemm_chunks(qf_ctx* ctx, const double* X, long ldx, Dev* W, int nchunks, long ldw, double** acc, long ldacc,
                       int B, int N, int K) {
     for (int c = 0; c < nchunks; ++c)
-        LAUNCH(qf_launch_gemm_f64(X, ldx, W[c].as<double>(), ldw, acc[c], ldacc, B, N, K, 1.0, 0.0, 0, ctx->stream));
+        LAUNCH(ctx_gemm(ctx, X, ldx, W[c].as<double>(), ldw, acc[c], ldacc, B, N, K, 1.0, 0.0, 0));
     return QF_OK;
 }
 
@@ -265,8 +290,7 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     int64_t* V = ctx->w[4].as<int64_t>();
     // p <- D_{Z^m, r sqrt(Sigma_2)} : x2 = sqrt(Sigma_2) * N(0,I), p_i <- D_{Z, r, x2_i}   (:315)
     LAUNCH(qf_launch_normal_fill(G, ldm, Bc, (int)ctx->m, seed, first, QF_STREAM_PERT_NORMAL, ctx->stream));
-    LAUNCH(qf_launch_gemm_f64(G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, 1,
-                              ctx->stream));
+    LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, 1));
     LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
                             ctx->stream));
     // v = u - A p   (:318)
@@ -288,8 +312,7 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     LAUNCH(qf_launch_gadget_sample(V, ctx->n, Z, ldnk, Bc, (int)ctx->n, (int)ctx->k, (int)ctx->prm.base, ctx->prm.q,
                                    ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed, first, ctx->stream));
     // e = p + [R; I] z   (:328-335): top block accumulates R z into p in place (exact small integers)
-    LAUNCH(qf_launch_gemm_f64(Z, ldnk, ctx->dR.as<double>(), ldnk, P, ldm, Bc, (int)ctx->m_bar, (int)ctx->nk, 1.0, 1.0, 0,
-                              ctx->stream));
+    LAUNCH(ctx_gemm(ctx, Z, ldnk, ctx->dR.as<double>(), ldnk, P, ldm, Bc, (int)ctx->m_bar, (int)ctx->nk, 1.0, 1.0, 0));
     LAUNCH(qf_launch_finalize_pert(P, ldm, Z, ldnk, dE, ctx->m, Bc, (int)ctx->m, (int)ctx->m_bar, ctx->dFlag.as<int>(),
                                    ctx->stream));
     return QF_OK;
@@ -331,7 +354,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         LAUNCH(qf_launch_combine_f64(ca, Sol, ldp, Bc, np, ctx->stream));
     }
     // centre c = -sol in GSO coordinates: T = -(B~^t D^-1)[:,P] sol_P   (gpv.rs:158)
-    LAUNCH(qf_launch_gemm_f64(Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0, ctx->stream));
+    LAUNCH(ctx_gemm(ctx, Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0));
     // randomized nearest plane, i = D-1 .. 0, blocked (gpv.rs:160)
     const double* U = ctx->dU.as<double>();
     for (long jb0 = ((D - 1) / NP_BIG) * NP_BIG; jb0 >= 0; jb0 -= NP_BIG) {
@@ -341,12 +364,11 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
             LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(), Bc, (int)j0, NP_NB, (int)D, seed,
                                      first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
             if (j0 > jb0)
-                LAUNCH(qf_launch_gemm_f64(Z + j0, ldD, U + jb0 * ldD + j0, ldD, T + jb0, ldD, Bc, (int)(j0 - jb0), nbe,
-                                          -1.0, 1.0, 0, ctx->stream));
+                LAUNCH(ctx_gemm(ctx, Z + j0, ldD, U + jb0 * ldD + j0, ldD, T + jb0, ldD, Bc, (int)(j0 - jb0), nbe,
+                                          -1.0, 1.0, 0));
         }
         if (jb0 > 0)
-            LAUNCH(qf_launch_gemm_f64(Z + jb0, ldD, U + jb0, ldD, T, ldD, Bc, (int)jb0, (int)(jb1 - jb0), -1.0, 1.0, 0,
-                                      ctx->stream));
+            LAUNCH(ctx_gemm(ctx, Z + jb0, ldD, U + jb0, ldD, T, ldD, Bc, (int)jb0, (int)(jb1 - jb0), -1.0, 1.0, 0));
     }
     // e = sol + S z   (exact integers; z split into z_bits-wide balanced chunks)
     {
@@ -374,8 +396,8 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(cudaMemsetAsync(acc[0], 0, (size_t)Bc * ldD * 8, ctx->stream));
         LAUNCH(qf_launch_scatter_cols_f64(Sol, ldp, ctx->dPiv.as<int>(), np, acc[0], ldD, Bc, 1.0, ctx->stream));
         for (int c = 0; c < nc; ++c)
-            LAUNCH(qf_launch_gemm_f64(zc[c], ldD, ctx->dS.as<double>(), ldD, acc[c], ldD, Bc, (int)D, (int)D, 1.0,
-                                      c == 0 ? 1.0 : 0.0, 0, ctx->stream));
+            LAUNCH(ctx_gemm(ctx, zc[c], ldD, ctx->dS.as<double>(), ldD, acc[c], ldD, Bc, (int)D, (int)D, 1.0,
+                                      c == 0 ? 1.0 : 0.0, 0));
         ca.nacc = nc; ca.acc_sign = 1; ca.ldacc = ldD; ca.base = nullptr; ca.ldbase = 0; ca.q = 0;
         LAUNCH(qf_launch_combine_i32(ca, dE, D, Bc, (int)D, ctx->dFlag.as<int>(), ctx->stream));
     }
@@ -532,6 +554,31 @@ qf_status qf_synchronize(qf_ctx* ctx) {
     return check_flag(ctx);
 }
 
+qf_status qf_profile(qf_ctx* ctx, int enable) {
+    if (!ctx) return QF_ERR_INVALID;
+    ctx->prof = enable != 0;
+    return QF_OK;
+}
+
+qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches) {
+    if (!ctx) return QF_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    double ms = 0, fl = 0;
+    for (auto& r : ctx->prof_recs) {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms += t;
+        fl += r.flops;
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = fl;
+    if (gemm_launches) *gemm_launches = ctx->prof_recs.size();
+    ctx->prof_recs.clear();
+    return QF_OK;
+}
+
 qf_status qf_set_a(qf_ctx* ctx, const int64_t* a) {
     if (!ctx || !a) return QF_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -603,8 +650,8 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     LAUNCH(qf_launch_colnorm2(dG.as<double>(), ld, (int)D, (int)D, dD.as<double>(), ctx->stream));
     LAUNCH(qf_launch_transpose_scale(dG.as<double>(), ld, dMt.as<double>(), ld, (int)D, (int)D, dD.as<double>(), ctx->stream));
     LAUNCH(qf_launch_transpose_scale(ctx->dS.as<double>(), ld, dSt.as<double>(), ld, (int)D, (int)D, nullptr, ctx->stream));
-    LAUNCH(qf_launch_gemm_f64(dMt.as<double>(), ld, dSt.as<double>(), ld, ctx->dU.as<double>(), ld, (int)D, (int)D, (int)D,
-                              1.0, 0.0, 0, ctx->stream));
+    LAUNCH(ctx_gemm(ctx, dMt.as<double>(), ld, dSt.as<double>(), ld, ctx->dU.as<double>(), ld, (int)D, (int)D, (int)D,
+                              1.0, 0.0, 0));
     LAUNCH(qf_launch_gather_cols(dMt.as<double>(), ld, ctx->dPiv.as<int>(), ctx->npiv, ctx->dMtP.as<double>(), ctx->ld_piv,
                                  (int)D, ctx->stream));
     LAUNCH(qf_launch_make_dg(dD.as<double>(), (int)D, ctx->prm.s, ctx->dDg.as<DGaussParams>(), ctx->stream));
