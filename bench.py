@@ -216,7 +216,11 @@ def main():
     psf._install_td(a, td)
     ctx = psf.ctx
     log(f"[rank {rank}] key setup {time.time() - t0:.1f}s  m={gp.m} s={s} batch/step/gpu={batch}")
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream shared by torch's events and the library's launches
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx.call("qf_set_stream", _ffi.ptr(stream))
     lib = _ffi.lib()
 
@@ -359,7 +363,7 @@ def main():
             threads = OC.threads()
             sample = threads  # one target per thread: ~ one pass over the 2.4 GB of basis + GSO each
             sb, sg = td
-            t1 = time.time()
+            t1 = time.perf_counter()
             piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
             us = hu_np[:sample]
             tc = time.perf_counter()

@@ -149,6 +149,12 @@ qf_status qf_decompress_i64(const int64_t* in, int64_t* out, size_t count, uint6
  * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers. */
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out);
 
+/* ---- self-test of the tensor-core integer contraction: out = X W^t (mod q if q != 0), exact.
+ * x: B x K signed with |x| < 2^(8 LX - 1); w: N x K, residues < 2^(8 LW) (w_signed = 0) or signed
+ * |w| < 2^(8 LW - 1) (w_signed = 1).  Host pointers. */
+qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int LX, int LW, int64_t B, int64_t N,
+                           int64_t K, uint64_t q, int64_t* out);
+
 /* ---- synthetic inputs for benchmarks (Philox, on device) -------------------------------- */
 qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* cuda_stream);
 

@@ -1039,6 +1039,57 @@ qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t se
     return rc;
 }
 
+// Debug / self-test entry: exact V = X W^t through the tcgen05 int8 path, host buffers.
+// x: B x K signed (|x| < 2^(8 LX - 1)), w: N x K (residues < 2^(8 LW) if !w_signed, else |w| < 2^(8 LW - 1)).
+qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int LX, int LW, int64_t B, int64_t N,
+                           int64_t K, uint64_t q, int64_t* out) {
+    if (!x || !w || !out || B < 1 || N < 1 || K < 1) return QF_ERR_INVALID;
+    const long ldk = (K + 127) / 128 * 128;
+    std::vector<int8_t> hx((size_t)LX * B * ldk, 0);
+    std::vector<uint8_t> hw((size_t)LW * N * ldk, 0);
+    for (long b = 0; b < B; ++b)
+        for (long kk = 0; kk < K; ++kk) {
+            long long v = x[b * K + kk];
+            for (int j = 0; j < LX; ++j) {
+                long long lo = ((v + 128) & 255) - 128;  // balanced digit in [-128,127]
+                if (j == LX - 1) lo = v;
+                hx[((size_t)j * B + b) * ldk + kk] = (int8_t)lo;
+                v = (v - lo) / 256;
+            }
+        }
+    for (long nn = 0; nn < N; ++nn)
+        for (long kk = 0; kk < K; ++kk) {
+            long long v = w[nn * K + kk];
+            for (int i = 0; i < LW; ++i) {
+                long long lo;
+                if (w_signed) { lo = ((v + 128) & 255) - 128; if (i == LW - 1) lo = v; v = (v - lo) / 256; }
+                else { lo = v & 255; v >>= 8; }
+                hw[((size_t)i * N + nn) * ldk + kk] = (uint8_t)(lo & 255);
+            }
+        }
+    int8_t* dx = nullptr; uint8_t* dw = nullptr; int64_t* dout = nullptr;
+    qf_status rc = QF_OK;
+    if (cudaMalloc(&dx, hx.size()) != cudaSuccess || cudaMalloc(&dw, hw.size()) != cudaSuccess ||
+        cudaMalloc(&dout, (size_t)B * N * 8) != cudaSuccess)
+        rc = QF_ERR_CUDA;
+    if (rc == QF_OK && (cudaMemcpy(dx, hx.data(), hx.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                        cudaMemcpy(dw, hw.data(), hw.size(), cudaMemcpyHostToDevice) != cudaSuccess))
+        rc = QF_ERR_CUDA;
+    if (rc == QF_OK) {
+        I8GemmArgs a{};
+        a.x = dx; a.ldx = ldk; a.x_plane = (long)B * ldk;
+        a.w = dw; a.ldw = ldk; a.w_plane = (long)N * ldk;
+        a.LX = LX; a.LW = LW; a.w_signed = w_signed; a.B = (int)B; a.N = (int)N; a.K = (int)K;
+        a.out_kind = 0; a.sign = 1; a.q = q; a.base = nullptr; a.ldbase = 0; a.out = dout; a.ldout = N; a.flag = nullptr;
+        cudaError_t e = qf_launch_gemm_i8(a, nullptr);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { fprintf(stderr, "qf_debug_gemm_i8: %s\n", cudaGetErrorString(e)); rc = QF_ERR_CUDA; }
+    }
+    if (rc == QF_OK && cudaMemcpy(out, dout, (size_t)B * N * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
+    cudaFree(dx); cudaFree(dw); cudaFree(dout);
+    return rc;
+}
+
 qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* st) {
     if (!out || q < 2) return QF_ERR_INVALID;
     return qf_launch_uniform_modq(out, (long)count, q, seed, 0, (cudaStream_t)st) == cudaSuccess ? QF_OK : QF_ERR_CUDA;

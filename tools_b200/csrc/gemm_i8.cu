@@ -1,0 +1,314 @@
+// Exact integer "targets x key-matrix" contraction on the 5th-gen tensor cores:
+// limb-split int8 tcgen05.mma (kind::i8, s32 accumulators in TMEM) fed by TMA.
+//
+//   V[b][n] = sum_k x[b][k] * w[n][k]          x, w multi-limb integers
+//   x = sum_j 256^j x_j  (balanced s8 limbs)     w = sum_i 256^i w_i  (u8 limbs of a residue,
+//                                                 or balanced s8 limbs of a signed entry)
+//   V = sum_d 256^d D_d ,   D_d = sum_{i+j=d} sum_k x_j[b][k] w_i[n][k]
+//
+// Every D_d lives in its own TMEM accumulator (128 lanes x NT columns of s32); all limb pairs
+// with i+j = d accumulate into the same one, so the epilogue reads ND = LX+LW-1 accumulators
+// and recombines them exactly (int64 / int128), then reduces mod q or stores the integer.
+// Used for f_a = A sigma (gpv.rs:190-193), v = u - A p and e = p + [R;I] z
+// (mp_perturbation.rs:318,335), e = sol + S z (gpv.rs:160) and TrapGen's A_bar R
+// (gadget_classical.rs:66).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 epilogue (tcgen05.ld 32x32b, one TMEM lane = one target row per thread).
+// Tile: 128 targets x NT coordinates x 128-byte K blocks, SWIZZLE_128B K-major operands,
+// multi-stage mbarrier pipeline.  K is long (m ~ 10^4) and the epilogue is < 3 % of a tile,
+// so one tile per CTA (no TMEM double buffering).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int BLOCK_K = 128;  // bytes = int8 elements
+constexpr int I8_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+struct I8Params {
+    int B, N, K;
+    int LX, LW;
+    int nt;        // N tile (multiple of 16)
+    int stages;
+    int w_signed;  // b_format: 1 = s8 limbs, 0 = u8 limbs
+    // epilogue
+    int out_kind;  // 0: int64 (optionally mod q, optional base, sign), 1: int32 store, 2: fp64 accumulate (+=)
+    int sign;      // +1 / -1 applied to V
+    unsigned long long q;  // 0: no reduction
+    const int64_t* base; long ldbase;
+    void* out; long ldout;
+    int* flag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();  // watchdog: never hang the device
+    }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand tile (rows of 128 bytes, 8-row atoms of 1024 bytes)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);      // start address
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset (8 rows x 128 B)
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned operand ring
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int x_tile = TILE_M * BLOCK_K, w_tile = p.nt * BLOCK_K;
+    const int stage_bytes = p.LX * x_tile + p.LW * w_tile;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * p.nt, m0 = blockIdx.y * TILE_M;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int ND = p.LX + p.LW - 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // allocate all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sx = smem + (size_t)stage * stage_bytes;
+                uint8_t* sw = sx + p.LX * x_tile;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                for (int j = 0; j < p.LX; ++j) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
+                for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D = s32, A = s8 (x limbs), B = u8/s8 (w limbs), K-major both, M = 128, N = nt
+        const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(p.w_signed ? 1 : 0) << 10) |
+                               ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0, inited = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sx = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sw = sx + p.LX * x_tile;
+                for (int i = 0; i < p.LW; ++i) {
+                    for (int j = 0; j < p.LX; ++j) {
+                        const int d = i + j;
+                        const uint64_t da = make_desc(sx + j * x_tile), db = make_desc(sw + i * w_tile);
+#pragma unroll
+                        for (int kk = 0; kk < BLOCK_K / 32; ++kk) {
+                            const uint32_t acc = (kk > 0 || ((inited >> d) & 1u)) ? 1u : 0u;
+                            // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                            mma_i8(tmem_base + (uint32_t)(d * p.nt), da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc);
+                        }
+                        inited |= 1u << d;
+                    }
+                }
+                mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+                if (kb == num_kb - 1) mma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+        const int lg = warp & 3;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + lg * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+            __int128 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = 0;
+            for (int d = 0; d < ND; ++d) {
+                int32_t t[16];
+                tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] += ((__int128)t[c]) << (8 * d);
+            }
+            if (row < p.B) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int n = n0 + c0 + c;
+                    if (n >= p.N) continue;
+                    __int128 val = p.sign < 0 ? -v[c] : v[c];
+                    if (p.out_kind == 0) {
+                        if (p.base) val += (__int128)p.base[(long)row * p.ldbase + n];
+                        long long r;
+                        if (p.q) {
+                            if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)val & (p.q - 1));
+                            else r = (long long)mod_i128(val, p.q);
+                        } else {
+                            r = (long long)val;
+                        }
+                        ((int64_t*)p.out)[(long)row * p.ldout + n] = r;
+                    } else if (p.out_kind == 1) {
+                        if (val > 2147483647 || val < -2147483647) {
+                            if (p.flag) atomicOr(p.flag, 4);
+                            val = 0;
+                        }
+                        ((int32_t*)p.out)[(long)row * p.ldout + n] = (int32_t)(long long)val;
+                    } else {
+                        ((double*)p.out)[(long)row * p.ldout + n] += (double)(long long)val;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// planes: `limbs` matrices of rows x K bytes (row stride ld, plane stride plane_bytes)
+bool make_map(CUtensorMap* map, const void* base, int K, int rows, int limbs, long ld, long plane_bytes, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)limbs};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int qf_i8_tile_n(int LX, int LW, int N) {
+    const int ND = LX + LW - 1;
+    int nt = (512 / ND) / 16 * 16;
+    if (nt > 256) nt = 256;
+    int need = (N + 15) / 16 * 16;
+    if (nt > need) nt = need;
+    return nt;
+}
+
+cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
+    if (a.B <= 0 || a.N <= 0) return cudaSuccess;
+    if (a.LX < 1 || a.LW < 1 || a.LX + a.LW - 1 > 16 || a.K < 1) return cudaErrorInvalidValue;
+    if ((a.ldx & 15) || (a.ldw & 15) || (a.x_plane & 15) || (a.w_plane & 15) || (((uintptr_t)a.x) & 15) ||
+        (((uintptr_t)a.w) & 15))
+        return cudaErrorMisalignedAddress;
+    const int nt = qf_i8_tile_n(a.LX, a.LW, a.N);
+    if (nt < 16) return cudaErrorInvalidValue;
+    I8Params p{};
+    p.B = a.B; p.N = a.N; p.K = a.K; p.LX = a.LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
+    p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
+    p.ldout = a.ldout; p.flag = a.flag;
+    const int stage_bytes = a.LX * TILE_M * BLOCK_K + a.LW * nt * BLOCK_K;
+    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+    int stages = budget / stage_bytes;
+    if (stages < 2) return cudaErrorInvalidValue;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    const int smem = stages * stage_bytes + 1024 + 256;
+    CUtensorMap mx, mw;
+    if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M)) return cudaErrorInvalidValue;
+    if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dim3 grid((a.N + nt - 1) / nt, (a.B + TILE_M - 1) / TILE_M);
+    gemm_i8_kernel<<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
+    return cudaGetLastError();
+}

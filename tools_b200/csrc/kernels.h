@@ -103,3 +103,23 @@ cudaError_t qf_launch_transpose_scale(const double* in, long ldin, double* out, 
 cudaError_t qf_launch_gather_cols(const double* in, long ldin, const int* cols, int ncols, double* out, long ldout,
                                   int rows, cudaStream_t stream);
 cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams* dg, cudaStream_t stream);
+
+// ---- gemm_i8.cu : exact integer contraction on tcgen05 (kind::i8) --------------------------
+struct I8GemmArgs {
+    const int8_t* x;    // LX planes of B x K balanced s8 limbs, row stride ldx, plane stride x_plane (bytes)
+    long ldx, x_plane;
+    const void* w;      // LW planes of N x K limbs (u8 residue limbs or balanced s8 limbs)
+    long ldw, w_plane;
+    int LX, LW, w_signed;
+    int B, N, K;
+    int out_kind;       // 0: int64 (base, sign, optional mod q)  1: int32 store  2: fp64 accumulate
+    int sign;
+    unsigned long long q;
+    const int64_t* base;
+    long ldbase;
+    void* out;
+    long ldout;
+    int* flag;
+};
+int qf_i8_tile_n(int LX, int LW, int N);
+cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
