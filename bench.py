@@ -259,7 +259,9 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - l0
     gms, gfl, gln = _ffi.C.c_double(), _ffi.C.c_double(), _ffi.C.c_uint64()
-    ctx.call("qf_profile_read", _ffi.C.byref(gms), _ffi.C.byref(gfl), _ffi.C.byref(gln))
+    ims, iops, iiss, iln = _ffi.C.c_double(), _ffi.C.c_double(), _ffi.C.c_double(), _ffi.C.c_uint64()
+    ctx.call("qf_profile_read", _ffi.C.byref(gms), _ffi.C.byref(gfl), _ffi.C.byref(gln), _ffi.C.byref(ims),
+             _ffi.C.byref(iops), _ffi.C.byref(iiss), _ffi.C.byref(iln))
     ctx.call("qf_profile", 0)
     clock_info = clocks.stop() if rank == 0 else None
     ctx.call("qf_synchronize")
@@ -345,7 +347,7 @@ def main():
     del x, y
     achieved = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else None
     roofline = {
-        "kernel": "gemm_f64_kernel (mma.sync.m8n8k4.f64, fp64 tensor pipe)",
+        "kernel": "gemm_f64_kernel (mma.sync.m8n8k4.f64, fp64 tensor pipe): nearest-plane coefficient updates",
         "bound": "tensor", "achieved": achieved, "peak": dgemm_tf, "unit": "TFLOP/s",
         "frac": (achieved / dgemm_tf) if achieved else None, "traffic": None,
         "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json holds only bf16 "
@@ -353,6 +355,20 @@ def main():
         "kernel_ms_per_step": gms.value / args.steps, "kernel_share_of_step": gms.value / ms,
         "launches": int(gln.value),
     }
+    i8 = None
+    if ims.value > 0:
+        bf16 = peaks.get("bf16_tflops") or 1590.0
+        i8 = {
+            "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8 + TMA + TMEM): exact e = sol + S z",
+            "bound": "tensor", "unit": "TOP/s",
+            "achieved_algorithmic": iops.value / (ims.value * 1e-3) / 1e12,
+            "achieved_issued": iiss.value / (ims.value * 1e-3) / 1e12,
+            "peak": 2.0 * bf16, "frac_issued": iiss.value / (ims.value * 1e-3) / 1e12 / (2.0 * bf16),
+            "peak_source": "2 x the measured bf16 burst of MEASURED_PEAKS.json (int8 is not in the file; nominal 4.5 POP/s)"
+                           if peaks.get("bf16_tflops") else "2 x fallback bf16 1.59 PF/s",
+            "kernel_ms_per_step": ims.value / args.steps, "kernel_share_of_step": ims.value / ms,
+            "launches": int(iln.value),
+        }
 
     # ---- CPU baseline: the oracle's C restatement on a bounded sample ----------------------------------
     cpu = None
@@ -389,6 +405,7 @@ def main():
         "f_a": {"value": fa_value, "unit": "evals/s", "ms_per_step": fa_ms / fa_steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_i8": i8,
         "cpu_baseline": cpu,
         "clocks": clock_info,
     }

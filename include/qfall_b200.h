@@ -79,11 +79,14 @@ qf_status qf_synchronize(qf_ctx* ctx);
 /* number of kernels this context has launched so far */
 uint64_t qf_launch_count(const qf_ctx* ctx);
 
-/* Per-launch CUDA-event timing of the dominant kernel (the fp64 tensor contraction) on the
- * context's stream.  qf_profile_read synchronises, returns the summed kernel time, the
- * algorithmic flops those launches performed and their count, and resets the counters. */
+/* Per-launch CUDA-event timing of the two contraction kernels on the context's stream: the fp64
+ * DMMA contraction (gemm_*) and the tcgen05 int8 limb contraction (i8_*).  qf_profile_read
+ * synchronises, returns the summed kernel time, the algorithmic operations (2*B*N*K per launch;
+ * i8_issued_ops additionally counts every digit-pair product the tensor pipe executed) and the
+ * launch counts, and resets the counters.  Any output pointer may be NULL. */
 qf_status qf_profile(qf_ctx* ctx, int enable);
-qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches);
+qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches, double* i8_ms,
+                          double* i8_ops, double* i8_issued_ops, uint64_t* i8_launches);
 
 /* ---- key material -------------------------------------------------------- */
 /* A: n x m residues (PSFGPV / PSFPerturbation `A`, gpv.rs:60, mp_perturbation.rs:194) */

@@ -24,10 +24,10 @@ def _run(x, w, w_signed, lx, lw, q):
 ])
 def test_gemm_i8_exact(B, N, K, lx, lw, w_signed, q):
     rng = np.random.default_rng(B * N + K)
-    xmax = 2 ** (8 * lx - 1) - 1
+    xmax = 127 * (256**lx - 1) // 255  # largest value with lx balanced digits in [-128,127]
     x = rng.integers(-xmax, xmax + 1, (B, K), dtype=np.int64)
     if w_signed:
-        wmax = 2 ** (8 * lw - 1) - 1
+        wmax = 127 * (256**lw - 1) // 255
         w = rng.integers(-wmax, wmax + 1, (N, K), dtype=np.int64)
     else:
         hi = min(2 ** (8 * lw), q if q else 2 ** (8 * lw))

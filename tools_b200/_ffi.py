@@ -42,7 +42,8 @@ SIGNATURES = {
     "qf_synchronize": (_i32, [_vp]),
     "qf_launch_count": (_u64, [_vp]),
     "qf_profile": (_i32, [_vp, _i32]),
-    "qf_profile_read": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "qf_profile_read": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "qf_set_a": (_i32, [_vp, _vp]),
     "qf_set_trapdoor_perturbation": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "qf_set_trapdoor_gpv": (_i32, [_vp, _vp, _vp]),

@@ -107,9 +107,18 @@ struct qf_ctx {
     // workspace
     Dev w[12];
     Dev dNorm, dFlag, io_a, io_b, io_c;
-    // optional per-launch timing of the dominant kernel (gemm_f64), CUDA events on ctx->stream
+    // tcgen05 int8 path for the exact integer contractions
+    bool use_i8 = true;
+    long ldk_dim = 0, ldk_nk = 0;
+    int x_limbs = 0;       // digits for Domain-sized values (|.| <= sqrt(bound))
+    int a_limbs = 0;       // u8 digits of a residue
+    Dev dAl;               // A as a_limbs planes of n x ldk_dim
+    Dev dRl;               // R as one s8 plane m_bar x ldk_nk
+    Dev dSl;               // S as s_limbs planes of dim x ldk_dim
+    int s_limbs = 0, z_limbs = 0;
+    // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
-    struct ProfRec { cudaEvent_t a, b; double flops; };
+    struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> ev_pool;
 
@@ -215,6 +224,65 @@ cudaError_t ctx_gemm(qf_ctx* ctx, const double* X, long ldx, const double* W, lo
     return e;
 }
 
+// smallest number of balanced base-256 digits that hold |v| <= maxabs
+int limbs_for(double maxabs) {
+    double cap = 127.0, pw = 1.0;
+    int L = 1;
+    while (cap < maxabs && L < 9) { pw *= 256.0; cap += 127.0 * pw; ++L; }
+    return L;
+}
+double limb_capacity(int L) {
+    double cap = 0, pw = 1.0;
+    for (int l = 0; l < L; ++l) { cap += 127.0 * pw; pw *= 256.0; }
+    return cap;
+}
+
+// integer matrix (host int64, rows x cols) -> L planes of rows x ldk bytes on the device
+qf_status upload_limbs(qf_ctx* ctx, const int64_t* h, long rows, long cols, long ldk, int L, bool is_signed, Dev& dst) {
+    std::vector<uint8_t> tmp((size_t)L * rows * ldk, 0);
+    for (long i = 0; i < rows; ++i)
+        for (long j = 0; j < cols; ++j) {
+            long long v = h[i * cols + j];
+            for (int l = 0; l < L; ++l) {
+                long long lo;
+                if (is_signed) {
+                    lo = ((v + 128) & 255) - 128;
+                    if (l == L - 1) lo = v;
+                    v = (v - lo) >> 8;
+                } else {
+                    lo = v & 255;
+                    v >>= 8;
+                }
+                tmp[((size_t)l * rows + i) * ldk + j] = (uint8_t)(lo & 255);
+            }
+        }
+    CK(dst.ensure(tmp.size()));
+    CK(cudaMemcpyAsync(dst.p, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QF_OK;
+}
+
+// tcgen05 int8 contraction with optional event timing
+cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
+    qf_ctx::ProfRec rec{};
+    if (ctx->prof) {
+        for (cudaEvent_t* e : {&rec.a, &rec.b}) {
+            if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) return cudaErrorUnknown;
+        }
+        rec.kind = 1;
+        rec.flops = 2.0 * a.B * (double)a.N * a.K;
+        rec.issued = rec.flops * a.LX * a.LW;
+        cudaEventRecord(rec.a, ctx->stream);
+    }
+    cudaError_t e = qf_launch_gemm_i8(a, ctx->stream);
+    if (ctx->prof) {
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof_recs.push_back(rec);
+    }
+    return e;
+}
+
 // ---------------------------------------------------------------------------
 // exact  out = X * W^t  with W given as non-negative fp64 digit matrices
 // ---------------------------------------------------------------------------
@@ -230,6 +298,26 @@ qf_status gemm_chunks(qf_ctx* ctx, const double* X, long ldx, Dev* W, int nchunk
 // ---------------------------------------------------------------------------
 qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uint8_t* dFlags) {
     const long ldm = ctx->ld_dim, ldn = ctx->ld_n;
+    if (ctx->use_i8) {
+        const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
+        CK(ctx->w[0].ensure((size_t)ctx->x_limbs * plane));
+        CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+        LAUNCH(qf_launch_split_i32_limbs(dSigma, ctx->dim, ctx->w[0].as<int8_t>(), plane, ldk, Bc, (int)ctx->dim,
+                                         ctx->x_limbs, ctx->dNorm.as<unsigned long long>(), ctx->stream));
+        if (dFlags)
+            LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, dFlags, Bc, ctx->stream));
+        if (dU) {
+            I8GemmArgs g{};
+            g.x = ctx->w[0].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
+            g.w = ctx->dAl.p; g.ldw = ldk; g.w_plane = (long)ctx->n * ldk;
+            g.LX = ctx->x_limbs; g.LW = ctx->a_limbs; g.w_signed = 0;
+            g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->m;
+            g.out_kind = 0; g.sign = 1; g.q = ctx->prm.q; g.base = nullptr; g.ldbase = 0; g.out = dU; g.ldout = ctx->n;
+            g.flag = ctx->dFlag.as<int>();
+            LAUNCH(ctx_gemm_i8(ctx, g));
+        }
+        return QF_OK;
+    }
     CK(ctx->w[0].ensure((size_t)ctx->chunk * ldm * 8));
     CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
     double* X = ctx->w[0].as<double>();
@@ -294,7 +382,20 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
                             ctx->stream));
     // v = u - A p   (:318)
-    {
+    if (ctx->use_i8) {
+        const long ldk = ctx->ldk_dim, plane = C * ldk;
+        CK(ctx->w[0].ensure((size_t)ctx->x_limbs * plane));  // g is dead: reuse as digit planes of p
+        LAUNCH(qf_launch_split_f64_limbs(P, ldm, ctx->w[0].as<int8_t>(), plane, ldk, Bc, (int)ctx->m, ctx->x_limbs,
+                                         ctx->dFlag.as<int>(), ctx->stream));
+        I8GemmArgs g{};
+        g.x = ctx->w[0].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dAl.p; g.ldw = ldk; g.w_plane = (long)ctx->n * ldk;
+        g.LX = ctx->x_limbs; g.LW = ctx->a_limbs; g.w_signed = 0;
+        g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->m;
+        g.out_kind = 0; g.sign = -1; g.q = ctx->prm.q; g.base = dUin; g.ldbase = ctx->n; g.out = V; g.ldout = ctx->n;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    } else {
         double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
         CombineArgs ca{};
         for (int c = 0; c < ctx->a_nchunks; ++c) {
@@ -312,7 +413,23 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     LAUNCH(qf_launch_gadget_sample(V, ctx->n, Z, ldnk, Bc, (int)ctx->n, (int)ctx->k, (int)ctx->prm.base, ctx->prm.q,
                                    ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed, first, ctx->stream));
     // e = p + [R; I] z   (:328-335): top block accumulates R z into p in place (exact small integers)
-    LAUNCH(ctx_gemm(ctx, Z, ldnk, ctx->dR.as<double>(), ldnk, P, ldm, Bc, (int)ctx->m_bar, (int)ctx->nk, 1.0, 1.0, 0));
+    if (ctx->use_i8) {
+        const long ldk = ctx->ldk_nk, plane = C * ldk;
+        const int LZ = 2;
+        CK(ctx->w[1].ensure((size_t)LZ * plane));  // x2 is dead: reuse as digit planes of z
+        LAUNCH(qf_launch_split_f64_limbs(Z, ldnk, ctx->w[1].as<int8_t>(), plane, ldk, Bc, (int)ctx->nk, LZ,
+                                         ctx->dFlag.as<int>(), ctx->stream));
+        I8GemmArgs g{};
+        g.x = ctx->w[1].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dRl.p; g.ldw = ldk; g.w_plane = (long)ctx->m_bar * ldk;
+        g.LX = LZ; g.LW = 1; g.w_signed = 1;
+        g.B = Bc; g.N = (int)ctx->m_bar; g.K = (int)ctx->nk;
+        g.out_kind = 2; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = P; g.ldout = ldm;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    } else {
+        LAUNCH(ctx_gemm(ctx, Z, ldnk, ctx->dR.as<double>(), ldnk, P, ldm, Bc, (int)ctx->m_bar, (int)ctx->nk, 1.0, 1.0, 0));
+    }
     LAUNCH(qf_launch_finalize_pert(P, ldm, Z, ldnk, dE, ctx->m, Bc, (int)ctx->m, (int)ctx->m_bar, ctx->dFlag.as<int>(),
                                    ctx->stream));
     return QF_OK;
@@ -370,8 +487,23 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         if (jb0 > 0)
             LAUNCH(ctx_gemm(ctx, Z + jb0, ldD, U + jb0, ldD, T, ldD, Bc, (int)jb0, (int)(jb1 - jb0), -1.0, 1.0, 0));
     }
-    // e = sol + S z   (exact integers; z split into z_bits-wide balanced chunks)
-    {
+    // e = sol + S z   (exact integers)
+    if (ctx->use_i8) {
+        // z -> balanced base-256 digits, S z on the tensor cores, then add sol on its pivot columns
+        const long ldk = ctx->ldk_dim, plane = C * ldk;
+        CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->z_limbs * plane, C * ldD * 8)));  // T is dead: reuse
+        int8_t* zp = ctx->w[2].as<int8_t>();
+        LAUNCH(qf_launch_split_f64_limbs(Z, ldD, zp, plane, ldk, Bc, (int)D, ctx->z_limbs, ctx->dFlag.as<int>(), ctx->stream));
+        I8GemmArgs g{};
+        g.x = zp; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dSl.p; g.ldw = ldk; g.w_plane = D * ldk;
+        g.LX = ctx->z_limbs; g.LW = ctx->s_limbs; g.w_signed = 1;
+        g.B = Bc; g.N = (int)D; g.K = (int)D;
+        g.out_kind = 1; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = dE; g.ldout = D;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+        LAUNCH(qf_launch_add_cols_i32(dE, D, Sol, ldp, ctx->dPiv.as<int>(), np, Bc, ctx->stream));
+    } else {
         double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
         double* zc[4] = {nullptr, nullptr, nullptr, nullptr};
         CombineArgs ca{};
@@ -472,6 +604,8 @@ qf_status install_a(qf_ctx* ctx, const int64_t* a) {
     ctx->a_bits = wb;
     ctx->a_nchunks = nch;
     QF_TRY(upload_chunks(ctx, a, n, m, ctx->ld_dim, nch, wb, ctx->dA));
+    ctx->a_limbs = (qbits + 7) / 8;
+    QF_TRY(upload_limbs(ctx, a, n, m, ctx->ldk_dim, ctx->a_limbs, false, ctx->dAl));
     ctx->has_a = true;
     return QF_OK;
 }
@@ -511,6 +645,13 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
     } else {
         long double b = (long double)p->s * p->s * (long double)ctx->dim * (long double)r * r;
         ctx->bound = (unsigned long long)floorl(b);
+    }
+    ctx->ldk_dim = (ctx->dim + 127) / 128 * 128;
+    ctx->ldk_nk = (ctx->nk + 127) / 128 * 128;
+    ctx->x_limbs = limbs_for(std::sqrt((double)ctx->bound));
+    {
+        const char* env = getenv("QF_DISABLE_I8");
+        ctx->use_i8 = !(env && env[0] == '1');
     }
     // default chunk: keep ~6 fp64 work matrices within ~12 GB
     long per_target = ctx->ld_dim * 8 * 8;
@@ -560,21 +701,29 @@ qf_status qf_profile(qf_ctx* ctx, int enable) {
     return QF_OK;
 }
 
-qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches) {
+qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches, double* i8_ms,
+                          double* i8_ops, double* i8_issued_ops, uint64_t* i8_launches) {
     if (!ctx) return QF_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
-    double ms = 0, fl = 0;
+    double ms[2] = {0, 0}, fl[2] = {0, 0}, issued = 0;
+    uint64_t cnt[2] = {0, 0};
     for (auto& r : ctx->prof_recs) {
         float t = 0;
         cudaEventElapsedTime(&t, r.a, r.b);
-        ms += t;
-        fl += r.flops;
+        ms[r.kind] += t;
+        fl[r.kind] += r.flops;
+        cnt[r.kind] += 1;
+        if (r.kind == 1) issued += r.issued;
         ctx->ev_pool.push_back(r.a);
         ctx->ev_pool.push_back(r.b);
     }
-    if (gemm_ms) *gemm_ms = ms;
-    if (gemm_flops) *gemm_flops = fl;
-    if (gemm_launches) *gemm_launches = ctx->prof_recs.size();
+    if (gemm_ms) *gemm_ms = ms[0];
+    if (gemm_flops) *gemm_flops = fl[0];
+    if (gemm_launches) *gemm_launches = cnt[0];
+    if (i8_ms) *i8_ms = ms[1];
+    if (i8_ops) *i8_ops = fl[1];
+    if (i8_issued_ops) *i8_issued_ops = issued;
+    if (i8_launches) *i8_launches = cnt[1];
     ctx->prof_recs.clear();
     return QF_OK;
 }
@@ -591,6 +740,11 @@ qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const doubl
     if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");
     CK(cudaSetDevice(ctx->device));
     QF_TRY(upload_as_f64(ctx, r, ctx->m_bar, ctx->nk, ctx->ld_nk, ctx->dR));
+    {
+        std::vector<int64_t> r64((size_t)ctx->m_bar * ctx->nk);
+        for (size_t i = 0; i < r64.size(); ++i) r64[i] = r[i];
+        QF_TRY(upload_limbs(ctx, r64.data(), ctx->m_bar, ctx->nk, ctx->ldk_nk, 1, true, ctx->dRl));
+    }
     QF_TRY(upload_as_f64(ctx, l, ctx->m, ctx->m, ctx->ld_dim, ctx->dL));
     QF_TRY(upload_as_f64(ctx, sk, ctx->k, ctx->k, ctx->k, ctx->dSk));
     QF_TRY(upload_as_f64(ctx, skg, ctx->k, ctx->k, ctx->k, ctx->dSkGso));
@@ -676,6 +830,13 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     while (nch < 4 && z_est >= std::ldexp(1.0, nch * zb - 1)) ++nch;
     ctx->z_bits = zb; ctx->z_nchunks = nch;
     ctx->zlimit = std::min(std::ldexp(1.0, nch * zb - 1), std::ldexp(1.0, 52));
+    ctx->s_limbs = limbs_for((double)smax);
+    ctx->z_limbs = limbs_for(z_est);
+    if (ctx->use_i8) {
+        if (ctx->z_limbs + ctx->s_limbs - 1 > 16) return ctx->fail(QF_ERR_UNSUPPORTED, "too many digits for the int8 S*z product");
+        ctx->zlimit = std::min(ctx->zlimit, limb_capacity(ctx->z_limbs));
+        QF_TRY(upload_limbs(ctx, s, D, D, ctx->ldk_dim, ctx->s_limbs, true, ctx->dSl));
+    }
     ctx->has_np = true;
     return QF_OK;
 }
@@ -734,27 +895,46 @@ qf_status qf_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int8_t* r, c
     wb = std::min(wb, qbits);
     int nch = (qbits + wb - 1) / wb;
     if (nch > 4) return ctx->fail(QF_ERR_UNSUPPORTED, "modulus needs more than 4 digit matrices (TrapGen)");
-    Dev dW[4], dX, dAcc[4], dOut;
-    QF_TRY(upload_chunks(ctx, a_bar, n, mb, ldmb, nch, wb, dW));
-    {
-        std::vector<double> rt((size_t)nk * ldmb, 0.0);
-        for (long i = 0; i < mb; ++i)
-            for (long j = 0; j < nk; ++j) rt[(size_t)j * ldmb + i] = (double)r[i * nk + j];
-        CK(dX.ensure(rt.size() * 8));
-        CK(cudaMemcpy(dX.p, rt.data(), rt.size() * 8, cudaMemcpyHostToDevice));
-    }
-    double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
-    CombineArgs ca{};
-    for (int c = 0; c < nch; ++c) {
-        CK(dAcc[c].ensure((size_t)nk * ldn * 8));
-        acc[c] = dAcc[c].as<double>();
-        ca.acc[c] = acc[c];
-        ca.shift[c] = c * wb;
-    }
-    QF_TRY(gemm_chunks(ctx, dX.as<double>(), ldmb, dW, nch, ldmb, acc, ldn, (int)nk, (int)n, (int)mb));
-    ca.nacc = nch; ca.acc_sign = 1; ca.ldacc = ldn; ca.base = nullptr; ca.ldbase = 0; ca.q = q;
+    Dev dW[4], dX, dAcc[4], dOut, dWl, dXl;
     CK(dOut.ensure((size_t)nk * n * 8));
-    LAUNCH(qf_launch_combine_i64(ca, dOut.as<int64_t>(), n, (int)nk, (int)n, ctx->stream));
+    if (ctx->use_i8 && rmax <= 127) {
+        // tcgen05 path: "targets" = the nk columns of R (one s8 digit), key matrix = A_bar in u8 digits
+        const long ldk = (mb + 127) / 128 * 128;
+        const int LA = (qbits + 7) / 8;
+        QF_TRY(upload_limbs(ctx, a_bar, n, mb, ldk, LA, false, dWl));
+        std::vector<int64_t> rt((size_t)nk * mb);
+        for (long i = 0; i < mb; ++i)
+            for (long j = 0; j < nk; ++j) rt[(size_t)j * mb + i] = r[i * nk + j];
+        QF_TRY(upload_limbs(ctx, rt.data(), nk, mb, ldk, 1, true, dXl));
+        I8GemmArgs g{};
+        g.x = dXl.as<int8_t>(); g.ldx = ldk; g.x_plane = nk * ldk;
+        g.w = dWl.p; g.ldw = ldk; g.w_plane = n * ldk;
+        g.LX = 1; g.LW = LA; g.w_signed = 0;
+        g.B = (int)nk; g.N = (int)n; g.K = (int)mb;
+        g.out_kind = 0; g.sign = 1; g.q = q; g.base = nullptr; g.ldbase = 0; g.out = dOut.p; g.ldout = n;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    } else {
+        QF_TRY(upload_chunks(ctx, a_bar, n, mb, ldmb, nch, wb, dW));
+        {
+            std::vector<double> rt((size_t)nk * ldmb, 0.0);
+            for (long i = 0; i < mb; ++i)
+                for (long j = 0; j < nk; ++j) rt[(size_t)j * ldmb + i] = (double)r[i * nk + j];
+            CK(dX.ensure(rt.size() * 8));
+            CK(cudaMemcpy(dX.p, rt.data(), rt.size() * 8, cudaMemcpyHostToDevice));
+        }
+        double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
+        CombineArgs ca{};
+        for (int c = 0; c < nch; ++c) {
+            CK(dAcc[c].ensure((size_t)nk * ldn * 8));
+            acc[c] = dAcc[c].as<double>();
+            ca.acc[c] = acc[c];
+            ca.shift[c] = c * wb;
+        }
+        QF_TRY(gemm_chunks(ctx, dX.as<double>(), ldmb, dW, nch, ldmb, acc, ldn, (int)nk, (int)n, (int)mb));
+        ca.nacc = nch; ca.acc_sign = 1; ca.ldacc = ldn; ca.base = nullptr; ca.ldbase = 0; ca.q = q;
+        LAUNCH(qf_launch_combine_i64(ca, dOut.as<int64_t>(), n, (int)nk, (int)n, ctx->stream));
+    }
     std::vector<int64_t> art((size_t)nk * n);
     CK(cudaMemcpyAsync(art.data(), dOut.p, art.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -330,3 +330,87 @@ cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream
     ternary_kernel<<<grid_for((count + 15) / 16, TPB), TPB, 0, stream>>>(out, count, seed);
     return cudaGetLastError();
 }
+
+// ---- limb splitting for the tcgen05 int8 contraction ---------------------------------------
+// value = sum_l 256^l d_l with balanced digits d_l in [-128,127]; L digits cover
+// [-128 S, 127 S], S = (256^L - 1)/255.  planes: L matrices of B x ldk bytes.
+namespace {
+
+__device__ __forceinline__ void split_digits(long long v, int L, int8_t* planes, long plane_stride, long off, int* flag) {
+    for (int l = 0; l < L - 1; ++l) {
+        long long lo = ((v + 128) & 255) - 128;
+        planes[l * plane_stride + off] = (int8_t)lo;
+        v = (v - lo) >> 8;
+    }
+    if ((v > 127 || v < -128) && flag) atomicOr(flag, 8);
+    planes[(L - 1) * plane_stride + off] = (int8_t)v;
+}
+
+__global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin, int8_t* __restrict__ planes,
+                                       long plane_stride, long ldk, int B, int M, int L, int* flag) {
+    long total = (long)B * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / M;
+        int j = (int)(i - b * M);
+        double v = in[b * ldin + j];
+        if (!(fabs(v) < 9.0e18)) {
+            if (flag) atomicOr(flag, 8);
+            v = 0;
+        }
+        split_digits(__double2ll_rn(v), L, planes, plane_stride, b * ldk + j, flag);
+    }
+}
+
+__global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __restrict__ planes,
+                                       long plane_stride, long ldk, int B, int M, int L,
+                                       unsigned long long* __restrict__ norm2) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long b = (long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long)gridDim.x * wpb) {
+        const int32_t* src = in + b * ldin;
+        unsigned long long acc = 0;
+        for (int j = lane; j < M; j += 32) {
+            long long v = src[j];
+            acc += (unsigned long long)(v * v);
+            // out-of-range entries belong to out-of-domain targets (flagged through norm2): saturate silently
+            split_digits(v, L, planes, plane_stride, b * ldk + j, nullptr);
+        }
+        if (norm2) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) norm2[b] = acc;
+        }
+    }
+}
+
+__global__ void add_cols_i32_kernel(int32_t* __restrict__ e, long lde, const double* __restrict__ sol, long ldsol,
+                                    const int* __restrict__ cols, int ncols, int B) {
+    long total = (long)B * ncols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long b = i / ncols;
+        int j = (int)(i - b * ncols);
+        e[b * lde + cols[j]] += (int32_t)__double2ll_rn(sol[b * ldsol + j]);
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
+                                      int M, int L, int* flag, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    split_f64_limbs_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk, B, M,
+                                                                               L, flag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
+                                      int M, int L, unsigned long long* norm2, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    split_i32_limbs_kernel<<<grid_for(B, TPB / 32), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk, B, M, L, norm2);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
+                                   int B, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    add_cols_i32_kernel<<<grid_for((long long)B * ncols, TPB), TPB, 0, stream>>>(e, lde, sol, ldsol, cols, ncols, B);
+    return cudaGetLastError();
+}

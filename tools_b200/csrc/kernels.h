@@ -123,3 +123,13 @@ struct I8GemmArgs {
 };
 int qf_i8_tile_n(int LX, int LW, int N);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
+
+// ---- limb splitting (elementwise.cu) ---------------------------------------------------------
+// balanced s8 digits; *flag |= 8 when a value does not fit L digits
+cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
+                                      int M, int L, int* flag, cudaStream_t stream);
+cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
+                                      int M, int L, unsigned long long* norm2, cudaStream_t stream);
+// e[b][cols[j]] += (int32) sol[b][j]
+cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
+                                   int B, cudaStream_t stream);
