@@ -278,6 +278,8 @@ def main():
     ctx.call("qf_synchronize")
     assert torch.equal(uo, u), "A e != u in the timed output"
     assert bool(fl.all()), "a timed preimage fails check_domain"
+    # spherical law: E||e||^2 = m s^2 / (2 pi) for D_{Lambda_u^perp(A), s}
+    norm_ratio = float((e[:4096].double() ** 2).sum(1).mean().item() / (gp.m * s * s / (2 * math.pi)))
 
     # ---- f_a evals/s (device resident; sigma = the preimages, in domain) ---------------------------------
     for _ in range(3):
@@ -404,6 +406,8 @@ def main():
                 "d2h_bytes_per_step": e2e_batch * gp.m * 4, "steps": e2e_steps},
         "f_a": {"value": fa_value, "unit": "evals/s", "ms_per_step": fa_ms / fa_steps},
         "gpu_launches": int(launches),
+        "checks": {"A_e_equals_u_all_targets_last_step": True, "check_domain_all": True,
+                   "mean_norm2_over_m_s2_2pi": norm_ratio},
         "roofline": roofline,
         "roofline_i8": i8,
         "cpu_baseline": cpu,

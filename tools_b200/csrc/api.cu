@@ -439,8 +439,29 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
 // GPV / ring samp_p on one chunk: GPV08 SampleD in GSO coordinates (gpv.rs:152-161,
 // gpv_ring.rs:160-212)
 // ---------------------------------------------------------------------------
-constexpr int NP_NB = 32;
-constexpr int NP_BIG = 1024;
+constexpr long NP_SIZES[3] = {64, 256, 1024};
+
+// Process coordinates [lo, hi) in descending order.  Precondition: T[:, lo:hi] already carries the
+// updates of every coordinate >= hi.  level 0 = one sequential diagonal block.
+qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, int level, uint64_t seed, uint64_t first) {
+    const long D = ctx->dim, ldD = ctx->ld_dim;
+    const double* U = ctx->dU.as<double>();
+    if (level == 0) {
+        LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(), Bc, (int)lo, (int)(hi - lo), (int)D,
+                                 seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
+        return QF_OK;
+    }
+    const long step = NP_SIZES[level - 1];
+    for (long sub_hi = hi; sub_hi > lo;) {
+        const long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
+        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, seed, first));
+        if (sub_lo > lo)
+            LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
+                            (int)(sub_hi - sub_lo), -1.0, 1.0, 0));
+        sub_hi = sub_lo;
+    }
+    return QF_OK;
+}
 
 qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
     const long D = ctx->dim, ldD = ctx->ld_dim, ldp = ctx->ld_piv, C = ctx->chunk;
@@ -472,21 +493,10 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
     }
     // centre c = -sol in GSO coordinates: T = -(B~^t D^-1)[:,P] sol_P   (gpv.rs:158)
     LAUNCH(ctx_gemm(ctx, Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0));
-    // randomized nearest plane, i = D-1 .. 0, blocked (gpv.rs:160)
-    const double* U = ctx->dU.as<double>();
-    for (long jb0 = ((D - 1) / NP_BIG) * NP_BIG; jb0 >= 0; jb0 -= NP_BIG) {
-        const long jb1 = std::min(D, jb0 + NP_BIG);
-        for (long j0 = ((jb1 - 1 - jb0) / NP_NB) * NP_NB + jb0; j0 >= jb0; j0 -= NP_NB) {
-            const int nbe = (int)std::min((long)NP_NB, D - j0);
-            LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(), Bc, (int)j0, NP_NB, (int)D, seed,
-                                     first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
-            if (j0 > jb0)
-                LAUNCH(ctx_gemm(ctx, Z + j0, ldD, U + jb0 * ldD + j0, ldD, T + jb0, ldD, Bc, (int)(j0 - jb0), nbe,
-                                          -1.0, 1.0, 0));
-        }
-        if (jb0 > 0)
-            LAUNCH(ctx_gemm(ctx, Z + jb0, ldD, U + jb0, ldD, T, ldD, Bc, (int)jb0, (int)(jb1 - jb0), -1.0, 1.0, 0));
-    }
+    // randomized nearest plane, i = D-1 .. 0 (gpv.rs:160), blocked on three levels: 64-wide diagonal
+    // blocks are sequential per target (np_diag); everything off the diagonal is a GEMM with K = 64, 256
+    // or 1024, so that most of the work runs at K = 1024.
+    QF_TRY(np_block(ctx, T, Z, Bc, 0, D, 3, seed, first));
     // e = sol + S z   (exact integers)
     if (ctx->use_i8) {
         // z -> balanced base-256 digits, S z on the tensor cores, then add sol on its pivot columns

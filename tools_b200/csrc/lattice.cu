@@ -67,28 +67,30 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
     }
 }
 
-constexpr int NP_TPB = 128;
-constexpr int NP_NB_MAX = 32;
+constexpr int NP_TPB = 64;
+constexpr int NP_NB_MAX = 64;
 
 __global__ void __launch_bounds__(NP_TPB)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, int B, int j0, int nb, int dim, uint64_t seed,
                uint64_t first_target, double zlimit, int* flag) {
-    __shared__ double us[NP_NB_MAX * NP_NB_MAX];
-    __shared__ double ts[NP_NB_MAX * (NP_TPB + 1)];
-    __shared__ DGaussParams dgs[NP_NB_MAX];
+    extern __shared__ __align__(16) double np_sm[];
+    double* us = np_sm;                         // nb x nb mu-coefficients of the diagonal block
+    double* ts = np_sm + nb * nb;               // nb x (NP_TPB+1) centres, then samples
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(ts + nb * (NP_TPB + 1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbe = min(nb, dim - j0);  // valid coordinates in this block
     for (int i = tid; i < nb * nb; i += NP_TPB) {
         int r = i / nb, c = i - r * nb;
         us[i] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
     }
-    if (tid < nbe) dgs[tid] = dg_g[j0 + tid];
+    for (int i = tid; i < nbe; i += NP_TPB) dgs[i] = dg_g[j0 + i];
     const long b0 = (long)blockIdx.x * NP_TPB;
-    // stage T[b0 .. b0+127][j0 .. j0+nb) : each warp copies rows, lanes on coordinates
+    // stage T[b0 .. b0+TPB)[j0 .. j0+nb): each warp copies rows, lanes on coordinates (coalesced)
     for (int r = warp; r < NP_TPB; r += NP_TPB / 32) {
         long b = b0 + r;
-        if (b < B && lane < nbe) ts[lane * (NP_TPB + 1) + r] = T[b * ldt + j0 + lane];
+        if (b < B)
+            for (int c = lane; c < nbe; c += 32) ts[c * (NP_TPB + 1) + r] = T[b * ldt + j0 + c];
     }
     __syncthreads();
     const long b = b0 + tid;
@@ -106,7 +108,8 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
     __syncthreads();
     for (int r = warp; r < NP_TPB; r += NP_TPB / 32) {
         long bb = b0 + r;
-        if (bb < B && lane < nbe) Z[bb * ldz + j0 + lane] = ts[lane * (NP_TPB + 1) + r];
+        if (bb < B)
+            for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[c * (NP_TPB + 1) + r];
     }
 }
 
@@ -138,7 +141,14 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TPB - 1) / NP_TPB;
-    np_diag_kernel<<<grid, NP_TPB, 0, stream>>>(T, ldt, Z, ldz, U, ldu, dg, B, j0, nb, dim, seed, first_target,
-                                                zlimit, flag);
+    size_t smem = (size_t)(nb * nb + nb * (NP_TPB + 1)) * sizeof(double) + (size_t)nb * sizeof(DGaussParams);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, B, j0, nb, dim, seed, first_target,
+                                                   zlimit, flag);
     return cudaGetLastError();
 }
