@@ -223,7 +223,8 @@ def test_sample_z_matches_reference_sampler(T):
 
     s, c, n = 3.0 * np.sqrt(5), 0.3, 200_000
     out = np.empty(n, dtype=np.int64)
-    assert _ffi.lib().qf_sample_z(_ffi.ptr(np.full(n, c)), n, s, 99, _ffi.ptr(out)) == 0
+    centers = np.full(n, c, dtype=np.float64)
+    assert _ffi.lib().qf_sample_z(_ffi.ptr(centers), n, s, 99, _ffi.ptr(out)) == 0
     rng = np.random.default_rng(5)
     # vectorised restatement of O.sample_z (same proposal / acceptance rule)
     lo, hi = int(np.ceil(c - np.ceil(6 * s))), int(np.floor(c + np.floor(6 * s)))
@@ -237,7 +238,7 @@ def test_sample_z_matches_reference_sampler(T):
     a = np.array([(out == x).sum() for x in xs], dtype=np.float64)
     b = np.array([(ref == x).sum() for x in xs], dtype=np.float64)
     keep = (a + b) >= 20
-    chi = (((a - b) ** 2) / (a + b))[keep].sum()
+    chi = (((a - b) ** 2)[keep] / (a + b)[keep]).sum()
     dof = keep.sum() - 1
     assert chi < dof + 5 * np.sqrt(2 * dof), (chi, dof)
 

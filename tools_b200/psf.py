@@ -128,7 +128,8 @@ class PSFGPV(_PSFBase):
 
     def _install_a(self, a):
         if self._a_id is not a:
-            self.ctx.call("qf_set_a", _ffi.ptr(np.ascontiguousarray(a, dtype=np.int64)))
+            aa = np.ascontiguousarray(a, dtype=np.int64)  # keep alive across the call
+            self.ctx.call("qf_set_a", _ffi.ptr(aa))
             self._a_id, self._td_id = a, None
 
     def _install_td(self, a, td):
@@ -263,9 +264,10 @@ class PSFGPVRing(_PSFBase):
     def _install_td(self, a, td):
         if self._td_id is not td:
             r, e = td
-            basis = gadget.ring_short_basis_embedded(self.gp, np.asarray(a), np.asarray(r), np.asarray(e))
-            g = linalg.gso(basis)
-            self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(np.ascontiguousarray(basis)), _ffi.ptr(np.ascontiguousarray(g)))
+            basis = np.ascontiguousarray(
+                gadget.ring_short_basis_embedded(self.gp, np.asarray(a), np.asarray(r), np.asarray(e)), dtype=np.int64)
+            g = np.ascontiguousarray(linalg.gso(basis), dtype=np.float64)  # keep alive across the call
+            self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(basis), _ffi.ptr(g))
             self._td_id = td
 
     def trap_gen(self, seed=None):
