@@ -512,3 +512,38 @@ def test_device_entry_points_and_midsize(T):
     e_host = psf.samp_p_batch(a, td, u.cpu().numpy(), seed=5)
     assert np.array_equal(e_host, e.cpu().numpy())
     assert psf.ctx.launch_count() > 0
+
+
+def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch):
+    """The fixed-point (int8 tcgen05) nearest-plane updates against the fp64 DMMA path on the same key and
+    seed: both must give exact preimages with the same second moment; with identical Philox streams almost
+    every preimage is identical (centres agree to ~2^-40)."""
+    import math
+
+    n, q = 40, 2**16
+    gp = T.GadgetParameters.init_default(n, q)
+    assert gp.m > 1024
+    s = float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))
+    rng = np.random.default_rng(12)
+    u = rng.integers(0, q, (2048, n), dtype=np.int64)
+    outs = []
+    key = None
+    for mode in ("ozaki", "fp64"):
+        if mode == "ozaki":
+            monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
+            monkeypatch.delenv("QF_DISABLE_OZAKI", raising=False)
+        else:
+            monkeypatch.setenv("QF_DISABLE_OZAKI", "1")
+        psf = T.PSFGPV(gp, s)
+        if key is None:
+            key = psf.trap_gen(seed=31)
+        a, td = key
+        psf._a_id = None
+        e = psf.samp_p_batch(a, td, u, seed=77)
+        assert np.array_equal(O.f_a_classical_batch(a, e, q), u)
+        assert psf.check_domain_batch(e).all()
+        ratio = (e.astype(np.float64) ** 2).sum(1).mean() / (gp.m * s * s / (2 * math.pi))
+        assert abs(ratio - 1) < 0.02, ratio
+        outs.append(e)
+    same = (outs[0] == outs[1]).all(axis=1).mean()
+    assert same > 0.9, same

@@ -116,6 +116,10 @@ struct qf_ctx {
     Dev dRl;               // R as one s8 plane m_bar x ldk_nk
     Dev dSl;               // S as s_limbs planes of dim x ldk_dim
     int s_limbs = 0, z_limbs = 0;
+    // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
+    bool use_ozaki = false;
+    int u_limbs = 7;
+    Dev dUl, dUscale, dNz;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -302,8 +306,13 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
         const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
         CK(ctx->w[0].ensure((size_t)ctx->x_limbs * plane));
         CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+        const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
+        const size_t nzb = (size_t)ctx->x_limbs * nz_m * nz_kb;
+        CK(ctx->dNz.ensure(nzb));
+        CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
         LAUNCH(qf_launch_split_i32_limbs(dSigma, ctx->dim, ctx->w[0].as<int8_t>(), plane, ldk, Bc, (int)ctx->dim,
-                                         ctx->x_limbs, ctx->dNorm.as<unsigned long long>(), ctx->stream));
+                                         ctx->x_limbs, ctx->dNorm.as<unsigned long long>(), ctx->dNz.as<uint8_t>(), nz_m,
+                                         nz_kb, ctx->stream));
         if (dFlags)
             LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, dFlags, Bc, ctx->stream));
         if (dU) {
@@ -314,6 +323,7 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
             g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->m;
             g.out_kind = 0; g.sign = 1; g.q = ctx->prm.q; g.base = nullptr; g.ldbase = 0; g.out = dU; g.ldout = ctx->n;
             g.flag = ctx->dFlag.as<int>();
+            g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb;
             LAUNCH(ctx_gemm_i8(ctx, g));
         }
         return QF_OK;
@@ -386,7 +396,7 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
         const long ldk = ctx->ldk_dim, plane = C * ldk;
         CK(ctx->w[0].ensure((size_t)ctx->x_limbs * plane));  // g is dead: reuse as digit planes of p
         LAUNCH(qf_launch_split_f64_limbs(P, ldm, ctx->w[0].as<int8_t>(), plane, ldk, Bc, (int)ctx->m, ctx->x_limbs,
-                                         ctx->dFlag.as<int>(), ctx->stream));
+                                         ctx->dFlag.as<int>(), nullptr, 0, 0, 0, ctx->stream));
         I8GemmArgs g{};
         g.x = ctx->w[0].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
         g.w = ctx->dAl.p; g.ldw = ldk; g.w_plane = (long)ctx->n * ldk;
@@ -418,7 +428,7 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
         const int LZ = 2;
         CK(ctx->w[1].ensure((size_t)LZ * plane));  // x2 is dead: reuse as digit planes of z
         LAUNCH(qf_launch_split_f64_limbs(Z, ldnk, ctx->w[1].as<int8_t>(), plane, ldk, Bc, (int)ctx->nk, LZ,
-                                         ctx->dFlag.as<int>(), ctx->stream));
+                                         ctx->dFlag.as<int>(), nullptr, 0, 0, 0, ctx->stream));
         I8GemmArgs g{};
         g.x = ctx->w[1].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
         g.w = ctx->dRl.p; g.ldw = ldk; g.w_plane = (long)ctx->m_bar * ldk;
@@ -455,9 +465,32 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
     for (long sub_hi = hi; sub_hi > lo;) {
         const long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
         QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, seed, first));
-        if (sub_lo > lo)
+        if (level == 3 && ctx->use_ozaki) {
+            // digits of the finished block of z (kept: the final S z reuses them), then the update of all rows
+            // above it on the tensor cores:  T[:, 0:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
+            const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
+            const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
+            int8_t* zp = ctx->w[8].as<int8_t>();
+            LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
+                                             ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
+                                             ctx->stream));
+            if (sub_lo > lo) {
+                I8GemmArgs g{};
+                g.x = zp + sub_lo; g.ldx = ldk; g.x_plane = plane;
+                g.w = ctx->dUl.as<int8_t>() + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;
+                g.LX = ctx->z_limbs; g.LW = ctx->u_limbs; g.w_signed = 1;
+                g.B = Bc; g.N = (int)sub_lo; g.K = (int)(sub_hi - sub_lo);
+                g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = T; g.ldout = ldD;
+                g.flag = ctx->dFlag.as<int>();
+                g.scale = ctx->dUscale.as<double>() + (sub_lo / NP_SIZES[2]) * D;
+                g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb;
+                g.nz_kb_off = (int)(sub_lo / 128); g.nz_m_off = 0;
+                LAUNCH(ctx_gemm_i8(ctx, g));
+            }
+        } else if (sub_lo > lo) {
             LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
                             (int)(sub_hi - sub_lo), -1.0, 1.0, 0));
+        }
         sub_hi = sub_lo;
     }
     return QF_OK;
@@ -496,15 +529,29 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
     // randomized nearest plane, i = D-1 .. 0 (gpv.rs:160), blocked on three levels: 64-wide diagonal
     // blocks are sequential per target (np_diag); everything off the diagonal is a GEMM with K = 64, 256
     // or 1024, so that most of the work runs at K = 1024.
+    if (ctx->use_ozaki) {
+        const long ldk = ctx->ldk_dim;
+        const size_t nzb = (size_t)ctx->z_limbs * ((ctx->chunk + 127) / 128) * (ldk / 128);
+        CK(ctx->w[8].ensure((size_t)ctx->z_limbs * C * ldk));
+        CK(ctx->dNz.ensure(nzb));
+        CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
+    }
     QF_TRY(np_block(ctx, T, Z, Bc, 0, D, 3, seed, first));
     // e = sol + S z   (exact integers)
     if (ctx->use_i8) {
         // z -> balanced base-256 digits, S z on the tensor cores, then add sol on its pivot columns
         const long ldk = ctx->ldk_dim, plane = C * ldk;
-        CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->z_limbs * plane, C * ldD * 8)));  // T is dead: reuse
-        int8_t* zp = ctx->w[2].as<int8_t>();
-        LAUNCH(qf_launch_split_f64_limbs(Z, ldD, zp, plane, ldk, Bc, (int)D, ctx->z_limbs, ctx->dFlag.as<int>(), ctx->stream));
+        int8_t* zp;
         I8GemmArgs g{};
+        if (ctx->use_ozaki) {
+            zp = ctx->w[8].as<int8_t>();  // digits were produced block by block during the recursion
+            g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = (int)((ctx->chunk + 127) / 128); g.nz_kb_total = (int)(ldk / 128);
+        } else {
+            CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->z_limbs * plane, C * ldD * 8)));  // T is dead: reuse
+            zp = ctx->w[2].as<int8_t>();
+            LAUNCH(qf_launch_split_f64_limbs(Z, ldD, zp, plane, ldk, Bc, (int)D, ctx->z_limbs, ctx->dFlag.as<int>(), nullptr, 0,
+                                             0, 0, ctx->stream));
+        }
         g.x = zp; g.ldx = ldk; g.x_plane = plane;
         g.w = ctx->dSl.p; g.ldw = ldk; g.w_plane = D * ldk;
         g.LX = ctx->z_limbs; g.LW = ctx->s_limbs; g.w_signed = 1;
@@ -846,6 +893,20 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
         if (ctx->z_limbs + ctx->s_limbs - 1 > 16) return ctx->fail(QF_ERR_UNSUPPORTED, "too many digits for the int8 S*z product");
         ctx->zlimit = std::min(ctx->zlimit, limb_capacity(ctx->z_limbs));
         QF_TRY(upload_limbs(ctx, s, D, D, ctx->ldk_dim, ctx->s_limbs, true, ctx->dSl));
+        const char* env = getenv("QF_DISABLE_OZAKI");
+        const char* envmin = getenv("QF_OZAKI_MIN_DIM");
+        const long min_dim = envmin ? atol(envmin) : 2 * NP_SIZES[2];
+        ctx->use_ozaki = D > std::max(min_dim, NP_SIZES[2]) && ctx->z_limbs + ctx->u_limbs - 1 <= 16 && !(env && env[0] == '1');
+        if (ctx->use_ozaki) {
+            const long nblk = (D + NP_SIZES[2] - 1) / NP_SIZES[2];
+            CK(ctx->dUscale.ensure((size_t)nblk * D * 8));
+            CK(ctx->dUl.ensure((size_t)ctx->u_limbs * D * ctx->ldk_dim));
+            CK(cudaMemsetAsync(ctx->dUl.p, 0, (size_t)ctx->u_limbs * D * ctx->ldk_dim, ctx->stream));
+            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], ctx->u_limbs,
+                                           ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
+                                           ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
     }
     ctx->has_np = true;
     return QF_OK;

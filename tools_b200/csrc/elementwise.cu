@@ -336,18 +336,23 @@ cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream
 // [-128 S, 127 S], S = (256^L - 1)/255.  planes: L matrices of B x ldk bytes.
 namespace {
 
-__device__ __forceinline__ void split_digits(long long v, int L, int8_t* planes, long plane_stride, long off, int* flag) {
+// nz (optional): zero-tile map, nz[l * nz_plane + nz_idx] = 1 when digit l is non-zero (benign race: all writers store 1)
+__device__ __forceinline__ void split_digits(long long v, int L, int8_t* planes, long plane_stride, long off, int* flag,
+                                             uint8_t* nz = nullptr, long nz_plane = 0, long nz_idx = 0) {
     for (int l = 0; l < L - 1; ++l) {
         long long lo = ((v + 128) & 255) - 128;
         planes[l * plane_stride + off] = (int8_t)lo;
+        if (nz && lo != 0 && !nz[l * nz_plane + nz_idx]) nz[l * nz_plane + nz_idx] = 1;
         v = (v - lo) >> 8;
     }
     if ((v > 127 || v < -128) && flag) atomicOr(flag, 8);
     planes[(L - 1) * plane_stride + off] = (int8_t)v;
+    if (nz && v != 0 && !nz[(L - 1) * nz_plane + nz_idx]) nz[(L - 1) * nz_plane + nz_idx] = 1;
 }
 
 __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin, int8_t* __restrict__ planes,
-                                       long plane_stride, long ldk, int B, int M, int L, int* flag) {
+                                       long plane_stride, long ldk, int B, int M, int L, int* flag, uint8_t* nz,
+                                       int nz_m_tiles, int nz_kb_total, int col0) {
     long total = (long)B * M;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         long b = i / M;
@@ -357,13 +362,15 @@ __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin,
             if (flag) atomicOr(flag, 8);
             v = 0;
         }
-        split_digits(__double2ll_rn(v), L, planes, plane_stride, b * ldk + j, flag);
+        split_digits(__double2ll_rn(v), L, planes, plane_stride, b * ldk + j, flag, nz, (long)nz_m_tiles * nz_kb_total,
+                     (b >> 7) * nz_kb_total + ((col0 + j) >> 7));
     }
 }
 
 __global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __restrict__ planes,
                                        long plane_stride, long ldk, int B, int M, int L,
-                                       unsigned long long* __restrict__ norm2) {
+                                       unsigned long long* __restrict__ norm2, uint8_t* nz, int nz_m_tiles,
+                                       int nz_kb_total) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (long b = (long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long)gridDim.x * wpb) {
@@ -373,7 +380,8 @@ __global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin
             long long v = src[j];
             acc += (unsigned long long)(v * v);
             // out-of-range entries belong to out-of-domain targets (flagged through norm2): saturate silently
-            split_digits(v, L, planes, plane_stride, b * ldk + j, nullptr);
+            split_digits(v, L, planes, plane_stride, b * ldk + j, nullptr, nz, (long)nz_m_tiles * nz_kb_total,
+                         (b >> 7) * nz_kb_total + (j >> 7));
         }
         if (norm2) {
 #pragma unroll
@@ -396,16 +404,19 @@ __global__ void add_cols_i32_kernel(int32_t* __restrict__ e, long lde, const dou
 }  // namespace
 
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
-                                      int M, int L, int* flag, cudaStream_t stream) {
+                                      int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
+                                      cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     split_f64_limbs_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk, B, M,
-                                                                               L, flag);
+                                                                               L, flag, nz, nz_m_tiles, nz_kb_total, col0);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
-                                      int M, int L, unsigned long long* norm2, cudaStream_t stream) {
+                                      int M, int L, unsigned long long* norm2, uint8_t* nz, int nz_m_tiles,
+                                      int nz_kb_total, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    split_i32_limbs_kernel<<<grid_for(B, TPB / 32), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk, B, M, L, norm2);
+    split_i32_limbs_kernel<<<grid_for(B, TPB / 32), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk, B, M, L, norm2,
+                                                                      nz, nz_m_tiles, nz_kb_total);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,

@@ -43,6 +43,11 @@ struct I8Params {
     const int64_t* base; long ldbase;
     void* out; long ldout;
     int* flag;
+    const double* scale;        // out_kind 3: out[b][n] -= V * scale[n]
+    // L2-aware rasterisation of the 1-D grid: groups of group_m target tiles, n fastest across groups
+    int m_tiles, n_tiles, group_m;
+    // optional zero-tile map of the x digit planes: nz[(j * m_tiles_total + m_tile) * kb_total + kb_off + kb]
+    const uint8_t* x_nz; int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,10 +120,28 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* tmem_full = bars + 2 * p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
 
+    uint32_t* inited_slot = tmem_slot + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * p.nt, m0 = blockIdx.y * TILE_M;
+    // tile rasterisation: consecutive CTAs walk group_m target tiles for one n tile, then the next n tile
+    int tile_m, tile_n;
+    {
+        const int t = blockIdx.x, per_group = p.group_m * p.n_tiles;
+        const int g = t / per_group, r = t - g * per_group;
+        const int gm = min(p.group_m, p.m_tiles - g * p.group_m);  // last group may be short
+        tile_m = g * p.group_m + r % gm;
+        tile_n = r / gm;
+    }
+    const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int ND = p.LX + p.LW - 1;
+    // which x digit planes are non-zero in this (target tile, k block)? (bit j of the returned mask)
+    auto plane_mask = [&](int kb) -> uint32_t {
+        if (!p.x_nz) return (1u << p.LX) - 1u;
+        uint32_t mk = 0;
+        for (int j = 0; j < p.LX; ++j)
+            if (p.x_nz[((size_t)j * p.nz_m_tiles + (p.nz_m_off + tile_m)) * p.nz_kb_total + p.nz_kb_off + kb]) mk |= 1u << j;
+        return mk;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -143,12 +166,18 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
+                const uint32_t mk = plane_mask(kb);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sx = smem + (size_t)stage * stage_bytes;
                 uint8_t* sw = sx + p.LX * x_tile;
-                mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                for (int j = 0; j < p.LX; ++j) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
-                for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                if (mk == 0) {  // nothing to multiply in this k block: just hand the stage over
+                    mbar_expect_tx(&full_bar[stage], 0);
+                } else {
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mk) * x_tile + p.LW * w_tile));
+                    for (int j = 0; j < p.LX; ++j)
+                        if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
+                    for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -160,6 +189,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0, inited = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
+            const uint32_t mk = plane_mask(kb);
             mbar_wait(&full_bar[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
@@ -167,6 +197,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const uint32_t sw = sx + p.LX * x_tile;
                 for (int i = 0; i < p.LW; ++i) {
                     for (int j = 0; j < p.LX; ++j) {
+                        if (!((mk >> j) & 1u)) continue;
                         const int d = i + j;
                         const uint64_t da = make_desc(sx + j * x_tile), db = make_desc(sw + i * w_tile);
 #pragma unroll
@@ -179,7 +210,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
                 mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
-                if (kb == num_kb - 1) mma_commit(tmem_full);
+                if (kb == num_kb - 1) {
+                    *inited_slot = inited;  // accumulators never written stay undefined: the epilogue skips them
+                    __threadfence_block();
+                    mma_commit(tmem_full);
+                }
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -191,11 +226,13 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + lg * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const uint32_t inited = *(volatile uint32_t*)inited_slot;
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
             __int128 v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0;
             for (int d = 0; d < ND; ++d) {
+                if (!((inited >> d) & 1u)) continue;  // warp-uniform
                 int32_t t[16];
                 tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -224,8 +261,16 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             val = 0;
                         }
                         ((int32_t*)p.out)[(long)row * p.ldout + n] = (int32_t)(long long)val;
-                    } else {
+                    } else if (p.out_kind == 2) {
                         ((double*)p.out)[(long)row * p.ldout + n] += (double)(long long)val;
+                    } else {
+                        // |val| may exceed 2^63: convert the 128-bit integer through its two halves
+                        const bool neg = val < 0;
+                        const unsigned __int128 a = neg ? (unsigned __int128)(-val) : (unsigned __int128)val;
+                        double dv = (double)(unsigned long long)(a >> 64) * 18446744073709551616.0 +
+                                    (double)(unsigned long long)a;
+                        if (neg) dv = -dv;
+                        ((double*)p.out)[(long)row * p.ldout + n] -= dv * p.scale[n];
                     }
                 }
             }
@@ -291,9 +336,22 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     I8Params p{};
     p.B = a.B; p.N = a.N; p.K = a.K; p.LX = a.LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
     p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
-    p.ldout = a.ldout; p.flag = a.flag;
+    p.ldout = a.ldout; p.flag = a.flag; p.scale = a.scale;
+    p.m_tiles = (a.B + TILE_M - 1) / TILE_M;
+    p.n_tiles = (a.N + nt - 1) / nt;
+    {
+        // one wave (148 CTAs) should touch group_m x-tiles and 148/group_m w-tiles with minimal bytes:
+        // group_m = sqrt(148 * w_tile / x_tile)
+        const double xt = (double)a.LX * TILE_M, wt = (double)a.LW * nt;
+        int gm = (int)(sqrt(148.0 * wt / xt) + 0.5);
+        if (gm < 1) gm = 1;
+        if (gm > p.m_tiles) gm = p.m_tiles;
+        p.group_m = gm;
+    }
+    p.x_nz = a.x_nz; p.nz_m_tiles = a.nz_m_tiles; p.nz_kb_total = a.nz_kb_total; p.nz_kb_off = a.nz_kb_off;
+    p.nz_m_off = a.nz_m_off;
     const int stage_bytes = a.LX * TILE_M * BLOCK_K + a.LW * nt * BLOCK_K;
-    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;  // barriers + tmem slot + inited mask
     int stages = budget / stage_bytes;
     if (stages < 2) return cudaErrorInvalidValue;
     if (stages > 8) stages = 8;
@@ -308,7 +366,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    dim3 grid((a.N + nt - 1) / nt, (a.B + TILE_M - 1) / TILE_M);
+    dim3 grid((unsigned)(p.m_tiles * p.n_tiles));
     gemm_i8_kernel<<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
     return cudaGetLastError();
 }

@@ -120,16 +120,28 @@ struct I8GemmArgs {
     void* out;
     long ldout;
     int* flag;
+    const double* scale;   // out_kind 3: out[b][n] -= V * scale[n]  (fp64)
+    // optional zero-tile map of x: nz[(j * nz_m_tiles + nz_m_off + m_tile) * nz_kb_total + nz_kb_off + kb] != 0
+    // iff digit plane j has a non-zero byte in that 128-target x 128-column tile (K offset must be 128-aligned)
+    const uint8_t* x_nz;
+    int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
 };
 int qf_i8_tile_n(int LX, int LW, int N);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
 
 // ---- limb splitting (elementwise.cu) ---------------------------------------------------------
 // balanced s8 digits; *flag |= 8 when a value does not fit L digits
+// nz (optional, pre-zeroed): zero-tile map [L][nz_m_tiles][nz_kb_total] over 128-target x 128-column tiles;
+// col0 = global column of in[.][0] (the planes pointer is already offset by col0)
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
-                                      int M, int L, int* flag, cudaStream_t stream);
+                                      int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
+                                      cudaStream_t stream);
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
-                                      int M, int L, unsigned long long* norm2, cudaStream_t stream);
+                                      int M, int L, unsigned long long* norm2, uint8_t* nz, int nz_m_tiles,
+                                      int nz_kb_total, cudaStream_t stream);
 // e[b][cols[j]] += (int32) sol[b][j]
 cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
                                    int B, cudaStream_t stream);
+// fixed-point digit planes of U for the tensor-core nearest-plane updates (see setup.cu)
+cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int L, double* scale, int8_t* planes,
+                                    long plane_stride, long ldk, cudaStream_t stream);

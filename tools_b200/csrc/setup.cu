@@ -81,3 +81,63 @@ cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams
     make_dg_kernel<<<(count + 127) / 128, 128, 0, stream>>>(d, count, s, dg);
     return cudaGetLastError();
 }
+
+// ---- fixed-point digit planes of the mu-coefficients for the tensor-core nearest-plane updates ----
+// For every row i and every `blk`-column block c with i < c*blk (the entries the big off-diagonal
+// updates use): U[i][j] * 2^e(i,c) rounded to an integer of L balanced base-256 digits;
+// scale[c*D + i] = 2^-e(i,c).  Rows at or below the block keep zero digits.
+namespace {
+
+__global__ void ozaki_scale_kernel(const double* __restrict__ U, long ld, int D, int blk, int L, double* __restrict__ scale) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int nblk = (D + blk - 1) / blk;
+    const long total = (long)D * nblk;
+    for (long w = (long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long)gridDim.x * wpb) {
+        const int c = (int)(w / D), i = (int)(w - (long)c * D);
+        double mx = 0.0;
+        if (i < c * blk) {
+            const int j1 = min(D, (c + 1) * blk);
+            for (int j = c * blk + lane; j < j1; j += 32) mx = fmax(mx, fabs(U[(long)i * ld + j]));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+            // |U| 2^e < 2^(8L-2)  (capacity of L balanced digits is ~0.498 * 256^L)
+            int e = (mx > 0.0) ? (8 * L - 2) - (ilogb(mx) + 1) : 0;
+            scale[(long)c * D + i] = ldexp(1.0, -e);
+        }
+    }
+}
+
+__global__ void ozaki_digits_kernel(const double* __restrict__ U, long ld, int D, int blk, int L,
+                                    const double* __restrict__ scale, int8_t* __restrict__ planes, long plane_stride,
+                                    long ldk) {
+    const long total = (long)D * D;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / D), j = (int)(t - (long)i * D);
+        const int c = j / blk;
+        long long v = 0;
+        if (i < c * blk) v = __double2ll_rn(U[(long)i * ld + j] / scale[(long)c * D + i]);
+        for (int l = 0; l < L; ++l) {
+            long long lo = ((v + 128) & 255) - 128;
+            if (l == L - 1) lo = v;
+            planes[l * plane_stride + (long)i * ldk + j] = (int8_t)lo;
+            v = (v - lo) >> 8;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int L, double* scale, int8_t* planes,
+                                    long plane_stride, long ldk, cudaStream_t stream) {
+    const int nblk = (D + blk - 1) / blk;
+    long long warps = (long long)D * nblk;
+    long long g = (warps + 7) / 8;
+    if (g > 148 * 32) g = 148 * 32;
+    ozaki_scale_kernel<<<(int)g, 256, 0, stream>>>(U, ld, D, blk, L, scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ozaki_digits_kernel<<<148 * 16, 256, 0, stream>>>(U, ld, D, blk, L, scale, planes, plane_stride, ldk);
+    return cudaGetLastError();
+}
