@@ -107,6 +107,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const int z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        ::"r"(taddr), "r"(z)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(I8_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -120,7 +128,6 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* tmem_full = bars + 2 * p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
 
-    uint32_t* inited_slot = tmem_slot + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile rasterisation: consecutive CTAs walk group_m target tiles for one n tile, then the next n tile
     int tile_m, tile_n;
@@ -159,6 +166,16 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // zero every accumulator so that all MMAs can accumulate: one MMA then covers several digit planes of w
+    // (N = g * nt) whose accumulators D_{j+i0} .. D_{j+i0+g-1} are adjacent column blocks
+    if (warp >= 2) {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -183,38 +200,35 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        // instruction descriptor: D = s32, A = s8 (x limbs), B = u8/s8 (w limbs), K-major both, M = 128, N = nt
-        const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(p.w_signed ? 1 : 0) << 10) |
-                               ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        // instruction descriptor: D = s32, A = s8 (x digits), B = u8/s8 (w digits), K-major both, M = 128;
+        // N = g * nt covers g adjacent digit planes of w (their smem tiles and their accumulators are contiguous)
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | ((uint32_t)(p.w_signed ? 1 : 0) << 10) | ((uint32_t)(TILE_M >> 4) << 24);
+        const int G = max(1, min(p.LW, 256 / p.nt));
+        const uint64_t desc0 = make_desc(smem_u32(smem));
         int stage = 0;
-        uint32_t phase = 0, inited = 0;
+        uint32_t phase = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             const uint32_t mk = plane_mask(kb);
             mbar_wait(&full_bar[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t sx = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sw = sx + p.LX * x_tile;
-                for (int i = 0; i < p.LW; ++i) {
-                    for (int j = 0; j < p.LX; ++j) {
-                        if (!((mk >> j) & 1u)) continue;
-                        const int d = i + j;
-                        const uint64_t da = make_desc(sx + j * x_tile), db = make_desc(sw + i * w_tile);
+                const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
+                const uint32_t sw_off = sx_off + ((uint32_t)(p.LX * x_tile) >> 4);
+                for (int j = 0; j < p.LX; ++j) {
+                    if (!((mk >> j) & 1u)) continue;
+                    const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
+                    for (int i0 = 0; i0 < p.LW; i0 += G) {
+                        const int g = min(G, p.LW - i0);
+                        const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
+                        const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
+                        const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
 #pragma unroll
-                        for (int kk = 0; kk < BLOCK_K / 32; ++kk) {
-                            const uint32_t acc = (kk > 0 || ((inited >> d) & 1u)) ? 1u : 0u;
-                            // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                            mma_i8(tmem_base + (uint32_t)(d * p.nt), da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc);
-                        }
-                        inited |= 1u << d;
+                        for (int kk = 0; kk < BLOCK_K / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
+                            mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
                     }
                 }
                 mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
-                if (kb == num_kb - 1) {
-                    *inited_slot = inited;  // accumulators never written stay undefined: the epilogue skips them
-                    __threadfence_block();
-                    mma_commit(tmem_full);
-                }
+                if (kb == num_kb - 1) mma_commit(tmem_full);
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -226,13 +240,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + lg * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        const uint32_t inited = *(volatile uint32_t*)inited_slot;
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
             __int128 v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0;
             for (int d = 0; d < ND; ++d) {
-                if (!((inited >> d) & 1u)) continue;  // warp-uniform
                 int32_t t[16];
                 tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
