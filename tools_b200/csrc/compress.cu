@@ -16,14 +16,23 @@ namespace {
 struct CParams {
     uint32_t q, d, half_q, mask, round;
     unsigned long long magic;  // ceil(2^64 / q)
+    uint32_t magic32;          // ceil(2^(32+sh) / q) for the 32-bit path
+    uint32_t sh;
+    uint32_t narrow;           // 1: numerator < 2^28, the 32-bit multiply-high is exact
 };
 
 __device__ __forceinline__ uint32_t comp1(uint32_t x, const CParams& p) {
+    if (p.narrow) {
+        // num < 2^28, magic32 = ceil(2^(32+sh)/q) with 2^sh <= q: floor(num * magic32 / 2^(32+sh)) is exact
+        // because the excess num * (magic32 q - 2^(32+sh)) / (q 2^(32+sh)) < 2^28 / 2^32 / ... < 1/q
+        const uint32_t num = (x << p.d) + p.half_q;
+        return (__umulhi(num, p.magic32) >> p.sh) & p.mask;
+    }
     unsigned long long num = ((unsigned long long)x << p.d) + p.half_q;
     return (uint32_t)__umul64hi(num, p.magic) & p.mask;
 }
 __device__ __forceinline__ uint32_t decomp1(uint32_t y, const CParams& p) {
-    return (uint32_t)(((unsigned long long)y * p.q + p.round) >> p.d);
+    return (y * p.q + p.round) >> p.d;  // y, q < 2^16: fits 32 bits
 }
 
 template <bool DEC>
@@ -91,6 +100,18 @@ cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t cou
     p.q = q; p.d = d; p.half_q = q / 2; p.mask = (d >= 32) ? 0xffffffffu : ((1u << d) - 1);
     p.round = 1u << (d - 1);
     p.magic = ~0ull / q + 1;  // ceil(2^64/q) for q not a power of two; exact quotient otherwise as well
+    {
+        // 32-bit path: exact when num = x 2^d + q/2 < 2^n_bits and e * num < 2^(32+sh) with e = magic32 q - 2^(32+sh) < q
+        uint32_t sh = 0;
+        while ((2u << sh) <= q) ++sh;  // 2^sh <= q < 2^(sh+1)
+        const unsigned long long pw = 1ull << (32 + sh);
+        const unsigned long long m32 = (pw + q - 1) / q;  // < 2^33 / ... fits 32 bits since q >= 2^sh
+        const unsigned long long e = m32 * q - pw;
+        const unsigned long long num_max = ((unsigned long long)(q - 1) << d) + q / 2;
+        p.sh = sh;
+        p.magic32 = (uint32_t)m32;
+        p.narrow = (m32 <= 0xffffffffull && num_max <= 0xffffffffull && e * num_max < pw) ? 1u : 0u;
+    }
     size_t nvec = count / 8;
     size_t want = (nvec + 2 * 256 - 1) / (2 * 256);
     int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
