@@ -418,7 +418,8 @@ def _ring_s(n):
     return ((2 * 2 * 1.005 * np.sqrt(n) + 1) * 2) * 4  # gpv_ring.rs:296-298
 
 
-@pytest.mark.parametrize("n,q", [(64, 3329), (256, 3329), (128, 7681), (64, 2**31 - 1), (8, 1024), (5, 256), (6, 128)])
+@pytest.mark.parametrize("n,q", [(64, 3329), (256, 3329), (128, 7681), (256, 7681), (512, 12289), (1024, 12289),
+                                 (64, 257), (64, 2**31 - 1), (256, 2**24), (8, 1024), (5, 256), (6, 128)])
 def test_ring_f_a_bit_exact(T, n, q):
     rng = np.random.default_rng(n)
     gp = T.GadgetParametersRing.init_default(n, q)

@@ -101,8 +101,10 @@ struct qf_ctx {
     int z_nchunks = 1, z_bits = 0;
     double zlimit = 0;
     // ring key
-    bool has_ring = false, ring_ntt = false;
-    Dev dAhat, dTw, dAraw;
+    bool has_ring = false, ring_ntt = false, ring_small = false;
+    int ring_d = 1;
+    uint32_t ring_np_inv = 0;
+    Dev dAhat, dTw, dAraw, dAhat32, dTw32;
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];
@@ -359,7 +361,11 @@ qf_status ring_f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU
         CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
         out = ctx->w[1].as<int64_t>();
     }
-    if (ctx->ring_ntt)
+    if (ctx->ring_small)
+        LAUNCH(qf_launch_ring_small(dSigma, ctx->dAhat32.as<uint32_t>(), out, ctx->dNorm.as<unsigned long long>(), Bc, npoly,
+                                    (int)ctx->n, ctx->ring_d, ctx->prm.q, ctx->ring_np_inv, ctx->dTw32.as<uint32_t>(),
+                                    ctx->stream));
+    else if (ctx->ring_ntt)
         LAUNCH(qf_launch_ring_f_a(dSigma, ctx->dAhat.as<uint64_t>(), out, ctx->dNorm.as<unsigned long long>(), Bc, npoly,
                                   (int)ctx->n, ctx->prm.q, ctx->dTw.as<uint64_t>(), ctx->stream));
     else
@@ -922,6 +928,24 @@ qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a) {
     ctx->hAring.assign(a, a + n * np);
     CK(ctx->dAraw.ensure((size_t)n * np * 8));
     CK(cudaMemcpy(ctx->dAraw.p, a, (size_t)n * np * 8, cudaMemcpyHostToDevice));
+    {
+        // word-size NTT-friendly prime (3329, 7681, 12289 ...): transform directly mod q
+        std::vector<uint32_t> tables;
+        int d = 1;
+        uint32_t np_inv = 0;
+        const char* env = getenv("QF_DISABLE_SMALL_NTT");
+        ctx->ring_small = !(env && env[0] == '1') && qf_ring_small_plan(ctx->prm.q, (int)n, &d, &tables, &np_inv) != 0;
+        if (ctx->ring_small) {
+            ctx->ring_d = d;
+            ctx->ring_np_inv = np_inv;
+            std::vector<uint32_t> ah((size_t)n * np);
+            qf_ring_small_key(a, (int)np, (int)n, d, ctx->prm.q, tables.data(), ah.data());
+            CK(ctx->dTw32.ensure(tables.size() * 4));
+            CK(cudaMemcpy(ctx->dTw32.p, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice));
+            CK(ctx->dAhat32.ensure(ah.size() * 4));
+            CK(cudaMemcpy(ctx->dAhat32.p, ah.data(), ah.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     ctx->ring_ntt = (n >= 64) && ((n & (n - 1)) == 0) && n <= 2048;
     if (ctx->ring_ntt) {
         // exactness of the integer product: npoly * n * (q/2) * max|sigma| < 2^63

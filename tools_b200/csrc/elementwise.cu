@@ -350,14 +350,13 @@ __device__ __forceinline__ void split_digits(long long v, int L, int8_t* planes,
     if (nz && v != 0 && !nz[(L - 1) * nz_plane + nz_idx]) nz[(L - 1) * nz_plane + nz_idx] = 1;
 }
 
-// 4 consecutive columns per thread: one vector load, one char4 store per digit plane, one zero-tile probe per
-// digit (the 4 columns share a 128-column tile because col0 and ldk are multiples of 4 here).
-template <typename LoadT>
+// One warp per target row, 128 columns (= one zero-tile) per warp iteration, 4 consecutive columns per lane:
+// one vector load, one char4 store per digit plane, and one warp vote per digit for the zero-tile map
+// (no global reads on the flag path).  col0 and ldk are multiples of 128 / 4 for every caller.
 __device__ __forceinline__ void split4(const long long v[4], int L, int8_t* planes, long plane_stride, long off, int* flag,
-                                       uint8_t* nz, long nz_plane, long nz_idx, int valid) {
+                                       uint8_t* nz, long nz_plane, long nz_idx, int valid, int lane) {
     long long w[4] = {v[0], v[1], v[2], v[3]};
     for (int l = 0; l < L; ++l) {
-        char4 d;
         int8_t dd[4];
         bool any = false;
 #pragma unroll
@@ -371,37 +370,51 @@ __device__ __forceinline__ void split4(const long long v[4], int L, int8_t* plan
             any |= (t < valid) && (dd[t] != 0);
             w[t] = (w[t] - lo) >> 8;
         }
-        d.x = dd[0]; d.y = dd[1]; d.z = dd[2]; d.w = dd[3];
         if (valid == 4) {
+            char4 d;
+            d.x = dd[0]; d.y = dd[1]; d.z = dd[2]; d.w = dd[3];
             *reinterpret_cast<char4*>(planes + l * plane_stride + off) = d;
         } else {
             for (int t = 0; t < valid; ++t) planes[l * plane_stride + off + t] = dd[t];
         }
-        if (nz && any && !nz[l * nz_plane + nz_idx]) nz[l * nz_plane + nz_idx] = 1;
+        if (nz) {
+            const bool warp_any = __any_sync(0xffffffffu, any);
+            if (warp_any && lane == 0) nz[l * nz_plane + nz_idx] = 1;
+        }
     }
 }
 
 __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin, int8_t* __restrict__ planes,
                                        long plane_stride, long ldk, int B, int M, int L, int* flag, uint8_t* nz,
                                        int nz_m_tiles, int nz_kb_total, int col0) {
-    const int M4 = (M + 3) >> 2;
-    long total = (long)B * M4;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        long b = i / M4;
-        int j = (int)(i - b * M4) << 2;
-        const int valid = min(4, M - j);
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int iters = (M + 127) >> 7;
+    const long total = (long)B * iters;  // (row, 128-column tile) pairs, one per warp iteration
+    for (long w = (long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long)gridDim.x * wpb) {
+        const long b = w / iters;
+        const int j = ((int)(w - b * iters) << 7) + lane * 4;
+        const int valid = max(0, min(4, M - j));
         long long v[4] = {0, 0, 0, 0};
         const double* src = in + b * ldin + j;
-        for (int t = 0; t < valid; ++t) {
-            double x = src[t];
-            if (!(fabs(x) < 9.0e18)) {
-                if (flag) atomicOr(flag, 8);
-                x = 0;
+        if (valid == 4 && ((((uintptr_t)src) & 15) == 0)) {
+            const double2 a0 = *reinterpret_cast<const double2*>(src), a1 = *reinterpret_cast<const double2*>(src + 2);
+            const double x[4] = {a0.x, a0.y, a1.x, a1.y};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                double xx = x[t];
+                if (!(fabs(xx) < 9.0e18)) { if (flag) atomicOr(flag, 8); xx = 0; }
+                v[t] = __double2ll_rn(xx);
             }
-            v[t] = __double2ll_rn(x);
+        } else {
+            for (int t = 0; t < valid; ++t) {
+                double xx = src[t];
+                if (!(fabs(xx) < 9.0e18)) { if (flag) atomicOr(flag, 8); xx = 0; }
+                v[t] = __double2ll_rn(xx);
+            }
         }
-        split4<double>(v, L, planes, plane_stride, b * ldk + j, flag, nz, (long)nz_m_tiles * nz_kb_total,
-                       (b >> 7) * nz_kb_total + ((col0 + j) >> 7), valid);
+        split4(v, L, planes, plane_stride, b * ldk + j, flag, nz, (long)nz_m_tiles * nz_kb_total,
+               (b >> 7) * nz_kb_total + ((col0 + j) >> 7), valid, lane);
     }
 }
 
@@ -412,11 +425,13 @@ __global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const bool vec = ((ldin & 3) == 0) && ((((uintptr_t)in) & 15) == 0);
+    const int iters = (M + 127) >> 7;
     for (long b = (long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long)gridDim.x * wpb) {
         const int32_t* src = in + b * ldin;
         unsigned long long acc = 0;
-        for (int j = lane * 4; j < M; j += 128) {
-            const int valid = min(4, M - j);
+        for (int it = 0; it < iters; ++it) {
+            const int j = (it << 7) + lane * 4;
+            const int valid = max(0, min(4, M - j));
             long long v[4] = {0, 0, 0, 0};
             if (valid == 4 && vec) {
                 int4 q4 = *reinterpret_cast<const int4*>(src + j);
@@ -427,8 +442,8 @@ __global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc += (unsigned long long)(v[t] * v[t]);
             // out-of-range entries belong to out-of-domain targets (flagged through norm2): no range flag here
-            split4<int>(v, L, planes, plane_stride, b * ldk + j, nullptr, nz, (long)nz_m_tiles * nz_kb_total,
-                        (b >> 7) * nz_kb_total + (j >> 7), valid);
+            split4(v, L, planes, plane_stride, b * ldk + j, nullptr, nz, (long)nz_m_tiles * nz_kb_total,
+                   (b >> 7) * nz_kb_total + (j >> 7), valid, lane);
         }
         if (norm2) {
 #pragma unroll
@@ -456,9 +471,9 @@ cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* plane
     if (B <= 0) return cudaSuccess;
     // char4 stores need 4-byte aligned plane addresses: planes pointer, ldk and col0 multiples of 4 (true for all callers)
     if ((((uintptr_t)planes) & 3) || (ldk & 3) || (col0 & 3)) return cudaErrorMisalignedAddress;
-    split_f64_limbs_kernel<<<grid_for((long long)B * ((M + 3) / 4), TPB), TPB, 0, stream>>>(in, ldin, planes, plane_stride, ldk,
-                                                                                           B, M, L, flag, nz, nz_m_tiles,
-                                                                                           nz_kb_total, col0);
+    if (nz && (col0 & 127)) return cudaErrorInvalidValue;
+    split_f64_limbs_kernel<<<grid_for((long long)B * ((M + 127) / 128), TPB / 32), TPB, 0, stream>>>(
+        in, ldin, planes, plane_stride, ldk, B, M, L, flag, nz, nz_m_tiles, nz_kb_total, col0);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,

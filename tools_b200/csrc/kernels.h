@@ -145,3 +145,14 @@ cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long
 // fixed-point digit planes of U for the tensor-core nearest-plane updates (see setup.cu)
 cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int L, double* scale, int8_t* planes,
                                     long plane_stride, long ldk, cudaStream_t stream);
+
+// ---- ring_small.cu : register/shuffle NTT mod q for NTT-friendly primes q < 2^16 ----------------
+#ifdef __cplusplus
+#include <vector>
+int qf_ring_small_plan(unsigned long long q, int n, int* d_out, std::vector<uint32_t>* tables, uint32_t* np_inv);
+#endif
+void qf_ring_small_key(const int64_t* a, int npoly, int n, int d, unsigned long long q, const uint32_t* tables,
+                       uint32_t* a_hat);
+cudaError_t qf_launch_ring_small(const int32_t* sigma, const uint32_t* a_hat, int64_t* out, unsigned long long* norm2,
+                                 int B, int npoly, int n, int d, unsigned long long q, uint32_t np_inv,
+                                 const uint32_t* tw, cudaStream_t stream);
