@@ -442,7 +442,7 @@ def test_ring_f_a_bit_exact(T, n, q):
     assert not psf.check_domain(np.zeros((gp.k + 1, n), dtype=np.int64))
     assert not psf.check_domain(np.zeros((gp.k + 3, n), dtype=np.int64))
     big = np.zeros((gp.k + 2, n), dtype=np.int64)
-    big[0, 0] = round(psf.s) * (gp.k + 2) * 8
+    big[0, 0] = round(psf.s) * (gp.k + 2) * 8 * max(1, n // 8)  # the reference uses n = 8 (gpv_ring.rs:436-439)
     assert not psf.check_domain(big)
     with pytest.raises(AssertionError):
         psf.f_a(a, big)

@@ -418,10 +418,41 @@ __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin,
     }
 }
 
-__global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __restrict__ planes,
-                                       long plane_stride, long ldk, int B, int M, int L,
-                                       unsigned long long* __restrict__ norm2, uint8_t* nz, int nz_m_tiles,
-                                       int nz_kb_total) {
+// 32-bit variant of split4 for int32 inputs (values beyond +-2^30 belong to out-of-domain targets: clamped)
+__device__ __forceinline__ void split4_i32(const int v[4], int L, int8_t* planes, long plane_stride, long off,
+                                           uint8_t* nz, long nz_plane, long nz_idx, int valid, int lane) {
+    int w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) w[t] = max(-(1 << 30), min(1 << 30, v[t]));
+    for (int l = 0; l < L; ++l) {
+        int dd[4];
+        int any = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int lo = ((w[t] + 128) & 255) - 128;
+            if (l == L - 1) lo = w[t];
+            dd[t] = lo;
+            any |= (t < valid) ? (lo & 255) : 0;
+            w[t] = (w[t] - lo) >> 8;
+        }
+        if (valid == 4) {
+            const unsigned pk = (dd[0] & 255) | ((dd[1] & 255) << 8) | ((dd[2] & 255) << 16) | ((unsigned)(dd[3] & 255) << 24);
+            *reinterpret_cast<unsigned*>(planes + l * plane_stride + off) = pk;
+        } else {
+            for (int t = 0; t < valid; ++t) planes[l * plane_stride + off + t] = (int8_t)dd[t];
+        }
+        if (nz) {
+            const bool warp_any = __any_sync(0xffffffffu, any != 0);
+            if (warp_any && lane == 0) nz[l * nz_plane + nz_idx] = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __restrict__ planes,
+                       long plane_stride, long ldk, int B, int M, int L,
+                       unsigned long long* __restrict__ norm2, uint8_t* nz, int nz_m_tiles,
+                       int nz_kb_total) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const bool vec = ((ldin & 3) == 0) && ((((uintptr_t)in) & 15) == 0);
@@ -429,21 +460,28 @@ __global__ void split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin
     for (long b = (long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long)gridDim.x * wpb) {
         const int32_t* src = in + b * ldin;
         unsigned long long acc = 0;
-        for (int it = 0; it < iters; ++it) {
+        const long nz_plane = (long)nz_m_tiles * nz_kb_total, nz_row = (b >> 7) * nz_kb_total;
+        int it = 0;
+        // two 128-column tiles per trip: both vector loads are issued before either is consumed
+        for (; it + 1 < iters && vec && ((it + 2) << 7) <= M; it += 2) {
+            const int j0 = (it << 7) + lane * 4, j1 = j0 + 128;
+            const int4 q0 = __ldcs(reinterpret_cast<const int4*>(src + j0));
+            const int4 q1 = __ldcs(reinterpret_cast<const int4*>(src + j1));
+            const int v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                acc += (unsigned long long)((long long)v0[t] * v0[t]) + (unsigned long long)((long long)v1[t] * v1[t]);
+            split4_i32(v0, L, planes, plane_stride, b * ldk + j0, nz, nz_plane, nz_row + (j0 >> 7), 4, lane);
+            split4_i32(v1, L, planes, plane_stride, b * ldk + j1, nz, nz_plane, nz_row + (j1 >> 7), 4, lane);
+        }
+        for (; it < iters; ++it) {
             const int j = (it << 7) + lane * 4;
             const int valid = max(0, min(4, M - j));
-            long long v[4] = {0, 0, 0, 0};
-            if (valid == 4 && vec) {
-                int4 q4 = *reinterpret_cast<const int4*>(src + j);
-                v[0] = q4.x; v[1] = q4.y; v[2] = q4.z; v[3] = q4.w;
-            } else {
-                for (int t = 0; t < valid; ++t) v[t] = src[j + t];
-            }
+            int v[4] = {0, 0, 0, 0};
+            for (int t = 0; t < valid; ++t) v[t] = src[j + t];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) acc += (unsigned long long)(v[t] * v[t]);
-            // out-of-range entries belong to out-of-domain targets (flagged through norm2): no range flag here
-            split4(v, L, planes, plane_stride, b * ldk + j, nullptr, nz, (long)nz_m_tiles * nz_kb_total,
-                   (b >> 7) * nz_kb_total + (j >> 7), valid, lane);
+            for (int t = 0; t < 4; ++t) acc += (unsigned long long)((long long)v[t] * v[t]);
+            split4_i32(v, L, planes, plane_stride, b * ldk + j, nz, nz_plane, nz_row + (j >> 7), valid, lane);
         }
         if (norm2) {
 #pragma unroll
