@@ -480,7 +480,11 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
                                              ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
                                              ctx->stream));
-            if (sub_lo > lo) {
+            if (sub_lo > lo && sub_hi - sub_lo < 512) {
+                // a thin block (the ragged last one): per-tile overheads dominate the tensor-core path, use fp64
+                LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
+                                (int)(sub_hi - sub_lo), -1.0, 1.0, 0));
+            } else if (sub_lo > lo) {
                 I8GemmArgs g{};
                 g.x = zp + sub_lo; g.ldx = ldk; g.x_plane = plane;
                 g.w = ctx->dUl.as<int8_t>() + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;

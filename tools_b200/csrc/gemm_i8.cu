@@ -107,6 +107,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
     const int z = 0;
     asm volatile(
@@ -240,6 +246,36 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + lg * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        if (p.out_kind == 3) {
+            // scaled fp64 update  out[b][n] -= V * scale[n]:  8 columns per trip, the old values are fetched
+            // first, all digit accumulators are read with one wait, and V = sum 256^d D_d is assembled from
+            // four exact 64-bit partial sums (4 digits each) instead of 128-bit arithmetic.
+            double* orow = (double*)p.out + (long)row * p.ldout;
+            for (int c0 = 0; c0 < p.nt; c0 += 8) {
+                double told[8];
+                const bool rv = row < p.B;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) told[c] = (rv && n0 + c0 + c < p.N) ? orow[n0 + c0 + c] : 0.0;
+                int32_t t[16][8];
+#pragma unroll
+                for (int d = 0; d < 16; ++d)
+                    if (d < ND) tmem_ld8(lane_addr + (uint32_t)(d * p.nt + c0), t[d]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    long long part[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int d = 0; d < 16; ++d)
+                        if (d < ND) part[d >> 2] += ((long long)t[d][c]) << (8 * (d & 3));
+                    double dv = (double)part[3];
+                    dv = fma(dv, 4294967296.0, (double)part[2]);
+                    dv = fma(dv, 4294967296.0, (double)part[1]);
+                    dv = fma(dv, 4294967296.0, (double)part[0]);
+                    const int n = n0 + c0 + c;
+                    if (rv && n < p.N) orow[n] = told[c] - dv * p.scale[n];
+                }
+            }
+        } else
         for (int c0 = 0; c0 < p.nt; c0 += 16) {
             __int128 v[16];
 #pragma unroll

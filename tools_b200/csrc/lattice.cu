@@ -67,49 +67,100 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
     }
 }
 
-constexpr int NP_TPB = 64;
+constexpr int NP_TARGETS = 32;   // targets per CTA
+constexpr int NP_TPB = 128;      // 4 lanes per target
 constexpr int NP_NB_MAX = 64;
+constexpr int NP_TS = 36;        // row stride of the centre tile (36 = 4 mod 16: conflict-free quad access)
 
+// One nb-wide diagonal block.  Three phases per CTA of 32 targets:
+//  0. stage the mu-block (transposed) and the 32 x nb tile of centres through shared memory (coalesced);
+//  1. ALL threads pre-generate, for every (target, coordinate), the first Philox block of that coordinate's
+//     stream turned into two proposals (two normals and the logs of two uniforms): the expensive
+//     transcendental work does not depend on the centres, so it leaves the sequential chain;
+//  2. the recursion i = nb-1 .. 0 with 4 lanes per target: accept / reject on the pre-generated proposals
+//     (a handful of flops), then a right-looking update c'_j -= mu_ji z_i of the remaining centres, the
+//     j's strided over the 4 lanes (independent FMAs instead of one dependent dot product).
+// Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
+// one-thread-per-target formulation.
 __global__ void __launch_bounds__(NP_TPB)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, int B, int j0, int nb, int dim, uint64_t seed,
                uint64_t first_target, double zlimit, int* flag) {
     extern __shared__ __align__(16) double np_sm[];
-    double* us = np_sm;                         // nb x nb mu-coefficients of the diagonal block
-    double* ts = np_sm + nb * nb;               // nb x (NP_TPB+1) centres, then samples
-    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(ts + nb * (NP_TPB + 1));
+    double* ust = np_sm;                                  // ust[c * nb + r] = U[j0+r][j0+c], c > r
+    double* ts = ust + nb * nb;                           // ts[i * NP_TS + t]
+    float4* rng = reinterpret_cast<float4*>(ts + nb * NP_TS);  // rng[i * NP_TARGETS + t] = (n0, n1, log u0, log u1)
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(rng + nb * NP_TARGETS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbe = min(nb, dim - j0);  // valid coordinates in this block
+    const int nbe = min(nb, dim - j0);
+    const long b0 = (long)blockIdx.x * NP_TARGETS;
     for (int i = tid; i < nb * nb; i += NP_TPB) {
-        int r = i / nb, c = i - r * nb;
-        us[i] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
+        const int r = i / nb, c = i - r * nb;  // coalesced read along c
+        ust[c * nb + r] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
     }
     for (int i = tid; i < nbe; i += NP_TPB) dgs[i] = dg_g[j0 + i];
-    const long b0 = (long)blockIdx.x * NP_TPB;
-    // stage T[b0 .. b0+TPB)[j0 .. j0+nb): each warp copies rows, lanes on coordinates (coalesced)
-    for (int r = warp; r < NP_TPB; r += NP_TPB / 32) {
-        long b = b0 + r;
+    for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
+        const long b = b0 + r;
         if (b < B)
-            for (int c = lane; c < nbe; c += 32) ts[c * (NP_TPB + 1) + r] = T[b * ldt + j0 + c];
+            for (int c = lane; c < nbe; c += 32) ts[c * NP_TS + r] = T[b * ldt + j0 + c];
+    }
+    // phase 1: first Philox block of every (target, coordinate) stream -> two proposals
+    for (int idx = tid; idx < nbe * NP_TARGETS; idx += NP_TPB) {
+        const int i = idx / NP_TARGETS, t = idx - i * NP_TARGETS;
+        const long b = b0 + t;
+        if (b >= B) continue;
+        Philox ph;
+        ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + i), QF_STREAM_NP);
+        float n0, n1;
+        ph.normal2(n0, n1);
+        const float u0 = ph.uniform24(), u1 = ph.uniform24();
+        rng[idx] = make_float4(n0, n1, __logf(u0), __logf(u1));
     }
     __syncthreads();
-    const long b = b0 + tid;
-    if (b < B) {
-        for (int ii = nbe - 1; ii >= 0; --ii) {
-            double cp = ts[ii * (NP_TPB + 1) + tid];
-            for (int jj = ii + 1; jj < nbe; ++jj) cp -= us[ii * nb + jj] * ts[jj * (NP_TPB + 1) + tid];
-            Philox rng;
-            rng.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), QF_STREAM_NP);
-            double z = sample_dgauss(dgs[ii], cp, rng);
-            if (!(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
-            ts[ii * (NP_TPB + 1) + tid] = z;
+    // phase 2
+    const int t = tid >> 2, qd = tid & 3;
+    const long b = b0 + t;
+    const bool live = b < B;
+    for (int ii = nbe - 1; ii >= 0; --ii) {
+        const double cp = ts[ii * NP_TS + t];
+        const DGaussParams dgp = dgs[ii];
+        const float4 pr = rng[ii * NP_TARGETS + t];
+        const double c_int = rint(cp);
+        const float c_frac = (float)(cp - c_int);
+        double z;
+        bool done = false;
+        {
+            float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
+            float d = x - c_frac;
+            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
+            if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
         }
+        if (!done) {
+            float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
+            float d = x - c_frac;
+            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
+            if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
+        }
+        if (!done && live) {  // both pre-generated proposals rejected: continue the stream from its second block
+            Philox ph;
+            ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), QF_STREAM_NP);
+            ph.c3 = 1;
+            z = sample_dgauss(dgp, cp, ph);
+        } else if (!done) {
+            z = 0.0;
+        }
+        if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
+        __syncwarp();
+        if (qd == 0) ts[ii * NP_TS + t] = z;
+        const double* ucol = ust + ii * nb;  // ucol[r] = U[j0+r][j0+ii]
+        for (int jj = qd; jj < ii; jj += 4) ts[jj * NP_TS + t] -= ucol[jj] * z;
+        __syncwarp();
     }
     __syncthreads();
-    for (int r = warp; r < NP_TPB; r += NP_TPB / 32) {
-        long bb = b0 + r;
+    for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
+        const long bb = b0 + r;
         if (bb < B)
-            for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[c * (NP_TPB + 1) + r];
+            for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[c * NP_TS + r];
     }
 }
 
@@ -140,8 +191,9 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
                               uint64_t first_target, double zlimit, int* flag, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
-    int grid = (B + NP_TPB - 1) / NP_TPB;
-    size_t smem = (size_t)(nb * nb + nb * (NP_TPB + 1)) * sizeof(double) + (size_t)nb * sizeof(DGaussParams);
+    int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
+    size_t smem = (size_t)(nb * nb + nb * NP_TS) * sizeof(double) + (size_t)nb * NP_TARGETS * sizeof(float4) +
+                  (size_t)nb * sizeof(DGaussParams);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
