@@ -88,7 +88,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                uint64_t first_target, double zlimit, int* flag) {
     extern __shared__ __align__(16) double np_sm[];
     double* ust = np_sm;                                  // ust[c * nb + r] = U[j0+r][j0+c], c > r
-    double* ts = ust + nb * nb;                           // ts[i * NP_TS + t]
+    double* ts = ust + ((nb * nb + 1) & ~1);              // ts[i * NP_TS + t]  (16-byte aligned)
     float4* rng = reinterpret_cast<float4*>(ts + nb * NP_TS);  // rng[i * NP_TARGETS + t] = (n0, n1, log u0, log u1)
     DGaussParams* dgs = reinterpret_cast<DGaussParams*>(rng + nb * NP_TARGETS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -192,7 +192,7 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
-    size_t smem = (size_t)(nb * nb + nb * NP_TS) * sizeof(double) + (size_t)nb * NP_TARGETS * sizeof(float4) +
+    size_t smem = (size_t)(((nb * nb + 1) & ~1) + nb * NP_TS) * sizeof(double) + (size_t)nb * NP_TARGETS * sizeof(float4) +
                   (size_t)nb * sizeof(DGaussParams);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
