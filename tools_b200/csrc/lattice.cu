@@ -68,7 +68,7 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
 }
 
 constexpr int NP_TARGETS = 32;   // targets per CTA
-constexpr int NP_TPB = 128;      // 4 lanes per target
+constexpr int NP_TPB = 512;      // phases 0/1 use all threads; phase 2 the first 128 (4 lanes per target)
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = 36;        // row stride of the centre tile (36 = 4 mod 16: conflict-free quad access)
 
@@ -117,10 +117,11 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         rng[idx] = make_float4(n0, n1, __logf(u0), __logf(u1));
     }
     __syncthreads();
-    // phase 2
-    const int t = tid >> 2, qd = tid & 3;
+    // phase 2 (first 4 warps; the others wait at the barrier below)
+    const int t = (tid >> 2) & (NP_TARGETS - 1), qd = tid & 3;
     const long b = b0 + t;
     const bool live = b < B;
+    if (tid < 4 * NP_TARGETS)
     for (int ii = nbe - 1; ii >= 0; --ii) {
         const double cp = ts[ii * NP_TS + t];
         const DGaussParams dgp = dgs[ii];
