@@ -117,45 +117,55 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         rng[idx] = make_float4(n0, n1, __logf(u0), __logf(u1));
     }
     __syncthreads();
-    // phase 2 (first 4 warps; the others wait at the barrier below)
+    // phase 2 (first 4 warps; the others wait at the barrier below).  Lane qd of a target's quad keeps the
+    // centres of coordinates 4k+qd in registers; the recursion is fully unrolled so that every register index
+    // is static: per step one quad shuffle, the accept/reject arithmetic, and 16 predicated register FMAs.
     const int t = (tid >> 2) & (NP_TARGETS - 1), qd = tid & 3;
     const long b = b0 + t;
     const bool live = b < B;
-    if (tid < 4 * NP_TARGETS)
-    for (int ii = nbe - 1; ii >= 0; --ii) {
-        const double cp = ts[ii * NP_TS + t];
-        const DGaussParams dgp = dgs[ii];
-        const float4 pr = rng[ii * NP_TARGETS + t];
-        const double c_int = rint(cp);
-        const float c_frac = (float)(cp - c_int);
-        double z;
-        bool done = false;
-        {
-            float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
-            float d = x - c_frac;
-            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
-            if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
+    if (tid < 4 * NP_TARGETS) {
+        double c[NP_NB_MAX / 4];
+#pragma unroll
+        for (int k = 0; k < NP_NB_MAX / 4; ++k) c[k] = (4 * k + qd < nbe) ? ts[(4 * k + qd) * NP_TS + t] : 0.0;
+#pragma unroll
+        for (int ii = NP_NB_MAX - 1; ii >= 0; --ii) {
+            if (ii >= nbe) continue;  // uniform
+            const int owner = ii & 3, k = ii >> 2;
+            const double cp = __shfl_sync(0xffffffffu, c[k], (lane & ~3) | owner);
+            const DGaussParams dgp = dgs[ii];
+            const float4 pr = rng[ii * NP_TARGETS + t];
+            const double c_int = rint(cp);
+            const float c_frac = (float)(cp - c_int);
+            double z = 0.0;
+            bool done = false;
+            {
+                float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
+                float d = x - c_frac;
+                float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
+                if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
+            }
+            if (!done) {
+                float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
+                float d = x - c_frac;
+                float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
+                if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
+            }
+            if (!done && live) {  // both pre-generated proposals rejected: continue the stream from its second block
+                Philox ph;
+                ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), QF_STREAM_NP);
+                ph.c3 = 1;
+                z = sample_dgauss(dgp, cp, ph);
+            }
+            if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
+            if (qd == owner) c[k] = z;
+            const double* ucol = ust + ii * nb + qd;  // ucol[4 kk] = U[j0 + 4 kk + qd][j0 + ii]
+#pragma unroll
+            for (int kk = 0; kk < NP_NB_MAX / 4; ++kk)
+                if (4 * kk < ii && 4 * kk + qd < ii) c[kk] = fma(-ucol[4 * kk], z, c[kk]);
         }
-        if (!done) {
-            float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
-            float d = x - c_frac;
-            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
-            if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
-        }
-        if (!done && live) {  // both pre-generated proposals rejected: continue the stream from its second block
-            Philox ph;
-            ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), QF_STREAM_NP);
-            ph.c3 = 1;
-            z = sample_dgauss(dgp, cp, ph);
-        } else if (!done) {
-            z = 0.0;
-        }
-        if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
-        __syncwarp();
-        if (qd == 0) ts[ii * NP_TS + t] = z;
-        const double* ucol = ust + ii * nb;  // ucol[r] = U[j0+r][j0+ii]
-        for (int jj = qd; jj < ii; jj += 4) ts[jj * NP_TS + t] -= ucol[jj] * z;
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NP_NB_MAX / 4; ++k)
+            if (4 * k + qd < nbe) ts[(4 * k + qd) * NP_TS + t] = c[k];
     }
     __syncthreads();
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
