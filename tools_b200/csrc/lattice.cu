@@ -67,6 +67,14 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
     }
 }
 
+// rare path of np_diag (both pre-generated proposals rejected): continue the coordinate's Philox stream
+__device__ __noinline__ double np_sample_slow(DGaussParams dgp, double cp, uint64_t seed, uint64_t index) {
+    Philox ph;
+    ph.init(seed, index, QF_STREAM_NP);
+    ph.c3 = 1;
+    return sample_dgauss(dgp, cp, ph);
+}
+
 constexpr int NP_TARGETS = 32;   // targets per CTA
 constexpr int NP_TPB = 512;      // phases 0/1 use all threads; phase 2 the first 128 (4 lanes per target)
 constexpr int NP_NB_MAX = 64;
@@ -124,48 +132,53 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
     const long b = b0 + t;
     const bool live = b < B;
     if (tid < 4 * NP_TARGETS) {
-        double c[NP_NB_MAX / 4];
+        constexpr int NG = NP_NB_MAX / 4;  // 16 coordinate groups; group j = coordinates 4j .. 4j+3
+        double c[NG];
 #pragma unroll
-        for (int k = 0; k < NP_NB_MAX / 4; ++k) c[k] = (4 * k + qd < nbe) ? ts[(4 * k + qd) * NP_TS + t] : 0.0;
+        for (int k = 0; k < NG; ++k) c[k] = (4 * k + qd < nbe) ? ts[(4 * k + qd) * NP_TS + t] : 0.0;
+        // the group being sampled always sits in c[NG-1]; after each group the register file is rotated by one,
+        // so all register indices are static while the loop over groups stays rolled (small code footprint)
+        for (int kidx = 0; kidx < NG; ++kidx) {
+            const int g = NG - 1 - kidx;
 #pragma unroll
-        for (int ii = NP_NB_MAX - 1; ii >= 0; --ii) {
-            if (ii >= nbe) continue;  // uniform
-            const int owner = ii & 3, k = ii >> 2;
-            const double cp = __shfl_sync(0xffffffffu, c[k], (lane & ~3) | owner);
-            const DGaussParams dgp = dgs[ii];
-            const float4 pr = rng[ii * NP_TARGETS + t];
-            const double c_int = rint(cp);
-            const float c_frac = (float)(cp - c_int);
-            double z = 0.0;
-            bool done = false;
-            {
-                float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
-                float d = x - c_frac;
-                float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
-                if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
-            }
-            if (!done) {
-                float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
-                float d = x - c_frac;
-                float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
-                if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
-            }
-            if (!done && live) {  // both pre-generated proposals rejected: continue the stream from its second block
-                Philox ph;
-                ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), QF_STREAM_NP);
-                ph.c3 = 1;
-                z = sample_dgauss(dgp, cp, ph);
-            }
-            if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
-            if (qd == owner) c[k] = z;
-            const double* ucol = ust + ii * nb + qd;  // ucol[4 kk] = U[j0 + 4 kk + qd][j0 + ii]
+            for (int owner = 3; owner >= 0; --owner) {
+                const int ii = 4 * g + owner;
+                if (ii >= nbe) continue;  // uniform
+                const double cp = __shfl_sync(0xffffffffu, c[NG - 1], (lane & ~3) | owner);
+                const DGaussParams dgp = dgs[ii];
+                const float4 pr = rng[ii * NP_TARGETS + t];
+                const double c_int = rint(cp);
+                const float c_frac = (float)(cp - c_int);
+                double z = 0.0;
+                bool done = false;
+                {
+                    float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
+                    float d = x - c_frac;
+                    float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
+                    if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
+                }
+                if (!done) {
+                    float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
+                    float d = x - c_frac;
+                    float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
+                    if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
+                }
+                if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
+                    z = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii));
+                if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
+                const double* ucol = ust + ii * nb + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
+                if (qd == owner) c[NG - 1] = z;
+                else if (qd < owner) c[NG - 1] = fma(-ucol[4 * g], z, c[NG - 1]);
 #pragma unroll
-            for (int kk = 0; kk < NP_NB_MAX / 4; ++kk)
-                if (4 * kk < ii && 4 * kk + qd < ii) c[kk] = fma(-ucol[4 * kk], z, c[kk]);
+                for (int kk = 0; kk < NG - 1; ++kk) {
+                    const int grp = kk - kidx;  // group held by c[kk]
+                    if (grp >= 0) c[kk] = fma(-ucol[4 * grp], z, c[kk]);
+                }
+            }
+            if (4 * g + qd < nbe) ts[(4 * g + qd) * NP_TS + t] = c[NG - 1];
+#pragma unroll
+            for (int kk = NG - 1; kk > 0; --kk) c[kk] = c[kk - 1];
         }
-#pragma unroll
-        for (int k = 0; k < NP_NB_MAX / 4; ++k)
-            if (4 * k + qd < nbe) ts[(4 * k + qd) * NP_TS + t] = c[k];
     }
     __syncthreads();
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
