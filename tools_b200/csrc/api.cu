@@ -463,13 +463,22 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
     const long D = ctx->dim, ldD = ctx->ld_dim;
     const double* U = ctx->dU.as<double>();
     if (level == 0) {
-        LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(), Bc, (int)lo, (int)(hi - lo), (int)D,
+        // proposals of the enclosing 1024-block start at column (lo / 1024) * 1024
+        const long blk0 = lo / NP_SIZES[2] * NP_SIZES[2];
+        LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
+                                 ctx->w[9].as<float4>() + (lo - blk0), NP_SIZES[2], Bc, (int)lo, (int)(hi - lo), (int)D,
                                  seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
         return QF_OK;
     }
     const long step = NP_SIZES[level - 1];
     for (long sub_hi = hi; sub_hi > lo;) {
         const long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
+        if (level == 3) {
+            // the rejection-sampling proposals of this 1024-block for all targets, at full occupancy
+            CK(ctx->w[9].ensure((size_t)ctx->chunk * NP_SIZES[2] * sizeof(float4)));
+            LAUNCH(qf_launch_np_propose(ctx->w[9].as<float4>(), NP_SIZES[2], Bc, (int)sub_lo, (int)(sub_hi - sub_lo), (int)D,
+                                        seed, first, ctx->stream));
+        }
         QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, seed, first));
         if (level == 3 && ctx->use_ozaki) {
             // digits of the finished block of z (kept: the final S z reuses them), then the update of all rows

@@ -70,9 +70,13 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
 // for i = j0+nb-1 .. j0:  c' = T[b][i] - sum_{j>i in block} U[i][j] z_j ;  z_i <- D_{Z, s/||b~_i||, c'}
 // writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).
 // *flag is set when |z| >= zlimit (exact-integer range check).
+// prop: this block's pre-generated proposals (np_propose), prop[b * ldprop + (i - j0)]
 cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
-                              const DGaussParams* dg, int B, int j0, int nb, int dim, uint64_t seed,
-                              uint64_t first_target, double zlimit, int* flag, cudaStream_t stream);
+                              const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream);
+// two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[b * ldo + (i - j_lo)]
+cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
+                                 uint64_t first_target, cudaStream_t stream);
 
 // ---- compress.cu -----------------------------------------------------------
 cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,

@@ -75,8 +75,27 @@ __device__ __noinline__ double np_sample_slow(DGaussParams dgp, double cp, uint6
     return sample_dgauss(dgp, cp, ph);
 }
 
+// First Philox block of every (target, coordinate) stream of the nearest-plane recursion turned into two
+// proposals (two normals, logs of two uniforms).  The transcendental work does not depend on the centres, so it
+// runs here at full occupancy instead of inside the sequential per-target chain of np_diag.
+__global__ void __launch_bounds__(256)
+np_propose_kernel(float4* __restrict__ out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
+                  uint64_t first_target) {
+    const long total = (long)B * width;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / width;
+        const int i = (int)(idx - b * width);
+        Philox ph;
+        ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j_lo + i), QF_STREAM_NP);
+        float n0, n1;
+        ph.normal2(n0, n1);
+        const float u0 = ph.uniform24(), u1 = ph.uniform24();
+        out[b * ldo + i] = make_float4(n0, n1, __logf(u0), __logf(u1));
+    }
+}
+
 constexpr int NP_TARGETS = 32;   // targets per CTA
-constexpr int NP_TPB = 512;      // phases 0/1 use all threads; phase 2 the first 128 (4 lanes per target)
+constexpr int NP_TPB = 128;      // 4 lanes per target
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = 36;        // row stride of the centre tile (36 = 4 mod 16: conflict-free quad access)
 
@@ -90,10 +109,10 @@ constexpr int NP_TS = 36;        // row stride of the centre tile (36 = 4 mod 16
 //     j's strided over the 4 lanes (independent FMAs instead of one dependent dot product).
 // Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
 // one-thread-per-target formulation.
-__global__ void __launch_bounds__(NP_TPB)
+__global__ void __launch_bounds__(NP_TPB, 2)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
-               long ldu, const DGaussParams* __restrict__ dg_g, int B, int j0, int nb, int dim, uint64_t seed,
-               uint64_t first_target, double zlimit, int* flag) {
+               long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
+               int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
     extern __shared__ __align__(16) double np_sm[];
     double* ust = np_sm;                                  // ust[c * nb + r] = U[j0+r][j0+c], c > r
     double* ts = ust + ((nb * nb + 1) & ~1);              // ts[i * NP_TS + t]  (16-byte aligned)
@@ -112,17 +131,11 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         if (b < B)
             for (int c = lane; c < nbe; c += 32) ts[c * NP_TS + r] = T[b * ldt + j0 + c];
     }
-    // phase 1: first Philox block of every (target, coordinate) stream -> two proposals
-    for (int idx = tid; idx < nbe * NP_TARGETS; idx += NP_TPB) {
-        const int i = idx / NP_TARGETS, t = idx - i * NP_TARGETS;
-        const long b = b0 + t;
-        if (b >= B) continue;
-        Philox ph;
-        ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + i), QF_STREAM_NP);
-        float n0, n1;
-        ph.normal2(n0, n1);
-        const float u0 = ph.uniform24(), u1 = ph.uniform24();
-        rng[idx] = make_float4(n0, n1, __logf(u0), __logf(u1));
+    // phase 1: stage this block's pre-generated proposals (np_propose_kernel); prop points at column j0
+    for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
+        const long b = b0 + r;
+        if (b < B)
+            for (int c = lane; c < nbe; c += 32) rng[c * NP_TARGETS + r] = prop[b * ldprop + c];
     }
     __syncthreads();
     // phase 2 (first 4 warps; the others wait at the barrier below).  Lane qd of a target's quad keeps the
@@ -210,9 +223,19 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
     return cudaGetLastError();
 }
 
+cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
+                                 uint64_t first_target, cudaStream_t stream) {
+    if (B <= 0 || width <= 0) return cudaSuccess;
+    long long total = (long long)B * width;
+    long long g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    np_propose_kernel<<<(int)g, 256, 0, stream>>>(out, ldo, B, j_lo, width, dim, seed, first_target);
+    return cudaGetLastError();
+}
+
 cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
-                              const DGaussParams* dg, int B, int j0, int nb, int dim, uint64_t seed,
-                              uint64_t first_target, double zlimit, int* flag, cudaStream_t stream) {
+                              const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
@@ -224,7 +247,7 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, B, j0, nb, dim, seed, first_target,
-                                                   zlimit, flag);
+    np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0, nb, dim, seed,
+                                                   first_target, zlimit, flag);
     return cudaGetLastError();
 }
