@@ -97,7 +97,8 @@ np_propose_kernel(float4* __restrict__ out, long ldo, int B, int j_lo, int width
 constexpr int NP_TARGETS = 32;   // targets per CTA
 constexpr int NP_TPB = 128;      // 4 lanes per target
 constexpr int NP_NB_MAX = 64;
-constexpr int NP_TS = 36;        // row stride of the centre tile (36 = 4 mod 16: conflict-free quad access)
+constexpr int NP_TS = NP_NB_MAX + 1;   // centre tile is target-major: ts[t * NP_TS + i]
+constexpr int NP_RS = NP_NB_MAX + 1;   // proposal tile likewise: rng[t * NP_RS + i] (65 float4: conflict-free reads)
 
 // One nb-wide diagonal block.  Three phases per CTA of 32 targets:
 //  0. stage the mu-block (transposed) and the 32 x nb tile of centres through shared memory (coalesced);
@@ -114,28 +115,29 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
                int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
     extern __shared__ __align__(16) double np_sm[];
-    double* ust = np_sm;                                  // ust[c * nb + r] = U[j0+r][j0+c], c > r
-    double* ts = ust + ((nb * nb + 1) & ~1);              // ts[i * NP_TS + t]  (16-byte aligned)
-    float4* rng = reinterpret_cast<float4*>(ts + nb * NP_TS);  // rng[i * NP_TARGETS + t] = (n0, n1, log u0, log u1)
-    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(rng + nb * NP_TARGETS);
+    const int us_ld = nb + 1;                             // padded: the transposing store is (almost) conflict-free
+    double* ust = np_sm;                                  // ust[c * us_ld + r] = U[j0+r][j0+c], c > r
+    double* ts = ust + ((nb * us_ld + 1) & ~1);           // ts[t * NP_TS + i]  (16-byte aligned)
+    float4* rng = reinterpret_cast<float4*>(ts + ((NP_TARGETS * NP_TS + 1) & ~1));  // rng[t * NP_RS + i]
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(rng + NP_TARGETS * NP_RS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbe = min(nb, dim - j0);
     const long b0 = (long)blockIdx.x * NP_TARGETS;
     for (int i = tid; i < nb * nb; i += NP_TPB) {
         const int r = i / nb, c = i - r * nb;  // coalesced read along c
-        ust[c * nb + r] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
+        ust[c * us_ld + r] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
     }
     for (int i = tid; i < nbe; i += NP_TPB) dgs[i] = dg_g[j0 + i];
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
         const long b = b0 + r;
         if (b < B)
-            for (int c = lane; c < nbe; c += 32) ts[c * NP_TS + r] = T[b * ldt + j0 + c];
+            for (int c = lane; c < nbe; c += 32) ts[r * NP_TS + c] = T[b * ldt + j0 + c];
     }
     // phase 1: stage this block's pre-generated proposals (np_propose_kernel); prop points at column j0
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
         const long b = b0 + r;
         if (b < B)
-            for (int c = lane; c < nbe; c += 32) rng[c * NP_TARGETS + r] = prop[b * ldprop + c];
+            for (int c = lane; c < nbe; c += 32) rng[r * NP_RS + c] = prop[b * ldprop + c];
     }
     __syncthreads();
     // phase 2 (first 4 warps; the others wait at the barrier below).  Lane qd of a target's quad keeps the
@@ -148,7 +150,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         constexpr int NG = NP_NB_MAX / 4;  // 16 coordinate groups; group j = coordinates 4j .. 4j+3
         double c[NG];
 #pragma unroll
-        for (int k = 0; k < NG; ++k) c[k] = (4 * k + qd < nbe) ? ts[(4 * k + qd) * NP_TS + t] : 0.0;
+        for (int k = 0; k < NG; ++k) c[k] = (4 * k + qd < nbe) ? ts[t * NP_TS + 4 * k + qd] : 0.0;
         // the group being sampled always sits in c[NG-1]; after each group the register file is rotated by one,
         // so all register indices are static while the loop over groups stays rolled (small code footprint)
         for (int kidx = 0; kidx < NG; ++kidx) {
@@ -159,7 +161,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                 if (ii >= nbe) continue;  // uniform
                 const double cp = __shfl_sync(0xffffffffu, c[NG - 1], (lane & ~3) | owner);
                 const DGaussParams dgp = dgs[ii];
-                const float4 pr = rng[ii * NP_TARGETS + t];
+                const float4 pr = rng[t * NP_RS + ii];
                 const double c_int = rint(cp);
                 const float c_frac = (float)(cp - c_int);
                 double z = 0.0;
@@ -179,7 +181,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                 if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
                     z = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii));
                 if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
-                const double* ucol = ust + ii * nb + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
+                const double* ucol = ust + ii * us_ld + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
                 if (qd == owner) c[NG - 1] = z;
                 else if (qd < owner) c[NG - 1] = fma(-ucol[4 * g], z, c[NG - 1]);
 #pragma unroll
@@ -188,7 +190,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                     if (grp >= 0) c[kk] = fma(-ucol[4 * grp], z, c[kk]);
                 }
             }
-            if (4 * g + qd < nbe) ts[(4 * g + qd) * NP_TS + t] = c[NG - 1];
+            if (4 * g + qd < nbe) ts[t * NP_TS + 4 * g + qd] = c[NG - 1];
 #pragma unroll
             for (int kk = NG - 1; kk > 0; --kk) c[kk] = c[kk - 1];
         }
@@ -197,7 +199,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
         const long bb = b0 + r;
         if (bb < B)
-            for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[c * NP_TS + r];
+            for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[r * NP_TS + c];
     }
 }
 
@@ -239,8 +241,8 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
-    size_t smem = (size_t)(((nb * nb + 1) & ~1) + nb * NP_TS) * sizeof(double) + (size_t)nb * NP_TARGETS * sizeof(float4) +
-                  (size_t)nb * sizeof(DGaussParams);
+    size_t smem = (size_t)(((nb * (nb + 1) + 1) & ~1) + ((NP_TARGETS * NP_TS + 1) & ~1)) * sizeof(double) +
+                  (size_t)NP_TARGETS * NP_RS * sizeof(float4) + (size_t)nb * sizeof(DGaussParams);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
