@@ -121,7 +121,7 @@ struct qf_ctx {
     // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
     bool use_ozaki = false;
     int u_limbs = 7;
-    Dev dUl, dUscale, dNz;
+    Dev dUl, dUscale, dNz, dMma;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -281,7 +281,9 @@ cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
         rec.issued = rec.flops * a.LX * a.LW;
         cudaEventRecord(rec.a, ctx->stream);
     }
-    cudaError_t e = qf_launch_gemm_i8(a, ctx->stream);
+    I8GemmArgs aa = a;
+    aa.mma_units = (ctx->prof && ctx->dMma.p) ? ctx->dMma.as<unsigned long long>() : nullptr;
+    cudaError_t e = qf_launch_gemm_i8(aa, ctx->stream);
     if (ctx->prof) {
         cudaEventRecord(rec.b, ctx->stream);
         ctx->prof_recs.push_back(rec);
@@ -774,6 +776,10 @@ qf_status qf_synchronize(qf_ctx* ctx) {
 qf_status qf_profile(qf_ctx* ctx, int enable) {
     if (!ctx) return QF_ERR_INVALID;
     ctx->prof = enable != 0;
+    if (ctx->prof) {
+        CK(ctx->dMma.ensure(8));
+        CK(cudaMemsetAsync(ctx->dMma.p, 0, 8, ctx->stream));
+    }
     return QF_OK;
 }
 
@@ -798,6 +804,12 @@ qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint
     if (gemm_launches) *gemm_launches = cnt[0];
     if (i8_ms) *i8_ms = ms[1];
     if (i8_ops) *i8_ops = fl[1];
+    if (ctx->dMma.p) {  // executed tensor-pipe operations counted by the kernel itself (zero digit tiles skipped)
+        unsigned long long h = 0;
+        CK(cudaMemcpy(&h, ctx->dMma.p, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(ctx->dMma.p, 0, 8));
+        issued = (double)h;
+    }
     if (i8_issued_ops) *i8_issued_ops = issued;
     if (i8_launches) *i8_launches = cnt[1];
     ctx->prof_recs.clear();

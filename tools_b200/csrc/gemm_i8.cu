@@ -48,6 +48,7 @@ struct I8Params {
     int m_tiles, n_tiles, group_m;
     // optional zero-tile map of the x digit planes: nz[(j * m_tiles_total + m_tile) * kb_total + kb_off + kb]
     const uint8_t* x_nz; int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
+    unsigned long long* mma_units;  // optional device counter of executed int8 operations (tensor pipe work)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,6 +122,12 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM and the barriers are set up
+// once; the TMA producer runs ahead into the next tile while the epilogue of the current one drains TMEM.
 __global__ void __launch_bounds__(I8_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -132,23 +139,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
+    uint64_t* tmem_empty = bars + 2 * p.stages + 1;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile rasterisation: consecutive CTAs walk group_m target tiles for one n tile, then the next n tile
-    int tile_m, tile_n;
-    {
-        const int t = blockIdx.x, per_group = p.group_m * p.n_tiles;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int ND = p.LX + p.LW - 1;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    // tile rasterisation: consecutive tiles walk group_m target tiles for one n tile, then the next n tile
+    auto tile_coords = [&](int t, int& tile_m, int& tile_n) {
+        const int per_group = p.group_m * p.n_tiles;
         const int g = t / per_group, r = t - g * per_group;
         const int gm = min(p.group_m, p.m_tiles - g * p.group_m);  // last group may be short
         tile_m = g * p.group_m + r % gm;
         tile_n = r / gm;
-    }
-    const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
-    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int ND = p.LX + p.LW - 1;
+    };
     // which x digit planes are non-zero in this (target tile, k block)? (bit j of the returned mask)
-    auto plane_mask = [&](int kb) -> uint32_t {
+    auto plane_mask = [&](int tile_m, int kb) -> uint32_t {
         if (!p.x_nz) return (1u << p.LX) - 1u;
         uint32_t mk = 0;
         for (int j = 0; j < p.LX; ++j)
@@ -162,6 +169,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // allocate all 512 TMEM columns (one CTA per SM)
@@ -173,7 +181,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     // zero every accumulator so that all MMAs can accumulate: one MMA then covers several digit planes of w
-    // (N = g * nt) whose accumulators D_{j+i0} .. D_{j+i0+g-1} are adjacent column blocks
+    // (N = g * nt) whose accumulators D_{j+i0} .. D_{j+i0+g-1} are adjacent column blocks.  Later tiles find the
+    // accumulators zeroed by the epilogue of the previous tile.
     if (warp >= 2) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
@@ -188,20 +197,25 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const uint32_t mk = plane_mask(kb);
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sx = smem + (size_t)stage * stage_bytes;
-                uint8_t* sw = sx + p.LX * x_tile;
-                if (mk == 0) {  // nothing to multiply in this k block: just hand the stage over
-                    mbar_expect_tx(&full_bar[stage], 0);
-                } else {
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mk) * x_tile + p.LW * w_tile));
-                    for (int j = 0; j < p.LX; ++j)
-                        if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
-                    for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int tile_m, tile_n;
+                tile_coords(tile, tile_m, tile_n);
+                const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t mk = plane_mask(tile_m, kb);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sx = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sw = sx + p.LX * x_tile;
+                    if (mk == 0) {  // nothing to multiply in this k block: just hand the stage over
+                        mbar_expect_tx(&full_bar[stage], 0);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mk) * x_tile + p.LW * w_tile));
+                        for (int j = 0; j < p.LX; ++j)
+                            if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
+                        for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -213,114 +227,134 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint64_t desc0 = make_desc(smem_u32(smem));
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const uint32_t mk = plane_mask(kb);
-            mbar_wait(&full_bar[stage], phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
-                const uint32_t sw_off = sx_off + ((uint32_t)(p.LX * x_tile) >> 4);
-                for (int j = 0; j < p.LX; ++j) {
-                    if (!((mk >> j) & 1u)) continue;
-                    const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
-                    for (int i0 = 0; i0 < p.LW; i0 += G) {
-                        const int g = min(G, p.LW - i0);
-                        const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
-                        const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
-                        const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
-#pragma unroll
-                        for (int kk = 0; kk < BLOCK_K / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
-                            mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
-                    }
-                }
-                mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
-                if (kb == num_kb - 1) mma_commit(tmem_full);
+        unsigned long long units = 0;  // executed (x digit, w digit, k block) products, for the profiler
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int tile_m, tile_n;
+            tile_coords(tile, tile_m, tile_n);
+            if (it > 0) {  // the epilogue must have drained (and re-zeroed) the accumulators of the previous tile
+                mbar_wait(tmem_empty, (uint32_t)((it - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const uint32_t mk = plane_mask(tile_m, kb);
+                mbar_wait(&full_bar[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
+                    const uint32_t sw_off = sx_off + ((uint32_t)(p.LX * x_tile) >> 4);
+                    for (int j = 0; j < p.LX; ++j) {
+                        if (!((mk >> j) & 1u)) continue;
+                        const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
+                        for (int i0 = 0; i0 < p.LW; i0 += G) {
+                            const int g = min(G, p.LW - i0);
+                            const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
+                            const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
+                            const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
+#pragma unroll
+                            for (int kk = 0; kk < BLOCK_K / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
+                                mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
+                            units += (unsigned long long)g;
+                        }
+                    }
+                    mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+                    if (kb == num_kb - 1) mma_commit(tmem_full);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
         }
+        if (lane == 0 && p.mma_units && units)
+            atomicAdd(p.mma_units, units * (2ull * TILE_M * BLOCK_K) * (unsigned long long)p.nt);  // int8 operations
     } else {
         // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
         const int lg = warp & 3;
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + lg * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        if (p.out_kind == 3) {
-            // scaled fp64 update  out[b][n] -= V * scale[n]:  8 columns per trip, the old values are fetched
-            // first, all digit accumulators are read with one wait, and V = sum 256^d D_d is assembled from
-            // four exact 64-bit partial sums (4 digits each) instead of 128-bit arithmetic.
-            double* orow = (double*)p.out + (long)row * p.ldout;
-            for (int c0 = 0; c0 < p.nt; c0 += 8) {
-                double told[8];
-                const bool rv = row < p.B;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int tile_m, tile_n;
+            tile_coords(tile, tile_m, tile_n);
+            const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
+            mbar_wait(tmem_full, (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + lg * 32 + lane;
+            if (p.out_kind == 3) {
+                // scaled fp64 update  out[b][n] -= V * scale[n]:  8 columns per trip, the old values are fetched
+                // first, all digit accumulators are read with one wait, and V = sum 256^d D_d is assembled from
+                // four exact 64-bit partial sums (4 digits each) instead of 128-bit arithmetic.
+                double* orow = (double*)p.out + (long)row * p.ldout;
+                for (int c0 = 0; c0 < p.nt; c0 += 8) {
+                    double told[8];
+                    const bool rv = row < p.B;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) told[c] = (rv && n0 + c0 + c < p.N) ? orow[n0 + c0 + c] : 0.0;
-                int32_t t[16][8];
-#pragma unroll
-                for (int d = 0; d < 16; ++d)
-                    if (d < ND) tmem_ld8(lane_addr + (uint32_t)(d * p.nt + c0), t[d]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    long long part[4] = {0, 0, 0, 0};
+                    for (int c = 0; c < 8; ++c) told[c] = (rv && n0 + c0 + c < p.N) ? orow[n0 + c0 + c] : 0.0;
+                    int32_t t[16][8];
 #pragma unroll
                     for (int d = 0; d < 16; ++d)
-                        if (d < ND) part[d >> 2] += ((long long)t[d][c]) << (8 * (d & 3));
-                    double dv = (double)part[3];
-                    dv = fma(dv, 4294967296.0, (double)part[2]);
-                    dv = fma(dv, 4294967296.0, (double)part[1]);
-                    dv = fma(dv, 4294967296.0, (double)part[0]);
-                    const int n = n0 + c0 + c;
-                    if (rv && n < p.N) orow[n] = told[c] - dv * p.scale[n];
-                }
-            }
-        } else
-        for (int c0 = 0; c0 < p.nt; c0 += 16) {
-            __int128 v[16];
+                        if (d < ND) tmem_ld8(lane_addr + (uint32_t)(d * p.nt + c0), t[d]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = 0;
-            for (int d = 0; d < ND; ++d) {
-                int32_t t[16];
-                tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int c = 0; c < 8; ++c) {
+                        long long part[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] += ((__int128)t[c]) << (8 * d);
-            }
-            if (row < p.B) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int n = n0 + c0 + c;
-                    if (n >= p.N) continue;
-                    __int128 val = p.sign < 0 ? -v[c] : v[c];
-                    if (p.out_kind == 0) {
-                        if (p.base) val += (__int128)p.base[(long)row * p.ldbase + n];
-                        long long r;
-                        if (p.q) {
-                            if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)val & (p.q - 1));
-                            else r = (long long)mod_i128(val, p.q);
-                        } else {
-                            r = (long long)val;
-                        }
-                        ((int64_t*)p.out)[(long)row * p.ldout + n] = r;
-                    } else if (p.out_kind == 1) {
-                        if (val > 2147483647 || val < -2147483647) {
-                            if (p.flag) atomicOr(p.flag, 4);
-                            val = 0;
-                        }
-                        ((int32_t*)p.out)[(long)row * p.ldout + n] = (int32_t)(long long)val;
-                    } else if (p.out_kind == 2) {
-                        ((double*)p.out)[(long)row * p.ldout + n] += (double)(long long)val;
-                    } else {
-                        // |val| may exceed 2^63: convert the 128-bit integer through its two halves
-                        const bool neg = val < 0;
-                        const unsigned __int128 a = neg ? (unsigned __int128)(-val) : (unsigned __int128)val;
-                        double dv = (double)(unsigned long long)(a >> 64) * 18446744073709551616.0 +
-                                    (double)(unsigned long long)a;
-                        if (neg) dv = -dv;
-                        ((double*)p.out)[(long)row * p.ldout + n] -= dv * p.scale[n];
+                        for (int d = 0; d < 16; ++d)
+                            if (d < ND) part[d >> 2] += ((long long)t[d][c]) << (8 * (d & 3));
+                        double dv = (double)part[3];
+                        dv = fma(dv, 4294967296.0, (double)part[2]);
+                        dv = fma(dv, 4294967296.0, (double)part[1]);
+                        dv = fma(dv, 4294967296.0, (double)part[0]);
+                        const int n = n0 + c0 + c;
+                        if (rv && n < p.N) orow[n] = told[c] - dv * p.scale[n];
                     }
                 }
+            } else {
+                for (int c0 = 0; c0 < p.nt; c0 += 16) {
+                    __int128 v[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] = 0;
+                    for (int d = 0; d < ND; ++d) {
+                        int32_t t[16];
+                        tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) v[c] += ((__int128)t[c]) << (8 * d);
+                    }
+                    if (row < p.B) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int n = n0 + c0 + c;
+                            if (n >= p.N) continue;
+                            __int128 val = p.sign < 0 ? -v[c] : v[c];
+                            if (p.out_kind == 0) {
+                                if (p.base) val += (__int128)p.base[(long)row * p.ldbase + n];
+                                long long r;
+                                if (p.q) {
+                                    if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)val & (p.q - 1));
+                                    else r = (long long)mod_i128(val, p.q);
+                                } else {
+                                    r = (long long)val;
+                                }
+                                ((int64_t*)p.out)[(long)row * p.ldout + n] = r;
+                            } else if (p.out_kind == 1) {
+                                if (val > 2147483647 || val < -2147483647) {
+                                    if (p.flag) atomicOr(p.flag, 4);
+                                    val = 0;
+                                }
+                                ((int32_t*)p.out)[(long)row * p.ldout + n] = (int32_t)(long long)val;
+                            } else {
+                                ((double*)p.out)[(long)row * p.ldout + n] += (double)(long long)val;
+                            }
+                        }
+                    }
+                }
+            }
+            // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
+            if (tile + (int)gridDim.x < total_tiles) {
+                for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -414,7 +448,15 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    dim3 grid((unsigned)(p.m_tiles * p.n_tiles));
+    p.mma_units = a.mma_units;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    dim3 grid((unsigned)(total_tiles < sm_count ? total_tiles : sm_count));  // persistent: one CTA per SM
     gemm_i8_kernel<<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
     return cudaGetLastError();
 }

@@ -129,6 +129,8 @@ struct I8GemmArgs {
     // iff digit plane j has a non-zero byte in that 128-target x 128-column tile (K offset must be 128-aligned)
     const uint8_t* x_nz;
     int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
+    // optional device counter: += int8 operations the tensor pipe actually executed (zero digit tiles are skipped)
+    unsigned long long* mma_units;
 };
 int qf_i8_tile_n(int LX, int LW, int N);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
