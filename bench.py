@@ -369,8 +369,9 @@ def main():
             "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z and exact e = sol + S*z",
             "bound": "tensor", "achieved": algo, "achieved_issued": issued, "peak": i8_peak, "unit": "TOP/s",
             "frac": issued / i8_peak, "frac_algorithmic": algo / i8_peak,
-            "traffic": 3.63e9, "traffic_note": "dram read+write of the S*z launch from the ncu --set full capture in profiles/ "
-                                              "(algorithmic 2.0 GB)",
+            "traffic": 8.77e9, "traffic_note": "dram read+write of the S*z launch (the largest one) from the ncu --set full "
+                                              "capture profiles/prof_i8_sz_r1.ncu-rep; algorithmic 2.0 GB per launch "
+                                              "(z digits 0.97 + S digits 0.31 + e 0.77)",
             "peak_source": i8_src, "digit_pairs_per_mac": issued / algo if algo else None,
             "kernel_ms_per_step": ims.value / args.steps, "kernel_share_of_step": ims.value / ms, "launches": int(iln.value),
         }
