@@ -108,7 +108,9 @@ struct qf_ctx {
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];
-    Dev dNorm, dFlag, io_a, io_b, io_c;
+    Dev dNorm, dFlag, io_a, io_b, io_c, io_a2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // tcgen05 int8 path for the exact integer contractions
     bool use_i8 = true;
     long ldk_dim = 0, ldk_nk = 0;
@@ -749,6 +751,13 @@ void qf_ctx_destroy(qf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaStream_t s = ctx->own_stream;
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
     if (s) cudaStreamDestroy(s);
 }
@@ -1260,15 +1269,41 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
     const long C = ctx->chunk;
     CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    // results leave through a second stream: the device->host copy of chunk i overlaps the computation of
+    // chunk i+1 (two result buffers, events in both directions)
+    const bool overlap = batch > C;
+    if (overlap) {
+        CK(ctx->io_a2.ensure((size_t)C * ctx->dim * 4));
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            }
+        }
+    }
+    int64_t idx = 0;
     QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        const int slot = (int)(idx & 1);
+        int32_t* dres = (overlap && slot) ? ctx->io_a2.as<int32_t>() : ctx->io_a.as<int32_t>();
+        if (overlap && idx >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));  // buffer free again?
         CK(cudaMemcpyAsync(ctx->io_b.p, u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
         QF_TRY(ctx->prm.kind == QF_PSF_PERTURBATION
-                   ? samp_p_pert_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, ctx->io_a.as<int32_t>())
-                   : samp_p_np_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, ctx->io_a.as<int32_t>()));
-        CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, ctx->io_a.p, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+                   ? samp_p_pert_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres)
+                   : samp_p_np_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres));
+        if (overlap) {
+            CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[slot], 0));
+            CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, dres, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+        } else {
+            CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, dres, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        ++idx;
         return QF_OK;
     }));
+    if (overlap) CK(cudaStreamSynchronize(ctx->copy_stream));
     return check_flag(ctx);
 }
 
