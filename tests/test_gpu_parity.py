@@ -548,3 +548,56 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch):
         outs.append(e)
     same = (outs[0] == outs[1]).all(axis=1).mean()
     assert same > 0.9, same
+
+
+def test_full_size_c2_properties(T):
+    """BASELINE.json configs[1] at full key size (PSFGPV n = 256, q = 2^24, m = 12352): the size-independent
+    properties -- A e = u for every target (checked here in exact numpy integer arithmetic, not by the
+    device), check_domain, the second moment of the spherical law, batch splitting, and f_a linearity."""
+    import math
+
+    n, q = 256, 2**24
+    gp = T.GadgetParameters.init_default(n, q)
+    assert (gp.k, gp.m_bar, gp.m) == (24, 6208, 12352)
+    s = float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))
+    psf = T.PSFGPV(gp, s)
+    a, td = psf.trap_gen(seed=2)
+    rng = np.random.default_rng(3)
+    B = 1536
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=9)
+    # exact integer check on the host: entries of A < 2^24, |e| < 2^15, m < 2^14  =>  fits int64
+    assert np.array_equal((e.astype(np.int64) @ a.T) % q, u)
+    assert psf.check_domain_batch(e).all()
+    ratio = (e.astype(np.float64) ** 2).sum(1).mean() / (gp.m * s * s / (2 * math.pi))
+    assert abs(ratio - 1) < 0.01, ratio
+    # splitting the batch across calls (= across GPUs) reproduces the same preimages
+    e2 = np.concatenate([psf.samp_p_batch(a, td, u[:500], seed=9), psf.samp_p_batch(a, td, u[500:], seed=9, first_index=500)])
+    assert np.array_equal(e, e2)
+    # f_a on the device agrees with the host product, and is additive mod q where the sum stays in the domain
+    uu, flags = psf.f_a_batch(a, e)
+    assert flags.all() and np.array_equal(uu, u)
+    d = psf.samp_d_batch(64, seed=5)
+    half = (d // 2).astype(np.int32)
+    rest = (d - half).astype(np.int32)
+    u1, _ = psf.f_a_batch(a, half)
+    u2, _ = psf.f_a_batch(a, rest)
+    u12, _ = psf.f_a_batch(a, d)
+    assert np.array_equal((u1 + u2) % q, u12)
+
+
+def test_full_size_c5_compression_properties(T):
+    """C5 shape (degree-256 polynomials mod 3329), 1 Mi polynomials: decompress(compress(x)) stays within the
+    FIPS 203 bound, compress is idempotent on decompressed values, and a checksum of the output agrees with
+    the oracle on a strided sample."""
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 3329, (1 << 20, 256)).astype(np.uint16)
+    for d in (1, 4, 10, 11):
+        c = T.lossy_compress(x, d, 3329)
+        back = T.lossy_decompress(c, d, 3329)
+        dist = np.abs(back.astype(np.int32) - x.astype(np.int32))
+        dist = np.minimum(dist, 3329 - dist)
+        assert dist.max() <= 2 ** (12 - d - 1)
+        assert np.array_equal(T.lossy_compress(back % 3329, d, 3329), c)  # Compress(Decompress(y)) = y
+        sample = x[::4099]
+        assert np.array_equal(c[::4099].astype(np.uint64), O.lossy_compress_np(sample, d, 3329))
