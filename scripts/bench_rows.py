@@ -169,6 +169,8 @@ ROWS = {
     "f_a": row_f_a,
     "pert_c1": lambda: row_pert(8, 64, 3.0, 25.0, 262144, "C1 PSFPerturbation n=8 q=64 r=3 s=25"),
     "pert_256": lambda: row_pert(256, 2**24, 8.0, pert_s(256, 2**24), 15616, "PSFPerturbation n=256 q=2^24 r=8"),
+    # C4 per-GPU shard: n = 512, q = 2^32 - 5, k = 32, m = 32849 (the 4 Mi targets are split over 8 GPUs)
+    "pert_c4": lambda: row_pert(512, 2**32 - 5, 9.0, pert_s(512, 2**32 - 5), 11264, "C4 PSFPerturbation n=512 q=2^32-5 r=9 (one GPU shard)"),
 }
 
 if __name__ == "__main__":
