@@ -92,10 +92,18 @@ qf_status qf_profile_read(qf_ctx* ctx, double* gemm_ms, double* gemm_flops, uint
 /* A: n x m residues (PSFGPV / PSFPerturbation `A`, gpv.rs:60, mp_perturbation.rs:194) */
 qf_status qf_set_a(qf_ctx* ctx, const int64_t* a);
 /* PSFPerturbation trapdoor (mp_perturbation.rs:195): R m_bar x nk in {-1,0,1} (any small ints),
- * sqrt_sigma_2 m x m lower-triangular, and ONE k x k diagonal block of the gadget short basis
- * I_n (x) S_k with its GSO (gadget_classical.rs:248-287; the shim checks block-diagonality). */
+ * sqrt_sigma_2 m x m (any square root of Sigma_2; a lower-triangular one such as the Cholesky factor
+ * compute_sqrt_sigma_2 returns costs half the work), and ONE k x k diagonal block of the gadget short basis
+ * I_n (x) S_k with its GSO (gadget_classical.rs:248-287; the shim checks block-diagonality).
+ * sqrt_sigma_2 == NULL: the backend derives its own square root of the DEFAULT covariance
+ * Sigma = s^2 I (what PSFPerturbation::trap_gen builds, mp_perturbation.rs:227-231) from R, s, r on the
+ * device, in block form (only an m_bar x m_bar Cholesky factor is dense) -- same law, ~4x less work per target. */
 qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const double* sqrt_sigma_2,
                                        const int64_t* s_block, const double* s_block_gso);
+/* compute_sqrt_sigma_2 (mp_perturbation.rs:111-139) on the device: lower Cholesky factor (m x m, row-major, host)
+ * of Sigma_2 = r^2/(2 pi) (Sigma - (b^2+1) [R;I][R;I]^t - I); sigma == NULL means Sigma = s^2 I.
+ * QF_ERR_INVALID when Sigma_2 is not positive definite (the reference panics in the Cholesky). */
+qf_status qf_compute_sqrt_sigma_2(qf_ctx* ctx, const int8_t* r, const double* sigma, double* sqrt_sigma_2_out);
 /* PSFGPV trapdoor (gpv.rs:61): short basis S (dim x dim, columns are basis vectors) and its
  * GSO.  dim = m for QF_PSF_GPV, n*(k+2) (coefficient embedding) for QF_PSF_GPV_RING. */
 qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* s_gso);

@@ -129,11 +129,11 @@ def row_f_a():
                       "samp_d_ms": ms_d, "samp_d_draws_per_s": B * gp.m / ms_d * 1e3}), flush=True)
 
 
-def row_pert(n, q, r, s, B, label):
+def row_pert(n, q, r, s, B, label, dense=None):
     gp = T.GadgetParameters.init_default(n, q)
     psf = T.PSFPerturbation(gp, r, s)
     t0 = time.time()
-    a, td = psf.trap_gen(seed=4)
+    a, td = psf.trap_gen(seed=4, dense_sqrt_sigma_2=dense)
     psf._install_a(a)
     psf._install_td(a, td)
     setup = time.time() - t0
@@ -150,6 +150,7 @@ def row_pert(n, q, r, s, B, label):
     assert torch.equal(uo, u) and bool(fl.all())
     m = gp.m
     print(json.dumps({"row": label, "n": n, "q": q, "m": m, "r": r, "s": s, "B": B, "ms": ms,
+                      "sqrt_sigma_2": "dense m x m (reference form)" if td[1] is not None else "block-structured (backend)",
                       "preimages_per_s": B / ms * 1e3, "key_setup_s": setup,
                       "ops_per_target": m * (m + 1) + 2 * n * m + 2 * gp.m_bar * n * gp.k,
                       "norm2_ratio": float((e.double() ** 2).sum(1).mean().item() / (m * (s * r) ** 2 / (2 * math.pi)))}),
@@ -169,6 +170,9 @@ ROWS = {
     "f_a": row_f_a,
     "pert_c1": lambda: row_pert(8, 64, 3.0, 25.0, 262144, "C1 PSFPerturbation n=8 q=64 r=3 s=25"),
     "pert_256": lambda: row_pert(256, 2**24, 8.0, pert_s(256, 2**24), 15616, "PSFPerturbation n=256 q=2^24 r=8"),
+    "pert_256_dense": lambda: row_pert(256, 2**24, 8.0, pert_s(256, 2**24), 15616, "PSFPerturbation n=256 q=2^24 r=8", True),
+    "pert_c4_dense": lambda: row_pert(512, 2**32 - 5, 9.0, pert_s(512, 2**32 - 5), 11264,
+                                      "C4 PSFPerturbation n=512 q=2^32-5 r=9 (one GPU shard)", True),
     # C4 per-GPU shard: n = 512, q = 2^32 - 5, k = 32, m = 32849 (the 4 Mi targets are split over 8 GPUs)
     "pert_c4": lambda: row_pert(512, 2**32 - 5, 9.0, pert_s(512, 2**32 - 5), 11264, "C4 PSFPerturbation n=512 q=2^32-5 r=9 (one GPU shard)"),
 }

@@ -346,6 +346,89 @@ def test_samp_p_perturbation_distribution(T):
     assert abs(ref.var() / e.var() - 1) < 0.06
 
 
+@pytest.mark.parametrize("n,q,r,s", [(8, 64, 3.0, 25.0), (16, 2**10, 4.0, 60.0), (40, 2**12, 5.0, 300.0)])
+def test_compute_sqrt_sigma_2_matches_oracle(T, n, q, r, s):
+    """compute_sqrt_sigma_2 (mp_perturbation.rs:111-139) through the library's blocked Cholesky against the
+    oracle's float64 restatement; fp64 tolerance 1e-9 relative to the entries (|L| <= s r)."""
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, r, s)
+    rng = np.random.default_rng(n)
+    rm = (rng.integers(0, 2, (gp.m_bar, n * gp.k)) - rng.integers(0, 2, (gp.m_bar, n * gp.k))).astype(np.int8)
+    want = O.compute_sqrt_sigma_2(rm, s, r, 2)
+    got = psf.compute_sqrt_sigma_2(rm)
+    assert got.shape == (gp.m, gp.m) and not np.triu(got, 1).any()
+    assert np.allclose(got, want, rtol=0, atol=1e-9 * s * r)
+    # a supplied covariance (mp_perturbation.rs:94-104): Sigma = s^2 I + a small symmetric perturbation
+    d = rng.normal(size=(gp.m, 3))
+    sigma = (s * s) * np.eye(gp.m) + d @ d.T
+    t = np.vstack([rm.astype(np.float64), np.eye(n * gp.k)])
+    ref = np.linalg.cholesky((r * r) / (2 * np.pi) * (sigma - 5.0 * (t @ t.T) - np.eye(gp.m)))
+    assert np.allclose(psf.compute_sqrt_sigma_2(rm, sigma), ref, rtol=0, atol=1e-9 * s * r)
+    # Sigma_2 not positive definite: the reference panics in the Cholesky (mp_perturbation.rs:109-110)
+    bad = T.PSFPerturbation(gp, r, 3.0)
+    with pytest.raises(T.QfError):
+        bad.compute_sqrt_sigma_2(rm)
+
+
+def test_samp_p_perturbation_structured_sqrt(T):
+    """sqrt_sigma_2 = None: the backend's block-structured square root of the default Sigma_2.  Same law as the
+    dense Cholesky factor: A e = u, check_domain, spherical covariance (s r)^2 / (2 pi), and the same ||e||^2
+    distribution as the dense path."""
+    n, q, r, s = 8, 64, 3.0, 25.0
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, r, s)
+    a, td_dense = psf.trap_gen(seed=1)
+    rmat, l, basis = td_dense
+    td = (rmat, None, basis)
+    rng = np.random.default_rng(8)
+    B = 20000
+    u1 = rng.integers(0, q, (3000, n), dtype=np.int64)
+    e1 = psf.samp_p_batch(a, td, u1, seed=5)
+    assert np.array_equal(O.f_a_classical_batch(a, e1, q), u1) and psf.check_domain_batch(e1).all()
+    assert np.array_equal(e1, np.concatenate([psf.samp_p_batch(a, td, u1[:1000], seed=5),
+                                              psf.samp_p_batch(a, td, u1[1000:], seed=5, first_index=1000)]))
+    u = np.tile(rng.integers(0, q, (1, n), dtype=np.int64), (B, 1))
+    e = psf.samp_p_batch(a, td, u, seed=21).astype(np.float64)
+    sigma2 = (s * r) ** 2 / (2 * np.pi)
+    var = e.var(axis=0)
+    assert np.all(np.abs(var / sigma2 - 1) < 0.08), (var.min() / sigma2, var.max() / sigma2)
+    corr = np.corrcoef(e.T)
+    assert np.abs(corr - np.eye(gp.m)).max() < 0.05
+    ed = psf.samp_p_batch(a, td_dense, u, seed=22).astype(np.float64)
+    n_s, n_d = (e**2).sum(1), (ed**2).sum(1)
+    se = np.sqrt(n_s.var() / B + n_d.var() / B)
+    assert abs(n_s.mean() - n_d.mean()) < 5 * se
+    assert abs(n_s.var() / n_d.var() - 1) < 0.1
+    z = (e - e.mean(0)) / e.std(0)
+    assert np.abs((z**4).mean(0) - 3).max() < 0.35  # Gaussian marginals
+
+
+def test_samp_p_perturbation_structured_midsize(T):
+    """n = 40, q = 2^12 (m = 996, several Cholesky blocks and tensor-core tiles), structured square root."""
+    n, q, r = 40, 2**12, float(np.log2(40))
+    gp = T.GadgetParameters.init_default(n, q)
+    s = 1.3 * np.sqrt(5 * ((np.sqrt(gp.m_bar) + np.sqrt(n * gp.k)) ** 2 / 2 + 1) + 1)
+    psf = T.PSFPerturbation(gp, r, s)
+    a, td = psf.trap_gen(seed=3, dense_sqrt_sigma_2=False)
+    assert td[1] is None
+    rng = np.random.default_rng(2)
+    u = rng.integers(0, q, (4096, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=9)
+    assert np.array_equal(O.f_a_classical_batch(a, e, q), u) and psf.check_domain_batch(e).all()
+    ef = e.astype(np.float64)
+    ratio = (ef**2).sum(1).mean() / (gp.m * (s * r) ** 2 / (2 * np.pi))
+    assert abs(ratio - 1) < 0.01, ratio
+    var = ef.var(axis=0) / ((s * r) ** 2 / (2 * np.pi))
+    assert np.all(np.abs(var - 1) < 0.15), (var.min(), var.max())
+    c = np.corrcoef(ef[:, ::37].T)
+    assert np.abs(c - np.eye(c.shape[0])).max() < 0.1
+    # and the dense path on the same key agrees in law
+    td_d = (td[0], psf.compute_sqrt_sigma_2(td[0]), td[2])
+    ed = psf.samp_p_batch(a, td_d, u, seed=9).astype(np.float64)
+    assert np.array_equal(O.f_a_classical_batch(a, ed.astype(np.int64), q), u)
+    assert abs((ed**2).sum(1).mean() / (ef**2).sum(1).mean() - 1) < 0.01
+
+
 def test_gadget_sampler_distribution(T):
     """The gadget part alone: z = e[m_bar:] - p[m_bar:] is not observable, but G z' = v structure
     is: with R = 0 the lower block of e is p_low + z; check A e = u and the conditional law of the

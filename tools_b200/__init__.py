@@ -10,5 +10,6 @@ All arithmetic on the hot path runs in the CUDA library behind include/qfall_b20
 from . import _ffi  # noqa: F401
 from .gadget import (GadgetParameters, GadgetParametersRing, find_solution_gadget_mat, find_solution_gadget_vec,  # noqa: F401
                      gen_gadget_mat, gen_gadget_vec, rot_minus, rot_minus_matrix, short_basis_gadget)
+from ._ffi import NotInDomain, QfError  # noqa: F401
 from .psf import PSFGPV, PSFGPVRing, PSFPerturbation  # noqa: F401
 from .compression import lossy_compress, lossy_decompress  # noqa: F401

@@ -91,6 +91,14 @@ struct qf_ctx {
     // perturbation trapdoor
     bool has_pert = false;
     Dev dR, dL, dSk, dSkGso;
+    // structured sqrt(Sigma_2) (qf_set_trapdoor_perturbation with sqrt_sigma_2 == NULL): x_b ~ N(0, beta I) on the
+    // gadget block, x_t = L_s g_t - kappa R x_b with L_s the m_bar x m_bar Cholesky factor of the Schur complement
+    bool pert_structured = false;
+    int l_tri = 1;   // supplied sqrt(Sigma_2) is lower triangular (the Cholesky factor): skip the zero half
+    Dev dLs, dXbScale;
+    long ld_mb = 0;
+    double sqrt_beta = 0, xb_fscale = 0;
+    int xb_limbs = 3;
     // nearest-plane engine (GPV, ring)
     bool has_np = false;
     int npiv = 0;
@@ -398,7 +406,26 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     int64_t* V = ctx->w[4].as<int64_t>();
     // p <- D_{Z^m, r sqrt(Sigma_2)} : x2 = sqrt(Sigma_2) * N(0,I), p_i <- D_{Z, r, x2_i}   (:315)
     LAUNCH(qf_launch_normal_fill(G, ldm, Bc, (int)ctx->m, seed, first, QF_STREAM_PERT_NORMAL, ctx->stream));
-    LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, 1));
+    if (ctx->pert_structured) {
+        // x_b = sqrt(beta) g_b (kept exact in x2, fixed-point digits for the tensor cores);
+        // x_t = L_s g_t - kappa R x_b
+        const long ldk = ctx->ldk_nk, plane = C * ldk;
+        CK(ctx->w[5].ensure((size_t)ctx->xb_limbs * plane));
+        LAUNCH(qf_launch_pert_xb(G, ldm, X2, ldm, ctx->w[5].as<int8_t>(), plane, ldk, Bc, (int)ctx->m_bar, (int)ctx->nk,
+                                 ctx->sqrt_beta, ctx->xb_fscale, ctx->xb_limbs, ctx->dFlag.as<int>(), ctx->stream));
+        LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dLs.as<double>(), ctx->ld_mb, X2, ldm, Bc, (int)ctx->m_bar, (int)ctx->m_bar, 1.0, 0.0, 1));
+        I8GemmArgs g{};
+        g.x = ctx->w[5].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dRl.p; g.ldw = ldk; g.w_plane = (long)ctx->m_bar * ldk;
+        g.LX = ctx->xb_limbs; g.LW = 1; g.w_signed = 1;
+        g.B = Bc; g.N = (int)ctx->m_bar; g.K = (int)ctx->nk;
+        g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = X2; g.ldout = ldm;
+        g.flag = ctx->dFlag.as<int>();
+        g.scale = ctx->dXbScale.as<double>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    } else {
+        LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, ctx->l_tri));
+    }
     LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
                             ctx->stream));
     // v = u - A p   (:318)
@@ -659,6 +686,86 @@ bool find_unit_pivots(const int64_t* A, long n, long m, uint64_t q, std::vector<
     return true;
 }
 
+// ---------------------------------------------------------------------------
+// Blocked right-looking Cholesky A = L L^t (lower, in place, fp64) on the device: 64-wide diagonal blocks in
+// shared memory (potrf_diag), panel solve and trailing update on the DMMA GEMM.  Replaces
+// MatQ::cholesky_decomposition_flint (mp_perturbation.rs:138).  The strict upper triangle is zeroed.
+// ---------------------------------------------------------------------------
+qf_status potrf_lower(qf_ctx* ctx, double* A, long ld, long n) {
+    constexpr long NB = 64, STRIP = 1024;
+    Dev dLinv, dPanel, dInfo;
+    CK(dLinv.ensure(NB * NB * 8));
+    CK(dPanel.ensure((size_t)std::max(1L, n) * NB * 8));
+    CK(dInfo.ensure(sizeof(int)));
+    CK(cudaMemsetAsync(dInfo.p, 0, sizeof(int), ctx->stream));
+    double* P = dPanel.as<double>();
+    for (long j = 0; j < n; j += NB) {
+        const int nb = (int)std::min(NB, n - j);
+        LAUNCH(qf_launch_potrf_diag(A + j * ld + j, ld, nb, dLinv.as<double>(), dInfo.as<int>(), ctx->stream));
+        const long rows = n - j - nb;
+        if (rows <= 0) break;
+        // L_ij = A_ij L_jj^-t  (explicit inverse of the well-conditioned diagonal block)
+        LAUNCH(ctx_gemm(ctx, A + (j + nb) * ld + j, ld, dLinv.as<double>(), NB, P, NB, (int)rows, nb, nb, 1.0, 0.0, 0));
+        LAUNCH(qf_launch_copy_block(P, NB, A + (j + nb) * ld + j, ld, rows, nb, ctx->stream));
+        // A_22 -= L_21 L_21^t, lower part only, in column strips
+        for (long c0 = j + nb; c0 < n; c0 += STRIP) {
+            const long c1 = std::min(n, c0 + STRIP);
+            const double* Pc = P + (c0 - j - nb) * NB;
+            LAUNCH(ctx_gemm(ctx, Pc, NB, Pc, NB, A + c0 * ld + c0, ld, (int)(n - c0), (int)(c1 - c0), nb, -1.0, 1.0, 0));
+        }
+    }
+    LAUNCH(qf_launch_tril(A, ld, n, ctx->stream));
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (info) return ctx->fail(QF_ERR_INVALID, "Sigma_2 is not positive definite (s too small for this R, mp_perturbation.rs:109-110)");
+    return QF_OK;
+}
+
+// G = R R^t (m_bar x m_bar, exact small integers in fp64) from the resident fp64 copy of R
+qf_status gram_r(qf_ctx* ctx, const double* R, double* G, long ldg) {
+    LAUNCH(ctx_gemm(ctx, R, ctx->ld_nk, R, ctx->ld_nk, G, ldg, (int)ctx->m_bar, (int)ctx->m_bar, (int)ctx->nk, 1.0, 0.0, 0));
+    return QF_OK;
+}
+
+// Structured square root of the default Sigma_2 = r^2/(2 pi) ((s^2 - 1) I - (b^2+1) T T^t), T = [R; I]
+// (mp_perturbation.rs:111-139 with Sigma = s^2 I).  Block form
+//   Sigma_2 = coef [[alpha I - c R R^t, -c R], [-c R^t, (alpha - c) I]]
+// so x_b ~ N(0, beta I), beta = coef (alpha - c), and x_t | x_b ~ N(-kappa R x_b, Schur),
+// kappa = c / (alpha - c), Schur = coef (alpha I - c alpha / (alpha - c) R R^t).  Any square root of Sigma_2
+// gives the same law (mp_perturbation.rs:94-104); only the m_bar x m_bar factor of Schur is dense.
+qf_status setup_structured_sigma2(qf_ctx* ctx) {
+    const double s = ctx->prm.s, r = ctx->prm.r, c = (double)(ctx->prm.base * ctx->prm.base + 1);
+    const double alpha = s * s - 1.0, coef = r * r / (2.0 * M_PI);
+    if (!(alpha - c > 0)) return ctx->fail(QF_ERR_INVALID, "Sigma_2 is not positive definite (s^2 <= b^2 + 2)");
+    const double beta = coef * (alpha - c), kappa = c / (alpha - c);
+    const long mb = ctx->m_bar;
+    ctx->ld_mb = pad16(mb);
+    CK(ctx->dLs.ensure((size_t)mb * ctx->ld_mb * 8));
+    CK(cudaMemsetAsync(ctx->dLs.p, 0, (size_t)mb * ctx->ld_mb * 8, ctx->stream));
+    QF_TRY(gram_r(ctx, ctx->dR.as<double>(), ctx->dLs.as<double>(), ctx->ld_mb));
+    LAUNCH(qf_launch_sigma2_assemble(ctx->dLs.as<double>(), ctx->ld_mb, mb, 0, nullptr, 0, nullptr, 0, mb, nullptr, 0, alpha,
+                                     c * alpha / (alpha - c), coef, ctx->stream));
+    QF_TRY(potrf_lower(ctx, ctx->dLs.as<double>(), ctx->ld_mb, mb));
+    // fixed-point digits of x_b for the ternary product R x_b on the tensor cores: |x_b| <= 8.7 sqrt(beta)
+    ctx->sqrt_beta = std::sqrt(beta);
+    ctx->xb_limbs = 3;
+    int f = (int)std::floor(std::log2(limb_capacity(3) / (8.7 * ctx->sqrt_beta)));
+    if (f < 8) {
+        ctx->xb_limbs = 4;
+        f = (int)std::floor(std::log2(limb_capacity(4) / (8.7 * ctx->sqrt_beta)));
+    }
+    if (f < 0) return ctx->fail(QF_ERR_UNSUPPORTED, "s * r too large for the fixed-point x_b digits");
+    f = std::min(f, 30);
+    ctx->xb_fscale = std::ldexp(1.0, f);
+    std::vector<double> sc((size_t)mb, kappa / ctx->xb_fscale);
+    CK(ctx->dXbScale.ensure(sc.size() * 8));
+    CK(cudaMemcpyAsync(ctx->dXbScale.p, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pert_structured = true;
+    return QF_OK;
+}
+
 template <typename F>
 qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
     for (int64_t b0 = 0; b0 < batch; b0 += ctx->chunk) {
@@ -833,8 +940,9 @@ qf_status qf_set_a(qf_ctx* ctx, const int64_t* a) {
 
 qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const double* l, const int64_t* sk,
                                        const double* skg) {
-    if (!ctx || !r || !l || !sk || !skg) return QF_ERR_INVALID;
+    if (!ctx || !r || !sk || !skg) return QF_ERR_INVALID;
     if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");
+    ctx->has_pert = false;
     CK(cudaSetDevice(ctx->device));
     QF_TRY(upload_as_f64(ctx, r, ctx->m_bar, ctx->nk, ctx->ld_nk, ctx->dR));
     {
@@ -842,10 +950,45 @@ qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const doubl
         for (size_t i = 0; i < r64.size(); ++i) r64[i] = r[i];
         QF_TRY(upload_limbs(ctx, r64.data(), ctx->m_bar, ctx->nk, ctx->ldk_nk, 1, true, ctx->dRl));
     }
-    QF_TRY(upload_as_f64(ctx, l, ctx->m, ctx->m, ctx->ld_dim, ctx->dL));
+    if (l) {
+        QF_TRY(upload_as_f64(ctx, l, ctx->m, ctx->m, ctx->ld_dim, ctx->dL));
+        ctx->pert_structured = false;
+        ctx->l_tri = 1;
+        for (long i = 0; i < ctx->m && ctx->l_tri; ++i)
+            for (long j = i + 1; j < ctx->m; ++j)
+                if (l[i * ctx->m + j] != 0.0) { ctx->l_tri = 0; break; }
+        ctx->dLs.release();
+    } else {
+        if (!ctx->use_i8) return ctx->fail(QF_ERR_UNSUPPORTED, "structured sqrt(Sigma_2) needs the int8 tensor path");
+        ctx->dL.release();
+        QF_TRY(setup_structured_sigma2(ctx));
+    }
     QF_TRY(upload_as_f64(ctx, sk, ctx->k, ctx->k, ctx->k, ctx->dSk));
     QF_TRY(upload_as_f64(ctx, skg, ctx->k, ctx->k, ctx->k, ctx->dSkGso));
     ctx->has_pert = true;
+    return QF_OK;
+}
+
+qf_status qf_compute_sqrt_sigma_2(qf_ctx* ctx, const int8_t* r, const double* sigma, double* out) {
+    if (!ctx || !r || !out) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");
+    CK(cudaSetDevice(ctx->device));
+    const long mb = ctx->m_bar, nk = ctx->nk, m = ctx->m, ld = ctx->ld_dim, ldmb = pad16(mb);
+    const double s = ctx->prm.s, rr = ctx->prm.r, c = (double)(ctx->prm.base * ctx->prm.base + 1);
+    Dev dG, dC, dSig, dRf;
+    QF_TRY(upload_as_f64(ctx, r, mb, nk, ctx->ld_nk, dRf));
+    CK(dG.ensure((size_t)mb * ldmb * 8));
+    QF_TRY(gram_r(ctx, dRf.as<double>(), dG.as<double>(), ldmb));
+    CK(dC.ensure((size_t)m * ld * 8));
+    if (sigma) QF_TRY(upload_as_f64(ctx, sigma, m, m, ld, dSig));
+    // Sigma_2 = r^2/(2 pi) (Sigma - (b^2+1) T T^t - I)   (mp_perturbation.rs:116-135)
+    LAUNCH(qf_launch_sigma2_assemble(dC.as<double>(), ld, m, 1, dG.as<double>(), ldmb, dRf.as<double>(), ctx->ld_nk, mb,
+                                     sigma ? dSig.as<double>() : nullptr, ld, s * s, c, rr * rr / (2.0 * M_PI), ctx->stream));
+    dSig.release();
+    dG.release();
+    QF_TRY(potrf_lower(ctx, dC.as<double>(), ld, m));
+    CK(cudaMemcpy2DAsync(out, (size_t)m * 8, dC.p, (size_t)ld * 8, (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return QF_OK;
 }
 

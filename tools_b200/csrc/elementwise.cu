@@ -503,6 +503,27 @@ __global__ void add_cols_i32_kernel(int32_t* __restrict__ e, long lde, const dou
 
 }  // namespace
 
+namespace {
+__global__ void pert_xb_kernel(const double* __restrict__ G, long ldg, double* __restrict__ X2, long ldx,
+                               int8_t* __restrict__ planes, long plane_stride, long ldk, int B, int mb, int nk,
+                               double sqrt_beta, double fscale, int L, int* flag) {
+    const long total = (long)B * nk;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / nk;
+        const int j = (int)(i - b * nk);
+        const double xb = sqrt_beta * G[b * ldg + mb + j];
+        X2[b * ldx + mb + j] = xb;
+        split_digits(__double2ll_rn(xb * fscale), L, planes, plane_stride, b * ldk + j, flag);
+    }
+}
+}  // namespace
+cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
+                              int B, int mb, int nk, double sqrt_beta, double fscale, int L, int* flag, cudaStream_t stream) {
+    if (B <= 0 || nk <= 0) return cudaSuccess;
+    pert_xb_kernel<<<grid_for((long long)B * nk, TPB), TPB, 0, stream>>>(G, ldg, X2, ldx, planes, plane_stride, ldk, B, mb, nk,
+                                                                        sqrt_beta, fscale, L, flag);
+    return cudaGetLastError();
+}
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
                                       cudaStream_t stream) {

@@ -55,6 +55,10 @@ cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t s
 cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32,
                              long ldoi, int B, int M, double s, uint64_t seed, uint64_t first_target,
                              uint32_t tag, cudaStream_t stream);
+// structured perturbation (api.cu setup_structured_sigma2): X2[b][mb+j] = sqrt_beta * G[b][mb+j] and the balanced
+// base-256 digits of rint(that * fscale) into L planes of B x ldk bytes
+cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
+                              int B, int mb, int nk, double sqrt_beta, double fscale, int L, int* flag, cudaStream_t stream);
 cudaError_t qf_launch_uniform_modq(int64_t* out, long count, unsigned long long q, uint64_t seed,
                                    uint64_t first_index, cudaStream_t stream);
 cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream_t stream);
@@ -107,6 +111,13 @@ cudaError_t qf_launch_transpose_scale(const double* in, long ldin, double* out, 
 cudaError_t qf_launch_gather_cols(const double* in, long ldin, const int* cols, int ncols, double* out, long ldout,
                                   int rows, cudaStream_t stream);
 cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams* dg, cudaStream_t stream);
+// blocked Cholesky building blocks (compute_sqrt_sigma_2, mp_perturbation.rs:111-139)
+cudaError_t qf_launch_potrf_diag(double* A, long ld, int nb, double* Linv, int* info, cudaStream_t stream);
+cudaError_t qf_launch_tril(double* A, long ld, long n, cudaStream_t stream);
+cudaError_t qf_launch_copy_block(const double* in, long ldin, double* out, long ldout, long rows, int cols, cudaStream_t stream);
+cudaError_t qf_launch_sigma2_assemble(double* C, long ldc, long n, int full, const double* Gin, long ldg, const double* R,
+                                      long ldr, long mb, const double* Sigma, long lds, double diag, double gcoef, double coef,
+                                      cudaStream_t stream);
 
 // ---- gemm_i8.cu : exact integer contraction on tcgen05 (kind::i8) --------------------------
 struct I8GemmArgs {

@@ -141,3 +141,128 @@ cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, in
     ozaki_digits_kernel<<<148 * 16, 256, 0, stream>>>(U, ld, D, blk, L, scale, planes, plane_stride, ldk);
     return cudaGetLastError();
 }
+
+// ---- blocked Cholesky (per key): compute_sqrt_sigma_2, mp_perturbation.rs:111-139 --------------------
+// One diagonal block (nb <= 64) in shared memory: A_jj = L L^t in place (strict upper part zeroed) and
+// Linv = L^-1 (row-major nb x 64, lower triangular) for the panel solve  L_ij = A_ij L_jj^-t  as a GEMM.
+namespace {
+
+constexpr int POTRF_NB = 64;
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double* A, long ld, int nb, double* Linv, int* info) {
+    __shared__ double L[POTRF_NB][POTRF_NB + 1];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int t = tid; t < POTRF_NB * POTRF_NB; t += blockDim.x) {
+        const int i = t / POTRF_NB, j = t % POTRF_NB;
+        L[i][j] = (i < nb && j <= i) ? A[(long)i * ld + j] : 0.0;
+        Linv[i * POTRF_NB + j] = 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        if (tid == 0) {
+            const double d = L[j][j];
+            if (!(d > 0.0)) { bad = 1; L[j][j] = 1.0; } else L[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double inv = 1.0 / L[j][j];
+        for (int i = j + 1 + tid; i < nb; i += blockDim.x) L[i][j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: L[i][k] -= L[i][j] L[k][j],  j < k <= i
+        const int r = nb - j - 1;
+        for (int t = tid; t < r * r; t += blockDim.x) {
+            const int i = j + 1 + t / r, k = j + 1 + t % r;
+            if (k <= i) L[i][k] -= L[i][j] * L[k][j];
+        }
+        __syncthreads();
+    }
+    // Linv = L^-1 by forward substitution, one column per thread (a thread only re-reads its own writes)
+    if (tid < nb) {
+        const int c = tid;
+        Linv[c * POTRF_NB + c] = 1.0 / L[c][c];
+        for (int i = c + 1; i < nb; ++i) {
+            double acc = 0.0;
+            for (int k = c; k < i; ++k) acc += L[i][k] * Linv[k * POTRF_NB + c];
+            Linv[i * POTRF_NB + c] = -acc / L[i][i];
+        }
+    }
+    for (int t = tid; t < POTRF_NB * POTRF_NB; t += blockDim.x) {
+        const int i = t / POTRF_NB, j = t % POTRF_NB;
+        if (i < nb && j < nb) A[(long)i * ld + j] = (j <= i) ? L[i][j] : 0.0;
+    }
+    if (tid == 0 && bad) atomicOr(info, 1);
+}
+
+// out[i][j] = in[i][j] for a rows x cols block (strided copy)
+__global__ void copy_block_kernel(const double* __restrict__ in, long ldin, double* __restrict__ out, long ldout, long rows,
+                                  int cols) {
+    const long total = rows * cols;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / cols;
+        const int j = (int)(t - i * cols);
+        out[i * ldout + j] = in[i * ldin + j];
+    }
+}
+
+// C (n x n, holds G = R R^t on entry for the top-left mb x mb block when full == 0):
+//   full == 0:  C[i][j] = coef * (diag * [i==j] - gcoef * C[i][j])                      (Schur complement, n = m_bar)
+//   full == 1:  C = coef * (Sigma - gcoef * [[G, R],[R^t, I]] - I) on n = m_bar + nk, G read from Gin (m_bar x m_bar),
+//               Sigma == nullptr means diag * I                                         (mp_perturbation.rs:125-135)
+__global__ void sigma2_assemble_kernel(double* __restrict__ C, long ldc, long n, int full, const double* __restrict__ Gin,
+                                       long ldg, const double* __restrict__ R, long ldr, long mb, const double* __restrict__ Sigma,
+                                       long lds, double diag, double gcoef, double coef) {
+    const long total = n * n;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / n, j = t - i * n;
+        double v;
+        if (!full) {
+            v = coef * ((i == j ? diag : 0.0) - gcoef * C[i * ldc + j]);
+        } else {
+            double tt;
+            if (i < mb && j < mb) tt = Gin[i * ldg + j];
+            else if (i < mb) tt = R[i * ldr + (j - mb)];
+            else if (j < mb) tt = R[j * ldr + (i - mb)];
+            else tt = (i == j) ? 1.0 : 0.0;
+            const double sg = Sigma ? Sigma[i * lds + j] : (i == j ? diag : 0.0);
+            v = coef * (sg - gcoef * tt - (i == j ? 1.0 : 0.0));
+        }
+        C[i * ldc + j] = v;
+    }
+}
+
+// zero the strict upper triangle of an n x n matrix
+__global__ void tril_kernel(double* __restrict__ A, long ld, long n) {
+    const long total = n * n;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / n, j = t - i * n;
+        if (j > i) A[i * ld + j] = 0.0;
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_tril(double* A, long ld, long n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    tril_kernel<<<148 * 8, 256, 0, stream>>>(A, ld, n);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_potrf_diag(double* A, long ld, int nb, double* Linv, int* info, cudaStream_t stream) {
+    if (nb < 1 || nb > POTRF_NB) return cudaErrorInvalidValue;
+    potrf_diag_kernel<<<1, 256, 0, stream>>>(A, ld, nb, Linv, info);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_copy_block(const double* in, long ldin, double* out, long ldout, long rows, int cols, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    long long g = ((long long)rows * cols + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    copy_block_kernel<<<(int)g, 256, 0, stream>>>(in, ldin, out, ldout, rows, cols);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_sigma2_assemble(double* C, long ldc, long n, int full, const double* Gin, long ldg, const double* R,
+                                      long ldr, long mb, const double* Sigma, long lds, double diag, double gcoef, double coef,
+                                      cudaStream_t stream) {
+    sigma2_assemble_kernel<<<148 * 8, 256, 0, stream>>>(C, ldc, n, full, Gin, ldg, R, ldr, mb, Sigma, lds, diag, gcoef, coef);
+    return cudaGetLastError();
+}

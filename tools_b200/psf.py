@@ -172,10 +172,11 @@ class PSFPerturbation(_PSFBase):
             k, n = self.gp.k, self.gp.n
             r8 = np.ascontiguousarray(r_mat, dtype=np.int8)
             assert np.array_equal(r8, np.asarray(r_mat)), "R entries must fit int8"
-            l = np.ascontiguousarray(sqrt_sigma_2, dtype=np.float64)
+            # None: the backend derives its own (block-structured) square root of the default Sigma_2
+            l = None if sqrt_sigma_2 is None else np.ascontiguousarray(sqrt_sigma_2, dtype=np.float64)
             sb = np.asarray(s_basis)
             sg = np.asarray(s_gso, dtype=np.float64)
-            assert r8.shape == (self.gp.m_bar, n * k) and l.shape == (self.m, self.m)
+            assert r8.shape == (self.gp.m_bar, n * k) and (l is None or l.shape == (self.m, self.m))
             if sb.shape == (n * k, n * k):
                 blk = np.ascontiguousarray(sb[:k, :k], dtype=np.int64)
                 gblk = np.ascontiguousarray(sg[:k, :k])
@@ -191,13 +192,25 @@ class PSFPerturbation(_PSFBase):
             self._keep = (r8, l, blk, gblk)
 
     def compute_sqrt_sigma_2(self, mat_r, mat_sigma=None) -> np.ndarray:
-        """mp_perturbation.rs:111-139."""
-        return linalg.compute_sqrt_sigma_2(mat_r, self.s, self.r, self.gp.base, mat_sigma)
+        """mp_perturbation.rs:111-139: lower Cholesky factor of r^2/(2 pi) (Sigma - (b^2+1) T T^t - I), T = [R; I],
+        Sigma = s^2 I by default; blocked Cholesky on the device.  Raises QfError (QF_ERR_INVALID) when Sigma_2 is
+        not positive definite, where the reference panics (:109-110)."""
+        r8 = np.ascontiguousarray(mat_r, dtype=np.int8)
+        assert np.array_equal(r8, np.asarray(mat_r)) and r8.shape == (self.gp.m_bar, self.gp.n * self.gp.k)
+        sig = None if mat_sigma is None else np.ascontiguousarray(mat_sigma, dtype=np.float64)
+        assert sig is None or sig.shape == (self.m, self.m)
+        out = np.empty((self.m, self.m), dtype=np.float64)
+        self.ctx.call("qf_compute_sqrt_sigma_2", _ffi.ptr(r8), _ffi.ptr(sig), _ffi.ptr(out))
+        return out
 
-    def trap_gen(self, seed=None, full_gadget_basis: bool = None):
-        """mp_perturbation.rs:221-244."""
+    def trap_gen(self, seed=None, full_gadget_basis: bool = None, dense_sqrt_sigma_2: bool = None):
+        """mp_perturbation.rs:221-244.  dense_sqrt_sigma_2=False leaves the second trapdoor component None: the
+        backend then uses its block-structured square root of the default Sigma_2 (same law, ~4x less work per
+        target); default: dense (the reference's m x m matrix) up to m = 2048, structured above."""
         a, r = _trap_gen_classical(self, seed)
-        sqrt_sigma_2 = self.compute_sqrt_sigma_2(r)
+        if dense_sqrt_sigma_2 is None:
+            dense_sqrt_sigma_2 = self.m <= 2048
+        sqrt_sigma_2 = self.compute_sqrt_sigma_2(r) if dense_sqrt_sigma_2 else None
         k, n = self.gp.k, self.gp.n
         if full_gadget_basis is None:
             full_gadget_basis = n * k <= 1024
