@@ -96,6 +96,12 @@ struct qf_ctx {
     bool pert_structured = false;
     int l_tri = 1;   // supplied sqrt(Sigma_2) is lower triangular (the Cholesky factor): skip the zero half
     Dev dLs, dXbScale;
+    // x_2 = L g on the tensor cores: fixed-point digit planes of L (one scale per row) times fixed-point normals
+    bool pert_i8 = false;
+    Dev dLl, dLlScale;
+    long ldk_l = 0, l_dim = 0;
+    int lg_limbs = 3, ll_limbs = 4;
+    double g_fscale = 0;
     long ld_mb = 0;
     double sqrt_beta = 0, xb_fscale = 0;
     int xb_limbs = 3;
@@ -391,6 +397,8 @@ qf_status ring_f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU
 // ---------------------------------------------------------------------------
 // PSFPerturbation::samp_p on one chunk (mp_perturbation.rs:304-336)
 // ---------------------------------------------------------------------------
+qf_status pert_lg_i8(qf_ctx* ctx, const int8_t* gp, long gplane, int Bc, double* X2, long ldx, bool tri);
+
 qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
     const long ldm = ctx->ld_dim, ldn = ctx->ld_n, ldnk = ctx->ld_nk;
     const long C = ctx->chunk;
@@ -405,15 +413,30 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     double* Z = ctx->w[3].as<double>();
     int64_t* V = ctx->w[4].as<int64_t>();
     // p <- D_{Z^m, r sqrt(Sigma_2)} : x2 = sqrt(Sigma_2) * N(0,I), p_i <- D_{Z, r, x2_i}   (:315)
-    LAUNCH(qf_launch_normal_fill(G, ldm, Bc, (int)ctx->m, seed, first, QF_STREAM_PERT_NORMAL, ctx->stream));
-    if (ctx->pert_structured) {
-        // x_b = sqrt(beta) g_b (kept exact in x2, fixed-point digits for the tensor cores);
-        // x_t = L_s g_t - kappa R x_b
+    const bool st = ctx->pert_structured;
+    if (st) CK(ctx->w[5].ensure((size_t)ctx->xb_limbs * C * ctx->ldk_nk));
+    if (ctx->pert_i8) {
+        // normals straight to fixed-point digits (no fp64 copy of g), x_2 = L g on tcgen05
+        const long gplane = C * ctx->ldk_l;
+        LAUNCH(qf_launch_pert_normal_digits(Bc, (int)ctx->m, st ? (int)ctx->m_bar : (int)ctx->m, seed, first,
+                                            ctx->w[0].as<int8_t>(), gplane, ctx->ldk_l, ctx->lg_limbs, ctx->g_fscale, X2, ldm,
+                                            st ? ctx->w[5].as<int8_t>() : nullptr, C * ctx->ldk_nk, ctx->ldk_nk, ctx->xb_limbs,
+                                            ctx->sqrt_beta, ctx->xb_fscale, ctx->dFlag.as<int>(), ctx->stream));
+        QF_TRY(pert_lg_i8(ctx, ctx->w[0].as<int8_t>(), gplane, Bc, X2, ldm, st ? true : ctx->l_tri != 0));
+    } else {
+        LAUNCH(qf_launch_normal_fill(G, ldm, Bc, (int)ctx->m, seed, first, QF_STREAM_PERT_NORMAL, ctx->stream));
+        if (st) {
+            // x_b = sqrt(beta) g_b (kept exact in x2, fixed-point digits for the tensor cores); x_t = L_s g_t
+            LAUNCH(qf_launch_pert_xb(G, ldm, X2, ldm, ctx->w[5].as<int8_t>(), C * ctx->ldk_nk, ctx->ldk_nk, Bc, (int)ctx->m_bar,
+                                     (int)ctx->nk, ctx->sqrt_beta, ctx->xb_fscale, ctx->xb_limbs, ctx->dFlag.as<int>(), ctx->stream));
+            LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dLs.as<double>(), ctx->ld_mb, X2, ldm, Bc, (int)ctx->m_bar, (int)ctx->m_bar, 1.0, 0.0, 1));
+        } else {
+            LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, ctx->l_tri));
+        }
+    }
+    if (st) {
+        // x_t -= kappa R x_b  (ternary R, fixed-point x_b) on tcgen05
         const long ldk = ctx->ldk_nk, plane = C * ldk;
-        CK(ctx->w[5].ensure((size_t)ctx->xb_limbs * plane));
-        LAUNCH(qf_launch_pert_xb(G, ldm, X2, ldm, ctx->w[5].as<int8_t>(), plane, ldk, Bc, (int)ctx->m_bar, (int)ctx->nk,
-                                 ctx->sqrt_beta, ctx->xb_fscale, ctx->xb_limbs, ctx->dFlag.as<int>(), ctx->stream));
-        LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dLs.as<double>(), ctx->ld_mb, X2, ldm, Bc, (int)ctx->m_bar, (int)ctx->m_bar, 1.0, 0.0, 1));
         I8GemmArgs g{};
         g.x = ctx->w[5].as<int8_t>(); g.ldx = ldk; g.x_plane = plane;
         g.w = ctx->dRl.p; g.ldw = ldk; g.w_plane = (long)ctx->m_bar * ldk;
@@ -423,8 +446,6 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
         g.flag = ctx->dFlag.as<int>();
         g.scale = ctx->dXbScale.as<double>();
         LAUNCH(ctx_gemm_i8(ctx, g));
-    } else {
-        LAUNCH(ctx_gemm(ctx, G, ldm, ctx->dL.as<double>(), ldm, X2, ldm, Bc, (int)ctx->m, (int)ctx->m, 1.0, 0.0, ctx->l_tri));
     }
     LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
                             ctx->stream));
@@ -766,6 +787,56 @@ qf_status setup_structured_sigma2(qf_ctx* ctx) {
     return QF_OK;
 }
 
+// Fixed-point digit planes of the dense factor L (sqrt(Sigma_2), or the Schur factor of the structured form) for
+// x_2 = L g on tcgen05: L rows scaled to ll_limbs balanced base-256 digits (relative resolution 2^-30 of the row
+// maximum), normals g quantised to 2^-20 (their fp32 Box-Muller source carries 24 bits).  The covariance of x_2
+// then differs from Sigma_2 by a relative 2^-29, far below what the rounding step D_{Z,r,x_2} can resolve.
+qf_status setup_pert_i8(qf_ctx* ctx) {
+    ctx->pert_i8 = false;
+    const char* env = getenv("QF_DISABLE_PERT_I8");
+    const long dimL = ctx->pert_structured ? ctx->m_bar : ctx->m;
+    if (!ctx->use_i8 || (env && env[0] == '1') || dimL < 512) return QF_OK;
+    const double* L = ctx->pert_structured ? ctx->dLs.as<double>() : ctx->dL.as<double>();
+    const long ldL = ctx->pert_structured ? ctx->ld_mb : ctx->ld_dim;
+    ctx->l_dim = dimL;
+    ctx->ldk_l = (dimL + 127) / 128 * 128;
+    const size_t bytes = (size_t)ctx->ll_limbs * dimL * ctx->ldk_l;
+    CK(ctx->dLl.ensure(bytes));
+    CK(ctx->dLlScale.ensure((size_t)dimL * 8));
+    CK(cudaMemsetAsync(ctx->dLl.p, 0, bytes, ctx->stream));
+    ctx->g_fscale = std::ldexp(1.0, (int)std::floor(std::log2(limb_capacity(ctx->lg_limbs) / 6.9)));
+    LAUNCH(qf_launch_fixed_rows_prepare(L, ldL, (int)dimL, (int)dimL, ctx->ll_limbs, -1.0 / ctx->g_fscale, ctx->dLlScale.as<double>(),
+                                        ctx->dLl.as<int8_t>(), dimL * ctx->ldk_l, ctx->ldk_l, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pert_i8 = true;
+    return QF_OK;
+}
+
+// X2[:, 0:l_dim] = L g from the digit planes of g (gp) and of L: one launch per 1024-row block of L, K limited to
+// the block's last column when L is lower triangular; K chunked so that the s32 accumulators cannot overflow.
+qf_status pert_lg_i8(qf_ctx* ctx, const int8_t* gp, long gplane, int Bc, double* X2, long ldx, bool tri) {
+    const long dimL = ctx->l_dim, ldk = ctx->ldk_l;
+    CK(cudaMemset2DAsync(X2, (size_t)ldx * 8, 0, (size_t)dimL * 8, (size_t)Bc, ctx->stream));
+    const long kmax = (131071 / std::min(ctx->lg_limbs, ctx->ll_limbs)) / 128 * 128;
+    for (long rb = 0; rb < dimL; rb += 1024) {
+        const long nrows = std::min(1024L, dimL - rb);
+        const long kend = tri ? std::min(dimL, rb + nrows) : dimL;
+        for (long k0 = 0; k0 < kend; k0 += kmax) {
+            const long kk = std::min(kmax, kend - k0);
+            I8GemmArgs g{};
+            g.x = gp + k0; g.ldx = ldk; g.x_plane = gplane;
+            g.w = ctx->dLl.as<int8_t>() + rb * ldk + k0; g.ldw = ldk; g.w_plane = dimL * ldk;
+            g.LX = ctx->lg_limbs; g.LW = ctx->ll_limbs; g.w_signed = 1;
+            g.B = Bc; g.N = (int)nrows; g.K = (int)kk;
+            g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = X2 + rb; g.ldout = ldx;
+            g.flag = ctx->dFlag.as<int>();
+            g.scale = ctx->dLlScale.as<double>() + rb;
+            LAUNCH(ctx_gemm_i8(ctx, g));
+        }
+    }
+    return QF_OK;
+}
+
 template <typename F>
 qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
     for (int64_t b0 = 0; b0 < batch; b0 += ctx->chunk) {
@@ -965,6 +1036,7 @@ qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const doubl
     }
     QF_TRY(upload_as_f64(ctx, sk, ctx->k, ctx->k, ctx->k, ctx->dSk));
     QF_TRY(upload_as_f64(ctx, skg, ctx->k, ctx->k, ctx->k, ctx->dSkGso));
+    QF_TRY(setup_pert_i8(ctx));
     ctx->has_pert = true;
     return QF_OK;
 }

@@ -517,6 +517,45 @@ __global__ void pert_xb_kernel(const double* __restrict__ G, long ldg, double* _
     }
 }
 }  // namespace
+namespace {
+__global__ void pert_normal_digits_kernel(int B, int M, int split, uint64_t seed, uint64_t first_target,
+                                          int8_t* __restrict__ gplanes, long gplane_stride, long ldkg, int LG, double gscale,
+                                          double* __restrict__ X2, long ldx, int8_t* __restrict__ bplanes, long bplane_stride,
+                                          long ldkb, int LB, double sqrt_beta, double bscale, int* flag) {
+    const int half = (M + 1) >> 1;
+    const long total = (long)B * half;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / half;
+        const int p = (int)(i - b * half);
+        Philox rng;
+        rng.init(seed, (first_target + (uint64_t)b) * (uint64_t)half + (uint64_t)p, QF_STREAM_PERT_NORMAL);
+        float nn[2];
+        rng.normal2(nn[0], nn[1]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int j = 2 * p + t;
+            if (j >= M) break;
+            if (j < split) {
+                split_digits(__double2ll_rn((double)nn[t] * gscale), LG, gplanes, gplane_stride, b * ldkg + j, flag);
+            } else {
+                const double xb = sqrt_beta * (double)nn[t];
+                X2[b * ldx + j] = xb;
+                split_digits(__double2ll_rn(xb * bscale), LB, bplanes, bplane_stride, b * ldkb + (j - split), flag);
+            }
+        }
+    }
+}
+}  // namespace
+cudaError_t qf_launch_pert_normal_digits(int B, int M, int split, uint64_t seed, uint64_t first_target, int8_t* gplanes,
+                                         long gplane_stride, long ldkg, int LG, double gscale, double* X2, long ldx,
+                                         int8_t* bplanes, long bplane_stride, long ldkb, int LB, double sqrt_beta, double bscale,
+                                         int* flag, cudaStream_t stream) {
+    if (B <= 0 || M <= 0) return cudaSuccess;
+    pert_normal_digits_kernel<<<grid_for((long long)B * ((M + 1) / 2), TPB), TPB, 0, stream>>>(
+        B, M, split, seed, first_target, gplanes, gplane_stride, ldkg, LG, gscale, X2, ldx, bplanes, bplane_stride, ldkb, LB,
+        sqrt_beta, bscale, flag);
+    return cudaGetLastError();
+}
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
                               int B, int mb, int nk, double sqrt_beta, double fscale, int L, int* flag, cudaStream_t stream) {
     if (B <= 0 || nk <= 0) return cudaSuccess;

@@ -59,6 +59,14 @@ cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, lo
 // base-256 digits of rint(that * fscale) into L planes of B x ldk bytes
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
                               int B, int mb, int nk, double sqrt_beta, double fscale, int L, int* flag, cudaStream_t stream);
+// N(0,1) draws of the perturbation (same Philox stream as qf_launch_normal_fill) written as fixed-point digits:
+// coordinates j < split: LG planes of rint(g * gscale) at gplanes[b * ldkg + j];
+// coordinates j >= split (structured square root only): x_b = sqrt_beta * g into X2[b][j] and LB planes of
+// rint(x_b * bscale) at bplanes[b * ldkb + (j - split)].
+cudaError_t qf_launch_pert_normal_digits(int B, int M, int split, uint64_t seed, uint64_t first_target, int8_t* gplanes,
+                                         long gplane_stride, long ldkg, int LG, double gscale, double* X2, long ldx,
+                                         int8_t* bplanes, long bplane_stride, long ldkb, int LB, double sqrt_beta, double bscale,
+                                         int* flag, cudaStream_t stream);
 cudaError_t qf_launch_uniform_modq(int64_t* out, long count, unsigned long long q, uint64_t seed,
                                    uint64_t first_index, cudaStream_t stream);
 cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream_t stream);
@@ -113,6 +121,8 @@ cudaError_t qf_launch_gather_cols(const double* in, long ldin, const int* cols, 
 cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams* dg, cudaStream_t stream);
 // blocked Cholesky building blocks (compute_sqrt_sigma_2, mp_perturbation.rs:111-139)
 cudaError_t qf_launch_potrf_diag(double* A, long ld, int nb, double* Linv, int* info, cudaStream_t stream);
+cudaError_t qf_launch_fixed_rows_prepare(const double* L, long ld, int rows, int cols, int Ldig, double mult, double* scale,
+                                         int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
 cudaError_t qf_launch_tril(double* A, long ld, long n, cudaStream_t stream);
 cudaError_t qf_launch_copy_block(const double* in, long ldin, double* out, long ldout, long rows, int cols, cudaStream_t stream);
 cudaError_t qf_launch_sigma2_assemble(double* C, long ldc, long n, int full, const double* Gin, long ldg, const double* R,

@@ -266,3 +266,61 @@ cudaError_t qf_launch_sigma2_assemble(double* C, long ldc, long n, int full, con
     sigma2_assemble_kernel<<<148 * 8, 256, 0, stream>>>(C, ldc, n, full, Gin, ldg, R, ldr, mb, Sigma, lds, diag, gcoef, coef);
     return cudaGetLastError();
 }
+
+// ---- fixed-point digit planes of a dense real key matrix, one scale per row -------------------------
+// (sqrt(Sigma_2) or its Schur factor for the perturbation contraction x_2 = L g on the tensor cores)
+// planes[l][i][j] = digit l of rint(L[i][j] * 2^e_i), 2^e_i chosen so that the row fits Ldig balanced digits;
+// scale[i] = mult * 2^-e_i  (the tensor-core epilogue computes out -= V * scale; mult carries the sign and the
+// fixed-point scale of the other operand).
+namespace {
+
+__global__ void scale_vec_kernel(double* __restrict__ v, int n, double mult) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= mult;
+}
+
+__global__ void fixed_rows_scale_kernel(const double* __restrict__ L, long ld, int rows, int cols, int Ldig,
+                                        double* __restrict__ scale) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long i = (long)blockIdx.x * wpb + (threadIdx.x >> 5); i < rows; i += (long)gridDim.x * wpb) {
+        double mx = 0.0;
+        for (int j = lane; j < cols; j += 32) mx = fmax(mx, fabs(L[i * ld + j]));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+            const int e = (mx > 0.0) ? (8 * Ldig - 2) - (ilogb(mx) + 1) : 0;
+            scale[i] = ldexp(1.0, -e);
+        }
+    }
+}
+
+__global__ void fixed_rows_digits_kernel(const double* __restrict__ L, long ld, int rows, int cols, int Ldig,
+                                         const double* __restrict__ scale, int8_t* __restrict__ planes, long plane_stride,
+                                         long ldk) {
+    const long total = (long)rows * cols;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / cols;
+        const int j = (int)(t - i * cols);
+        long long v = __double2ll_rn(L[i * ld + j] / scale[i]);
+        for (int l = 0; l < Ldig; ++l) {
+            long long lo = ((v + 128) & 255) - 128;
+            if (l == Ldig - 1) lo = v;
+            planes[l * plane_stride + i * ldk + j] = (int8_t)lo;
+            v = (v - lo) >> 8;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t qf_launch_fixed_rows_prepare(const double* L, long ld, int rows, int cols, int Ldig, double mult, double* scale,
+                                         int8_t* planes, long plane_stride, long ldk, cudaStream_t stream) {
+    int g = (rows + 7) / 8;
+    if (g > 148 * 32) g = 148 * 32;
+    fixed_rows_scale_kernel<<<g, 256, 0, stream>>>(L, ld, rows, cols, Ldig, scale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    fixed_rows_digits_kernel<<<148 * 16, 256, 0, stream>>>(L, ld, rows, cols, Ldig, scale, planes, plane_stride, ldk);
+    scale_vec_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(scale, rows, mult);
+    return cudaGetLastError();
+}
