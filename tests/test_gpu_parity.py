@@ -146,6 +146,15 @@ def test_f_a_classical_bit_exact(T, n, q, s, r):
     big[1, gp.m - 1] = -int(np.floor(s * r * np.sqrt(gp.m)))
     u2, f2 = psf.f_a_batch(a, big)
     assert f2.all() and np.array_equal(u2, O.f_a_classical_batch(a, big, q))
+    # the same huge entry inside an ordinary batch (the fused kernel's optimistic narrow-digit launch must notice it
+    # and re-run at full width for every row)
+    mixed = sig.copy()
+    mixed[17] = 0
+    mixed[17, 5] = big[0, 3]
+    mixed[B - 1] = 0
+    mixed[B - 1, gp.m - 2] = -big[0, 3]
+    u3, f3 = psf.f_a_batch(a, mixed)
+    assert f3.all() and np.array_equal(u3, O.f_a_classical_batch(a, mixed, q))
 
 
 def test_f_a_domain_errors(T):

@@ -122,11 +122,12 @@ struct qf_ctx {
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];
-    Dev dNorm, dFlag, io_a, io_b, io_c, io_a2;
+    Dev dNorm, dFlag, dRetry, io_a, io_b, io_c, io_a2;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // tcgen05 int8 path for the exact integer contractions
     bool use_i8 = true;
+    bool fused_fa = true;  // f_a: digit split fused into the contraction (gemm_i8_fused.cu)
     long ldk_dim = 0, ldk_nk = 0;
     int x_limbs = 0;       // digits for Domain-sized values (|.| <= sqrt(bound))
     int a_limbs = 0;       // u8 digits of a residue
@@ -322,6 +323,44 @@ qf_status gemm_chunks(qf_ctx* ctx, const double* X, long ldx, Dev* W, int nchunk
 // ---------------------------------------------------------------------------
 qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uint8_t* dFlags) {
     const long ldm = ctx->ld_dim, ldn = ctx->ld_n;
+    if (ctx->use_i8 && ctx->fused_fa && ctx->x_limbs <= 4) {
+        // one kernel: sigma (int32) -> digits in shared memory -> tcgen05, norms on the way
+        CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+        int64_t* out = dU;
+        if (!out) {  // check_domain only: the contraction still runs (cheap), into scratch
+            CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
+            out = ctx->w[1].as<int64_t>();
+        }
+        FaFusedArgs g{};
+        g.x = dSigma; g.ldx = ctx->dim;
+        g.w = ctx->dAl.p; g.ldw = ctx->ldk_dim; g.w_plane = (long)ctx->n * ctx->ldk_dim;
+        g.LX = ctx->x_limbs; g.LW = ctx->a_limbs; g.w_signed = 0;
+        g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->m;
+        g.q = ctx->prm.q; g.out = out; g.ldout = ctx->n;
+        g.norm2 = ctx->dNorm.as<unsigned long long>();
+        CK(ctx->dRetry.ensure(sizeof(int)));
+        g.retry_flag = ctx->dRetry.as<int>();
+        qf_ctx::ProfRec rec{};
+        if (ctx->prof) {
+            for (cudaEvent_t* e : {&rec.a, &rec.b}) {
+                if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+                else CK(cudaEventCreate(e));
+            }
+            rec.kind = 1;
+            rec.flops = 2.0 * Bc * (double)ctx->n * ctx->m;
+            rec.issued = rec.flops * g.LX * g.LW;
+            CK(cudaEventRecord(rec.a, ctx->stream));
+            g.mma_units = ctx->dMma.p ? ctx->dMma.as<unsigned long long>() : nullptr;
+        }
+        LAUNCH(qf_launch_f_a_fused(g, ctx->stream));
+        if (ctx->prof) {
+            CK(cudaEventRecord(rec.b, ctx->stream));
+            ctx->prof_recs.push_back(rec);
+        }
+        if (dFlags)
+            LAUNCH(qf_launch_domain_flags(ctx->dNorm.as<unsigned long long>(), ctx->bound, dFlags, Bc, ctx->stream));
+        return QF_OK;
+    }
     if (ctx->use_i8) {
         const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
         CK(ctx->w[0].ensure((size_t)ctx->x_limbs * plane));
@@ -910,11 +949,14 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
     {
         const char* env = getenv("QF_DISABLE_I8");
         ctx->use_i8 = !(env && env[0] == '1');
+        const char* envf = getenv("QF_DISABLE_FUSED_FA");
+        ctx->fused_fa = !(envf && envf[0] == '1');
     }
-    // default chunk: keep ~6 fp64 work matrices within ~12 GB
+    // default chunk: keep ~8 fp64-sized work matrices within ~16 GB; whole waves of 148 SMs x 128-target tiles
     long per_target = ctx->ld_dim * 8 * 8;
-    long c = (long)((12LL << 30) / std::max(1L, per_target));
-    c = std::max(128L, std::min(65536L, c / 128 * 128));
+    long c = (long)((16LL << 30) / std::max(1L, per_target));
+    c = std::max(128L, std::min(75776L, c / 128 * 128));
+    if (c >= 148 * 128) c = c / (148 * 128) * (148 * 128);
     ctx->chunk = c;
     if (ctx->dFlag.ensure(sizeof(int)) != cudaSuccess || cudaMemset(ctx->dFlag.p, 0, sizeof(int)) != cudaSuccess) {
         delete ctx;

@@ -1,0 +1,347 @@
+// f_a = A sigma mod q (gpv.rs:190-193, mp_perturbation.rs:366-369) with the digit split of sigma fused into the
+// tensor-core contraction: sigma is read from HBM once as int32, converted to balanced base-256 digit planes by
+// the CTA's own warps straight into the SWIZZLE_128B shared-memory operand tiles that tcgen05.mma consumes, and
+// the squared norms of check_domain (gpv.rs:219-224) are accumulated from the same registers.  No digit planes
+// ever touch HBM (the unfused path writes and re-reads them: 2x the algorithmic traffic plus a second launch).
+//
+// CTA = 10 warps: warps 0..7 convert (one 128-byte digit row per warp instruction: coalesced 512-byte global reads,
+// conflict-free 4-byte shared stores; the 16 rows of the NEXT k block are already in flight in registers while the
+// current ones are converted, i.e. 64 KB of loads outstanding per SM) and later run the epilogue (TMEM lane group =
+// warp % 4), warp 8 feeds the key digits (A, u8 limbs) through TMA, warp 9 owns TMEM and issues the MMAs.  One 128-target x nt-coordinate tile
+// per CTA, n tiles adjacent in the grid so that the CTAs sharing a block of sigma run together (L2 reuse).
+// Digit planes of sigma that are zero in a whole 128 x 128 block are skipped by the MMA issuer.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace {
+
+using namespace tc05;
+constexpr int CONV_WARPS = 16, ROWS_PER_WARP = 128 / CONV_WARPS;
+constexpr int FUSED_THREADS = (CONV_WARPS + 2) * 32;
+constexpr int MAX_LX = 4;
+
+struct FusedParams {
+    const int32_t* x; long ldx;
+    int B, N, K, LX, LW, nt, stages, w_signed, vec;
+    unsigned long long q;
+    int64_t* out; long ldout;
+    unsigned long long* norm2;
+    int n_tiles;
+    unsigned long long* mma_units;
+    int* overflow;        // optimistic launch (CHECK): set when some value needs one digit more than LXT
+    const int* run_if;    // conditional launch: exit at once unless *run_if != 0
+};
+
+// LXT digits of sigma are multiplied.  CHECK: the digits are those of the (LXT+1)-digit representation and the kernel
+// reports through p.overflow when a value has a non-zero digit LXT (the caller then re-runs with one digit more).
+template <int LXT, bool CHECK>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
+    if (p.run_if != nullptr && *p.run_if == 0) return;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int x_tile = TILE_M * BLOCK_K, w_tile = p.nt * BLOCK_K;
+    const int stage_bytes = p.LX * x_tile + p.LW * w_tile;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
+    volatile uint8_t* nzflag = (volatile uint8_t*)(tmem_slot + 2);  // [stage][converter warp]: non-zero plane mask
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int ND = p.LX + p.LW - 1;
+    const int tile_n = blockIdx.x % p.n_tiles, tile_m = blockIdx.x / p.n_tiles;
+    const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1 + CONV_WARPS);   // TMA expect_tx arrival + one arrival per converter warp
+            mbar_init(&empty_bar[s], 1);  // tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == CONV_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp < 4) {  // zero the accumulators: every MMA accumulates (one MMA spans several adjacent digit accumulators)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (warp == CONV_WARPS) {
+        // ===== TMA producer: key digit planes =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sw = smem + (size_t)stage * stage_bytes + p.LX * x_tile;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(p.LW * w_tile));
+                for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == CONV_WARPS + 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | ((uint32_t)(p.w_signed ? 1 : 0) << 10) | ((uint32_t)(TILE_M >> 4) << 24);
+        const int G = max(1, min(p.LW, 256 / p.nt));
+        const uint64_t desc0 = make_desc(smem_u32(smem));
+        int stage = 0;
+        uint32_t phase = 0;
+        unsigned long long units = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                uint32_t mk = 0;
+#pragma unroll
+                for (int w = 0; w < CONV_WARPS; ++w) mk |= (uint32_t)nzflag[stage * CONV_WARPS + w];
+                const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
+                const uint32_t sw_off = sx_off + ((uint32_t)(p.LX * x_tile) >> 4);
+                for (int j = 0; j < p.LX; ++j) {
+                    if (!((mk >> j) & 1u)) continue;
+                    const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
+                    for (int i0 = 0; i0 < p.LW; i0 += G) {
+                        const int g = min(G, p.LW - i0);
+                        const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
+                        const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
+                        const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
+#pragma unroll
+                        for (int kk = 0; kk < BLOCK_K / 32; ++kk)
+                            mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
+                        units += (unsigned long long)g;
+                    }
+                }
+                mma_commit(&empty_bar[stage]);
+                if (kb == num_kb - 1) mma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (lane == 0 && p.mma_units && units)
+            atomicAdd(p.mma_units, units * (2ull * TILE_M * BLOCK_K) * (unsigned long long)p.nt);
+    } else {
+        // ===== converters (warps 0..7): int32 sigma -> digit planes in shared memory; then the epilogue =====
+        const bool do_norm = p.norm2 != nullptr && tile_n == 0;
+        unsigned long long acc[ROWS_PER_WARP];
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_WARP; ++i) acc[i] = 0;
+        const int32_t* xrow = p.x + ((long)m0 + warp * ROWS_PER_WARP) * p.ldx + lane * 4;
+        const int rows_here = max(0, min(ROWS_PER_WARP, p.B - (m0 + warp * ROWS_PER_WARP)));
+        // fast path: all rows of this warp exist and are 16-byte aligned -> unpredicated 128-bit loads
+        const bool fast_rows = p.vec && rows_here == ROWS_PER_WARP;
+        const long ldx4 = p.ldx >> 2;  // row stride in int4 units (fast path only)
+        auto load_rows = [&](int4 (&dst)[ROWS_PER_WARP], int kb) {
+            if (fast_rows && (kb + 1) * BLOCK_K <= p.K) {
+                const int4* src = reinterpret_cast<const int4*>(xrow) + kb * (BLOCK_K / 4);
+#pragma unroll
+                for (int i = 0; i < ROWS_PER_WARP; ++i) dst[i] = src[i * ldx4];
+                return;
+            }
+            const int col = kb * BLOCK_K + lane * 4;
+#pragma unroll 1
+            for (int i = 0; i < ROWS_PER_WARP; ++i) {
+                int4 v = make_int4(0, 0, 0, 0);
+                if (i < rows_here && kb < num_kb) {
+                    const int32_t* src = xrow + (long)i * p.ldx + kb * BLOCK_K;
+                    if (col + 0 < p.K) v.x = src[0];
+                    if (col + 1 < p.K) v.y = src[1];
+                    if (col + 2 < p.K) v.z = src[2];
+                    if (col + 3 < p.K) v.w = src[3];
+                }
+#pragma unroll
+                for (int j = 0; j < ROWS_PER_WARP; ++j)
+                    if (j == i) dst[j] = v;  // static register indices
+            }
+        };
+        // shared-memory byte offset of this lane's 4 digits in row (warp * R + i): SWIZZLE_128B puts 16-byte chunk c
+        // of row r at chunk c ^ (r & 7); warp * R is a multiple of 8, so r & 7 = i & 7
+        const uint32_t lane_off = (uint32_t)(warp * ROWS_PER_WARP * 128 + (lane & 3) * 4);
+        const uint32_t chunk = (uint32_t)(lane >> 2);
+        int stage = 0;
+        uint32_t phase = 0;
+        auto convert_rows = [&](const int4 (&src)[ROWS_PER_WARP]) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sx = smem + (size_t)stage * stage_bytes + lane_off;
+            uint32_t nz0 = 0, nz1 = 0, nz2 = 0, nz3 = 0, ovf = 0;
+#pragma unroll
+            for (int i = 0; i < ROWS_PER_WARP; ++i) {
+                const int w0 = src[i].x, w1 = src[i].y, w2 = src[i].z, w3 = src[i].w;
+                if (do_norm)
+                    acc[i] += (unsigned long long)((long long)w0 * w0) + (unsigned long long)((long long)w1 * w1) +
+                              (unsigned long long)((long long)w2 * w2) + (unsigned long long)((long long)w3 * w3);
+                uint8_t* dst = sx + i * 128 + ((chunk ^ (uint32_t)(i & 7)) << 4);
+                // Balanced digits d_l of v: v_0 = v, d_l = low byte of v_l (as s8), v_{l+1} = (v_l + 128) >> 8.
+                // With t = v + 0x8080 (0x808080 for four digits): d_0 = byte0(t) ^ 0x80, d_1 = byte1(t) ^ 0x80,
+                // d_2 = byte2(t) [^ 0x80 when a fourth digit follows], d_3 = byte3(t): one add per value, the 4 x 4
+                // byte transpose done with PRMT.
+                constexpr int LB = LXT + (CHECK ? 1 : 0);  // digits of the representation
+                constexpr int BIAS = LB == 1 ? 0 : LB == 2 ? 0x80 : LB == 3 ? 0x8080 : 0x808080;
+                const uint32_t t0 = (uint32_t)(w0 + BIAS), t1 = (uint32_t)(w1 + BIAS), t2 = (uint32_t)(w2 + BIAS),
+                               t3 = (uint32_t)(w3 + BIAS);
+                if (CHECK) ovf |= (t0 | t1) | (t2 | t3);
+                const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140);  // b0 b0' b1 b1'
+                {
+                    const uint32_t pk = __byte_perm(lo01, lo23, 0x5410) ^ (LB > 1 ? 0x80808080u : 0u);
+                    *reinterpret_cast<uint32_t*>(dst) = pk;
+                    nz0 |= pk;
+                }
+                if (LXT > 1) {
+                    const uint32_t pk = __byte_perm(lo01, lo23, 0x7632) ^ (LB > 2 ? 0x80808080u : 0u);
+                    *reinterpret_cast<uint32_t*>(dst + x_tile) = pk;
+                    nz1 |= pk;
+                }
+                if (LXT > 2) {
+                    const uint32_t hi01 = __byte_perm(t0, t1, 0x7362), hi23 = __byte_perm(t2, t3, 0x7362);  // b2 b2' b3 b3'
+                    const uint32_t pk = __byte_perm(hi01, hi23, 0x5410) ^ (LB > 3 ? 0x80808080u : 0u);
+                    *reinterpret_cast<uint32_t*>(dst + 2 * x_tile) = pk;
+                    nz2 |= pk;
+                    if (LXT > 3) {
+                        const uint32_t pk3 = __byte_perm(hi01, hi23, 0x7632);
+                        *reinterpret_cast<uint32_t*>(dst + 3 * x_tile) = pk3;
+                        nz3 |= pk3;
+                    }
+                }
+            }
+            uint32_t nzm = (nz0 ? 1u : 0u) | (nz1 ? 2u : 0u) | (nz2 ? 4u : 0u) | (nz3 ? 8u : 0u);
+            if (CHECK && (ovf >> (8 * LXT)) != 0u) nzm |= 0x80u;  // a digit beyond LXT is non-zero
+            nzm = __reduce_or_sync(0xffffffffu, nzm);
+            if (CHECK && (nzm & 0x80u) && lane == 0) atomicOr(p.overflow, 1);
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) {
+                nzflag[stage * CONV_WARPS + warp] = (uint8_t)nzm;
+                mbar_arrive(&full_bar[stage]);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        };
+        // two register buffers, the k loop unrolled by two: the 16 row loads of the next k block are in flight while
+        // the current block is converted, without register moves between the buffers
+        int4 buf_a[ROWS_PER_WARP], buf_b[ROWS_PER_WARP];
+        load_rows(buf_a, 0);
+        for (int kb = 0; kb < num_kb; kb += 2) {
+            load_rows(buf_b, kb + 1);
+            convert_rows(buf_a);
+            if (kb + 1 < num_kb) {
+                load_rows(buf_a, kb + 2);
+                convert_rows(buf_b);
+            }
+        }
+        if (do_norm) {
+#pragma unroll
+            for (int i = 0; i < ROWS_PER_WARP; ++i) {
+                unsigned long long a = acc[i];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                const long grow = (long)m0 + warp * ROWS_PER_WARP + i;
+                if (lane == 0 && grow < p.B) p.norm2[grow] = a;
+            }
+        }
+        // ---- epilogue: V = sum_d 256^d D_d, reduce mod q ----
+        const int lg = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + lg * 32 + lane;
+        for (int c0 = (warp >> 2) * 16; c0 < p.nt; c0 += 16 * (CONV_WARPS / 4)) {
+            __int128 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = 0;
+            for (int d = 0; d < ND; ++d) {
+                int32_t t[16];
+                tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] += ((__int128)t[c]) << (8 * d);
+            }
+            if (row < p.B) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int n = n0 + c0 + c;
+                    if (n >= p.N) continue;
+                    long long r;
+                    if (p.q) {
+                        if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)v[c] & (p.q - 1));
+                        else r = (long long)mod_i128(v[c], p.q);
+                    } else {
+                        r = (long long)v[c];
+                    }
+                    p.out[(long)row * p.ldout + n] = r;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == CONV_WARPS + 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace
+
+static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const int* run_if, cudaStream_t stream) {
+    const int nt = qf_i8_tile_n(LX, a.LW, a.N);
+    if (nt < 16) return cudaErrorInvalidValue;
+    FusedParams p{};
+    p.x = a.x; p.ldx = a.ldx; p.B = a.B; p.N = a.N; p.K = a.K; p.LX = LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
+    p.vec = ((a.ldx & 3) == 0 && (((uintptr_t)a.x) & 15) == 0) ? 1 : 0;
+    p.q = a.q; p.out = a.out; p.ldout = a.ldout; p.norm2 = a.norm2; p.mma_units = a.mma_units;
+    p.overflow = a.retry_flag; p.run_if = run_if;
+    p.n_tiles = (a.N + nt - 1) / nt;
+    const int m_tiles = (a.B + tc05::TILE_M - 1) / tc05::TILE_M;
+    const int stage_bytes = LX * tc05::TILE_M * tc05::BLOCK_K + a.LW * nt * tc05::BLOCK_K;
+    const int budget = 227 * 1024 - 1024 - 256;
+    int stages = budget / stage_bytes;
+    if (stages < 2) return cudaErrorInvalidValue;
+    if (stages > 6) stages = 6;
+    p.stages = stages;
+    const int smem = stages * stage_bytes + 1024 + 256;
+    CUtensorMap mw;
+    if (!tc05::make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
+    void (*kern)(const CUtensorMap, FusedParams) = nullptr;
+    if (check) kern = LX == 1 ? f_a_fused_kernel<1, true> : LX == 2 ? f_a_fused_kernel<2, true> : f_a_fused_kernel<3, true>;
+    else kern = LX == 1 ? f_a_fused_kernel<1, false> : LX == 2 ? f_a_fused_kernel<2, false>
+              : LX == 3 ? f_a_fused_kernel<3, false> : f_a_fused_kernel<4, false>;
+    static int configured[2][MAX_LX + 1] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    if (smem > configured[check ? 1 : 0][LX]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[check ? 1 : 0][LX] = smem;
+    }
+    kern<<<dim3((unsigned)(m_tiles * p.n_tiles)), FUSED_THREADS, smem, stream>>>(mw, p);
+    return cudaGetLastError();
+}
+
+// LX is the digit count that covers every in-domain value.  With a retry flag the launch is optimistic: LX - 1
+// digits first (a wider coordinate tile, fewer passes over sigma), and the full-width kernel runs only if some value
+// really needed its top digit (decided on the device, no host round trip).
+cudaError_t qf_launch_f_a_fused(const FaFusedArgs& a, cudaStream_t stream) {
+    if (a.B <= 0 || a.N <= 0) return cudaSuccess;
+    if (a.LX < 1 || a.LX > MAX_LX || a.LW < 1 || a.LX + a.LW - 1 > 16 || a.K < 1) return cudaErrorInvalidValue;
+    if ((a.ldw & 15) || (a.w_plane & 15) || (((uintptr_t)a.w) & 15)) return cudaErrorMisalignedAddress;
+    if (a.retry_flag && a.LX >= 2 && qf_i8_tile_n(a.LX - 1, a.LW, a.N) > qf_i8_tile_n(a.LX, a.LW, a.N)) {
+        cudaError_t e = cudaMemsetAsync(a.retry_flag, 0, sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        e = launch_one(a, a.LX - 1, true, nullptr, stream);
+        if (e != cudaSuccess) return e;
+        return launch_one(a, a.LX, false, a.retry_flag, stream);
+    }
+    return launch_one(a, a.LX, false, nullptr, stream);
+}

@@ -154,6 +154,20 @@ struct I8GemmArgs {
     unsigned long long* mma_units;
 };
 int qf_i8_tile_n(int LX, int LW, int N);
+// gemm_i8_fused.cu: out = X W^t mod q with X read as int32 (digit split fused into the contraction) and the
+// squared row norms of X accumulated on the way (norm2 optional)
+struct FaFusedArgs {
+    const int32_t* x; long ldx;   // B x K
+    const void* w; long ldw, w_plane;  // LW planes of N x K limbs
+    int LX, LW, w_signed;
+    int B, N, K;
+    unsigned long long q;
+    int64_t* out; long ldout;
+    unsigned long long* norm2;
+    unsigned long long* mma_units;
+    int* retry_flag;   // optional device int: enables the optimistic (LX - 1 digits first) launch pair
+};
+cudaError_t qf_launch_f_a_fused(const FaFusedArgs& a, cudaStream_t stream);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
 
 // ---- limb splitting (elementwise.cu) ---------------------------------------------------------
