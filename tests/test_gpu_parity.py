@@ -512,7 +512,11 @@ def _ring_s(n):
 
 @pytest.mark.parametrize("n,q", [(64, 3329), (256, 3329), (128, 7681), (256, 7681), (512, 12289), (1024, 12289),
                                  (64, 257), (64, 2**31 - 1), (256, 2**24), (8, 1024), (5, 256), (6, 128)])
-def test_ring_f_a_bit_exact(T, n, q):
+@pytest.mark.parametrize("dense", [True, False])
+def test_ring_f_a_bit_exact(T, n, q, dense, monkeypatch):
+    """dense=True: rot^-(a) as one tensor-core contraction (n <= 512); dense=False: the NTT / schoolbook kernels."""
+    if not dense:
+        monkeypatch.setenv("QF_DISABLE_RING_DENSE", "1")
     rng = np.random.default_rng(n)
     gp = T.GadgetParametersRing.init_default(n, q)
     psf = T.PSFGPVRing(gp, float(_ring_s(n)), 1.005)

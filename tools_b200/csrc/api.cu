@@ -119,6 +119,11 @@ struct qf_ctx {
     int ring_d = 1;
     uint32_t ring_np_inv = 0;
     Dev dAhat, dTw, dAraw, dAhat32, dTw32;
+    // dense negacyclic matrix [rot^-(a_0) | ... | rot^-(a_{k+1})] mod q as u8 digit planes (n x n(k+2)): ring f_a
+    // as one tensor-core contraction with the digit split of sigma fused in (rotation_matrix.rs:41-96)
+    bool ring_dense = false;
+    int ring_limbs = 0;
+    Dev dRotl;
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];
@@ -335,6 +340,7 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
         g.x = dSigma; g.ldx = ctx->dim;
         g.w = ctx->dAl.p; g.ldw = ctx->ldk_dim; g.w_plane = (long)ctx->n * ctx->ldk_dim;
         g.LX = ctx->x_limbs; g.LW = ctx->a_limbs; g.w_signed = 0;
+        g.LX_typical = limbs_for(6.0 * ctx->s_samp_d + 1.0);
         g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->m;
         g.q = ctx->prm.q; g.out = out; g.ldout = ctx->n;
         g.norm2 = ctx->dNorm.as<unsigned long long>();
@@ -418,7 +424,19 @@ qf_status ring_f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU
         CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
         out = ctx->w[1].as<int64_t>();
     }
-    if (ctx->ring_small)
+    if (ctx->ring_dense && ctx->x_limbs <= 4) {
+        FaFusedArgs g{};
+        g.x = dSigma; g.ldx = ctx->dim;
+        g.w = ctx->dRotl.p; g.ldw = ctx->ldk_dim; g.w_plane = (long)ctx->n * ctx->ldk_dim;
+        g.LX = ctx->x_limbs; g.LW = ctx->ring_limbs; g.w_signed = 0;
+        g.LX_typical = limbs_for(6.0 * ctx->s_samp_d + 1.0);
+        g.B = Bc; g.N = (int)ctx->n; g.K = (int)ctx->dim;
+        g.q = ctx->prm.q; g.out = out; g.ldout = ctx->n;
+        g.norm2 = ctx->dNorm.as<unsigned long long>();
+        CK(ctx->dRetry.ensure(sizeof(int)));
+        g.retry_flag = ctx->dRetry.as<int>();
+        LAUNCH(qf_launch_f_a_fused(g, ctx->stream));
+    } else if (ctx->ring_small)
         LAUNCH(qf_launch_ring_small(dSigma, ctx->dAhat32.as<uint32_t>(), out, ctx->dNorm.as<unsigned long long>(), Bc, npoly,
                                     (int)ctx->n, ctx->ring_d, ctx->prm.q, ctx->ring_np_inv, ctx->dTw32.as<uint32_t>(),
                                     ctx->stream));
@@ -1235,6 +1253,25 @@ qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a) {
             CK(cudaMemcpy(ctx->dTw32.p, tables.data(), tables.size() * 4, cudaMemcpyHostToDevice));
             CK(ctx->dAhat32.ensure(ah.size() * 4));
             CK(cudaMemcpy(ctx->dAhat32.p, ah.data(), ah.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    {
+        // rot^-(a_j): column c holds the coefficients of a_j X^c mod X^n + 1 (rotation_matrix.rs:41-63):
+        // M[i][j n + c] = a_j[i - c] for i >= c, -a_j[n + i - c] below, reduced into [0, q)
+        const char* env = getenv("QF_DISABLE_RING_DENSE");
+        const int qbits = bitlen_u64(ctx->prm.q - 1);
+        ctx->ring_dense = ctx->use_i8 && ctx->fused_fa && !(env && env[0] == '1') && n >= 16 && n <= 512 && qbits <= 32;
+        if (ctx->ring_dense) {
+            std::vector<int64_t> rot((size_t)n * n * np);
+            const int64_t q = (int64_t)ctx->prm.q;
+            for (long j = 0; j < np; ++j)
+                for (long c = 0; c < n; ++c)
+                    for (long i = 0; i < n; ++i) {
+                        const int64_t v = i >= c ? a[j * n + (i - c)] : (q - a[j * n + (n + i - c)]) % q;
+                        rot[(size_t)i * (n * np) + j * n + c] = v;
+                    }
+            ctx->ring_limbs = (qbits + 7) / 8;
+            QF_TRY(upload_limbs(ctx, rot.data(), n, n * np, ctx->ldk_dim, ctx->ring_limbs, false, ctx->dRotl));
         }
     }
     ctx->ring_ntt = (n >= 64) && ((n & (n - 1)) == 0) && n <= 2048;

@@ -12,6 +12,8 @@
 // Digit planes of sigma that are zero in a whole 128 x 128 block are skipped by the MMA issuer.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
@@ -296,8 +298,16 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
 
 }  // namespace
 
+// coordinate tile: the widest the 512 TMEM columns allow, then balanced over the resulting number of tiles
+static int fused_tile_n(int LX, int LW, int N) {
+    const int nt_max = qf_i8_tile_n(LX, LW, N);
+    if (nt_max < 16) return nt_max;
+    const int tiles = (N + nt_max - 1) / nt_max;
+    return std::min(nt_max, ((N + tiles - 1) / tiles + 15) / 16 * 16);
+}
+
 static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const int* run_if, cudaStream_t stream) {
-    const int nt = qf_i8_tile_n(LX, a.LW, a.N);
+    const int nt = fused_tile_n(LX, a.LW, a.N);
     if (nt < 16) return cudaErrorInvalidValue;
     FusedParams p{};
     p.x = a.x; p.ldx = a.ldx; p.B = a.B; p.N = a.N; p.K = a.K; p.LX = LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
@@ -329,17 +339,20 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     return cudaGetLastError();
 }
 
-// LX is the digit count that covers every in-domain value.  With a retry flag the launch is optimistic: LX - 1
-// digits first (a wider coordinate tile, fewer passes over sigma), and the full-width kernel runs only if some value
-// really needed its top digit (decided on the device, no host round trip).
+// LX is the digit count that covers every in-domain value, LX_typical the count that covers what the samplers
+// produce (|x| <= 6 s r).  With a retry flag and LX_typical < LX the launch is optimistic: LX_typical digits first
+// (a wider coordinate tile, fewer passes over sigma), and the full-width kernel runs only if some value really
+// needed more (decided on the device, no host round trip).
 cudaError_t qf_launch_f_a_fused(const FaFusedArgs& a, cudaStream_t stream) {
     if (a.B <= 0 || a.N <= 0) return cudaSuccess;
     if (a.LX < 1 || a.LX > MAX_LX || a.LW < 1 || a.LX + a.LW - 1 > 16 || a.K < 1) return cudaErrorInvalidValue;
     if ((a.ldw & 15) || (a.w_plane & 15) || (((uintptr_t)a.w) & 15)) return cudaErrorMisalignedAddress;
-    if (a.retry_flag && a.LX >= 2 && qf_i8_tile_n(a.LX - 1, a.LW, a.N) > qf_i8_tile_n(a.LX, a.LW, a.N)) {
+    const bool opt = a.retry_flag && a.LX_typical >= 1 && a.LX_typical < a.LX && a.LX_typical <= 3;
+    const int t_full = fused_tile_n(a.LX, a.LW, a.N), t_opt = opt ? fused_tile_n(a.LX_typical, a.LW, a.N) : t_full;
+    if (opt && (a.N + t_opt - 1) / t_opt < (a.N + t_full - 1) / t_full) {
         cudaError_t e = cudaMemsetAsync(a.retry_flag, 0, sizeof(int), stream);
         if (e != cudaSuccess) return e;
-        e = launch_one(a, a.LX - 1, true, nullptr, stream);
+        e = launch_one(a, a.LX_typical, true, nullptr, stream);
         if (e != cudaSuccess) return e;
         return launch_one(a, a.LX, false, a.retry_flag, stream);
     }

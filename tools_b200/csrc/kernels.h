@@ -160,6 +160,7 @@ struct FaFusedArgs {
     const int32_t* x; long ldx;   // B x K
     const void* w; long ldw, w_plane;  // LW planes of N x K limbs
     int LX, LW, w_signed;
+    int LX_typical;   // digits covering the sampler's tail cut (0: unknown)
     int B, N, K;
     unsigned long long q;
     int64_t* out; long ldout;
