@@ -5,7 +5,7 @@
 //   decompress: x = floor((y * q + 2^(d-1)) / 2^d)                    (written unreduced)
 //
 // HBM-streaming kernel: u16 in, u16 out (4 algorithmic bytes per coefficient),
-// 128-bit loads/stores (8 coefficients per access, 2 accesses in flight per
+// 128-bit loads/stores (8 coefficients per access, 4 accesses in flight per
 // thread), grid = 148 SMs x 8 resident CTAs, no shared memory.  The division by
 // q is an exact multiply-high by ceil(2^64 / q) (numerator < 2^33, q < 2^16).
 #include "common.cuh"
@@ -56,14 +56,19 @@ compress_u16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
     uint4* vout = reinterpret_cast<uint4*>(out);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + stride < nvec; i += 2 * stride) {
-        uint4 a = __ldcs(vin + i), b = __ldcs(vin + i + stride);
-        a.x = map2<DEC>(a.x, p); a.y = map2<DEC>(a.y, p); a.z = map2<DEC>(a.z, p); a.w = map2<DEC>(a.w, p);
-        b.x = map2<DEC>(b.x, p); b.y = map2<DEC>(b.y, p); b.z = map2<DEC>(b.z, p); b.w = map2<DEC>(b.w, p);
-        __stcs(vout + i, a);
-        __stcs(vout + i + stride, b);
+    // four independent 128-bit loads in flight per thread (128 KB per SM at full occupancy) before any is consumed
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(vin + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u].x = map2<DEC>(v[u].x, p); v[u].y = map2<DEC>(v[u].y, p);
+            v[u].z = map2<DEC>(v[u].z, p); v[u].w = map2<DEC>(v[u].w, p);
+            __stcs(vout + i + u * stride, v[u]);
+        }
     }
-    if (i < nvec) {
+    for (; i < nvec; i += stride) {
         uint4 a = __ldcs(vin + i);
         a.x = map2<DEC>(a.x, p); a.y = map2<DEC>(a.y, p); a.z = map2<DEC>(a.z, p); a.w = map2<DEC>(a.w, p);
         __stcs(vout + i, a);
@@ -113,7 +118,7 @@ cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t cou
         p.narrow = (m32 <= 0xffffffffull && num_max <= 0xffffffffull && e * num_max < pw) ? 1u : 0u;
     }
     size_t nvec = count / 8;
-    size_t want = (nvec + 2 * 256 - 1) / (2 * 256);
+    size_t want = (nvec + 4 * 256 - 1) / (4 * 256);
     int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
     if (decompress)
         compress_u16_kernel<true><<<grid, 256, 0, stream>>>(in, out, count, p);
