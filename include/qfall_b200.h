@@ -100,6 +100,11 @@ qf_status qf_set_a(qf_ctx* ctx, const int64_t* a);
  * device, in block form (only an m_bar x m_bar Cholesky factor is dense) -- same law, ~4x less work per target. */
 qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const double* sqrt_sigma_2,
                                        const int64_t* s_block, const double* s_block_gso);
+/* gen_short_basis_for_trapdoor with tag = I (short_basis_classical.rs:54-110): the short basis
+ * S_A = [[I,R],[0,I]] [[0,I],[S',W]] = [[R S', I + R W],[S', W]] of Lambda^perp(A) for the installed A and the
+ * trapdoor R (m_bar x nk); W = digits of -A[:, :m_bar], S' column-reversed iff base^k = q.  The m_bar x nk x m_bar
+ * product R W runs on the tensor cores; s_out is m x m (host), columns are the basis vectors.  Exact. */
+qf_status qf_gen_short_basis(qf_ctx* ctx, const int8_t* r, int64_t* s_out);
 /* compute_sqrt_sigma_2 (mp_perturbation.rs:111-139) on the device: lower Cholesky factor (m x m, row-major, host)
  * of Sigma_2 = r^2/(2 pi) (Sigma - (b^2+1) [R;I][R;I]^t - I); sigma == NULL means Sigma = s^2 I.
  * QF_ERR_INVALID when Sigma_2 is not positive definite (the reference panics in the Cholesky). */

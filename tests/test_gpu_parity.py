@@ -457,6 +457,26 @@ def test_gadget_sampler_distribution(T):
 # ----------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("n,q", [(2, 8), (5, 256), (6, 127), (10, 3329), (24, 2**16), (40, 2**20 - 3), (64, 2**24)])
+def test_gen_short_basis_device_bit_exact(T, n, q):
+    """gen_short_basis_for_trapdoor (short_basis_classical.rs:54-110) with the R W product on the tensor cores against
+    the oracle's big-integer restatement (itself pinned on the reference's golden sa_l / sa_r, test_oracle_golden)."""
+    from tools_b200 import gadget
+
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFGPV(gp, 10.0 * n)
+    a, r = T.psf._trap_gen_classical(psf, seed=n + 7)
+    got = psf.gen_short_basis_for_trapdoor(r)
+    host = gadget.gen_short_basis_for_trapdoor(gp, a, r)
+    assert np.array_equal(got, host)
+    if n <= 24:
+        po = O.GadgetParameters.init_default(n, q)
+        tag = [[int(i == j) for j in range(n)] for i in range(n)]
+        want = O.gen_short_basis_for_trapdoor(po, tag, a.tolist(), r.tolist())
+        assert got.tolist() == [list(map(int, row)) for row in want]
+    assert not (a.astype(object).dot(got.astype(object)) % q).any()  # every column lies in Lambda^perp(A)
+
+
 @pytest.mark.parametrize("n,q,s", [(5, 256, 10.0), (6, 128, 10.0), (8, 128, 90.0), (10, 127, 40.0), (24, 2**16, 60.0)])
 def test_samp_p_gpv_preimage_and_domain(T, n, q, s):
     gp = T.GadgetParameters.init_default(n, q)

@@ -1101,6 +1101,83 @@ qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const doubl
     return QF_OK;
 }
 
+qf_status qf_gen_short_basis(qf_ctx* ctx, const int8_t* r, int64_t* s_out) {
+    if (!ctx || !r || !s_out) return QF_ERR_INVALID;
+    if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "ring context: the ring short basis is built by the host shim");
+    if (!ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "install A first (qf_set_a / qf_trap_gen)");
+    if (!ctx->use_i8) return ctx->fail(QF_ERR_UNSUPPORTED, "needs the int8 tensor path");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, k = ctx->k, mb = ctx->m_bar, nk = ctx->nk, m = ctx->m;
+    const uint64_t q = ctx->prm.q, base = (uint64_t)ctx->prm.base;
+    if (base > 256) return ctx->fail(QF_ERR_UNSUPPORTED, "gadget base > 256");
+    // S_k (gadget_classical.rs:248-272) and whether base^k == q (then S' = S with its columns reversed, :80-82)
+    u128 pw = 1;
+    for (long i = 0; i < k; ++i) pw *= base;
+    if (pw < q) return ctx->fail(QF_ERR_INVALID, "base^k < q");
+    const bool exact_pow = pw == (u128)q;
+    std::vector<int64_t> sk((size_t)k * k, 0);
+    for (long j = 0; j < k; ++j) sk[j * k + j] = (int64_t)base;
+    for (long i = 0; i + 1 < k; ++i) sk[(i + 1) * k + i] = -1;
+    if (!exact_pow) {
+        uint64_t qq = q;
+        for (long i = 0; i < k; ++i) { sk[i * k + (k - 1)] = (int64_t)(qq % base); qq /= base; }
+    }
+    // column c of S' = column (exact_pow ? nk-1-c : c) of I_n (x) S_k
+    auto sprime = [&](long row, long c) -> int64_t {
+        const long cc = exact_pow ? nk - 1 - c : c;
+        return (row / k == cc / k) ? sk[(row % k) * k + (cc % k)] : 0;
+    };
+    std::fill(s_out, s_out + (size_t)m * m, (int64_t)0);
+    // bottom-left S', top-left R S' (each column of S' has at most k non-zeros, all inside one k-block)
+    for (long c = 0; c < nk; ++c) {
+        const long cc = exact_pow ? nk - 1 - c : c, blk = cc / k;
+        for (long t = 0; t < k; ++t) {
+            const long row = blk * k + t;
+            const int64_t v = sprime(row, c);
+            if (!v) continue;
+            s_out[(size_t)(mb + row) * m + c] = v;
+            for (long i = 0; i < mb; ++i) s_out[(size_t)i * m + c] += (int64_t)r[i * nk + row] * v;
+        }
+    }
+    // W = base-b digits of -A[:, :m_bar] mod q (short_basis_classical.rs:105-110), stored transposed for the device:
+    // Wt[c][j k + t] = digit t of (q - A[j][c]) mod q
+    std::vector<int64_t> wt((size_t)mb * nk);
+    for (long j = 0; j < n; ++j)
+        for (long c = 0; c < mb; ++c) {
+            uint64_t v = (q - (uint64_t)ctx->hA[(size_t)j * m + c]) % q;
+            for (long t = 0; t < k; ++t) {
+                const int64_t d = (int64_t)(v % base);
+                v /= base;
+                wt[(size_t)c * nk + j * k + t] = d;
+                s_out[(size_t)(mb + j * k + t) * m + nk + c] = d;  // bottom-right W
+            }
+        }
+    // top-right I + R W: R (m_bar x nk, one s8 digit) times W on the tensor cores, exact int32
+    {
+        const long ldk = ctx->ldk_nk;
+        Dev dX, dW, dOut;
+        std::vector<int64_t> r64((size_t)mb * nk);
+        for (size_t i = 0; i < r64.size(); ++i) r64[i] = r[i];
+        QF_TRY(upload_limbs(ctx, r64.data(), mb, nk, ldk, 1, true, dX));
+        QF_TRY(upload_limbs(ctx, wt.data(), mb, nk, ldk, 1, false, dW));
+        CK(dOut.ensure((size_t)mb * mb * 4));
+        I8GemmArgs g{};
+        g.x = dX.as<int8_t>(); g.ldx = ldk; g.x_plane = mb * ldk;
+        g.w = dW.p; g.ldw = ldk; g.w_plane = mb * ldk;
+        g.LX = 1; g.LW = 1; g.w_signed = 0;
+        g.B = (int)mb; g.N = (int)mb; g.K = (int)nk;
+        g.out_kind = 1; g.sign = 1; g.q = 0; g.out = dOut.p; g.ldout = mb;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+        std::vector<int32_t> rw((size_t)mb * mb);
+        CK(cudaMemcpyAsync(rw.data(), dOut.p, rw.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (long i = 0; i < mb; ++i)
+            for (long c = 0; c < mb; ++c) s_out[(size_t)i * m + nk + c] = (int64_t)rw[(size_t)i * mb + c] + (i == c ? 1 : 0);
+    }
+    return check_flag(ctx);
+}
+
 qf_status qf_compute_sqrt_sigma_2(qf_ctx* ctx, const int8_t* r, const double* sigma, double* out) {
     if (!ctx || !r || !out) return QF_ERR_INVALID;
     if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");

@@ -144,10 +144,20 @@ class PSFGPV(_PSFBase):
     def trap_gen(self, seed=None):
         """gpv.rs:83-94: uniform A_bar, gen_trapdoor, short basis, GSO."""
         a, r = _trap_gen_classical(self, seed)
-        short_base = gadget.gen_short_basis_for_trapdoor(self.gp, a, r)
+        short_base = self.gen_short_basis_for_trapdoor(r)
         td = (short_base, linalg.gso(short_base))
         self._a_id = a  # qf_trap_gen installed it
         return a, td
+
+
+    def gen_short_basis_for_trapdoor(self, r) -> np.ndarray:
+        """short_basis_classical.rs:54-110 for the installed A, tag = I: the integer products run on the device
+        (qf_gen_short_basis); exact.  gadget.gen_short_basis_for_trapdoor is the host restatement (tags, tests)."""
+        r8 = np.ascontiguousarray(r, dtype=np.int8)
+        assert r8.shape == (self.gp.m_bar, self.gp.n * self.gp.k)
+        out = np.empty((self.m, self.m), dtype=np.int64)
+        self.ctx.call("qf_gen_short_basis", _ffi.ptr(r8), _ffi.ptr(out))
+        return out
 
 
 class PSFPerturbation(_PSFBase):
