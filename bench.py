@@ -106,7 +106,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import oracle_c as OC
-    from tools_b200 import gadget, linalg  # host-side numpy key setup only (untimed)
+    from tools_b200 import gadget  # host-side numpy key setup only (untimed)
 
     n, q, desc = WORKLOADS[args.workload]
     gp = gadget.GadgetParameters.init_default(n, q)
@@ -387,6 +387,8 @@ def main():
             threads = OC.threads()
             sample = threads  # one target per thread: ~ one pass over the 2.4 GB of basis + GSO each
             sb, sg = td
+            if sg is None:  # the backend kept the GSO on the device: fetch a host copy for the CPU arm (untimed)
+                sg = psf.gso(sb)
             t1 = time.perf_counter()
             piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
             us = np.ascontiguousarray(hu_np[:sample])

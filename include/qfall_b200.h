@@ -110,8 +110,12 @@ qf_status qf_gen_short_basis(qf_ctx* ctx, const int8_t* r, int64_t* s_out);
  * QF_ERR_INVALID when Sigma_2 is not positive definite (the reference panics in the Cholesky). */
 qf_status qf_compute_sqrt_sigma_2(qf_ctx* ctx, const int8_t* r, const double* sigma, double* sqrt_sigma_2_out);
 /* PSFGPV trapdoor (gpv.rs:61): short basis S (dim x dim, columns are basis vectors) and its
- * GSO.  dim = m for QF_PSF_GPV, n*(k+2) (coefficient embedding) for QF_PSF_GPV_RING. */
+ * GSO.  dim = m for QF_PSF_GPV, n*(k+2) (coefficient embedding) for QF_PSF_GPV_RING.
+ * s_gso == NULL: the GSO is computed on the device (as qf_gso) and never leaves it. */
 qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* s_gso);
+/* MatQ::gso as used at gpv.rs:91: unnormalised Gram-Schmidt of the columns of S (dim x dim) in fp64 on the
+ * device (blocked Gram-Schmidt with re-orthogonalisation).  gso_out: dim x dim, host. */
+qf_status qf_gso(qf_ctx* ctx, const int64_t* s, double* gso_out);
 /* ring key: (k+2) polynomials of n coefficients (gpv_ring.rs:70) */
 qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a);
 

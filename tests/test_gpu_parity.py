@@ -457,6 +457,32 @@ def test_gadget_sampler_distribution(T):
 # ----------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("n,q", [(5, 32), (8, 128), (24, 2**16), (40, 2**12)])
+def test_gso_device_matches_oracle(T, n, q):
+    """qf_gso (MatQ::gso, gpv.rs:91): blocked Gram-Schmidt on the device against the oracle's exact-rational GSO
+    (small) and float64 QR-free restatement; tolerance 1e-9 absolute on entries of size <= ||b_j|| ~ 10^2."""
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFGPV(gp, 10.0 * n)
+    a, (sb, sg) = psf.trap_gen(seed=3, dense_gso=True)
+    assert sg.shape == sb.shape
+    ref = O.gso_f64(sb.astype(np.float64))
+    assert np.allclose(sg, ref, rtol=0, atol=1e-8)
+    if gp.m <= 130:
+        ex = np.array(O.gso_exact(sb.tolist()), dtype=np.float64)
+        assert np.allclose(sg, ex, rtol=0, atol=1e-9)
+    # orthogonality and the triangular relation S = G U
+    gram = sg.T @ sg
+    off = gram - np.diag(np.diag(gram))
+    assert np.abs(off).max() < 1e-7 * np.diag(gram).max()
+    # a trapdoor installed without its GSO (None) samples the same law as with it
+    rng = np.random.default_rng(1)
+    u = rng.integers(0, q, (500, n), dtype=np.int64)
+    e1 = psf.samp_p_batch(a, (sb, sg), u, seed=4)
+    e2 = psf.samp_p_batch(a, (sb, None), u, seed=4)
+    assert np.array_equal(O.f_a_classical_batch(a, e2, q), u) and psf.check_domain_batch(e2).all()
+    assert np.array_equal(e1, e2)  # same GSO (bit-identical path) => same draws
+
+
 @pytest.mark.parametrize("n,q", [(2, 8), (5, 256), (6, 127), (10, 3329), (24, 2**16), (40, 2**20 - 3), (64, 2**24)])
 def test_gen_short_basis_device_bit_exact(T, n, q):
     """gen_short_basis_for_trapdoor (short_basis_classical.rs:54-110) with the R W product on the tensor cores against

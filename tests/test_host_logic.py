@@ -1,4 +1,4 @@
-"""CPU tests: host-side mirror (tools_b200.gadget / linalg) against the oracle, and the C-ABI
+"""CPU tests: host-side mirror (tools_b200.gadget) against the oracle, and the C-ABI
 library loads and exports every symbol include/qfall_b200.h declares (no compute calls)."""
 import ctypes
 import os
@@ -9,7 +9,6 @@ import pytest
 
 from oracle import qfall_oracle as O
 from tools_b200 import gadget as G
-from tools_b200 import linalg as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -88,13 +87,14 @@ def test_ring_short_basis_matches_oracle(n, q, goldens):
     assert got.tolist() == want
 
 
-def test_linalg_matches_oracle():
-    rng = np.random.default_rng(3)
-    b = rng.integers(-3, 4, (12, 12)).astype(np.float64) + 5 * np.eye(12)
-    g1, g2 = L.gso(b), O.gso_f64(b)
-    assert np.allclose(g1, g2)
-    ex = np.array(O.gso_exact(b.astype(int).tolist()), dtype=np.float64)
-    assert np.allclose(g1, ex, atol=1e-9)
+def test_gso_small_matches_oracle():
+    """The k x k gadget block's GSO (exact rationals on the host) against the oracle's exact and float64 GSO."""
+    for k, base, q in [(6, 2, 64), (7, 2, 100), (5, 3, 200), (24, 2, 2**24 - 3)]:
+        blk = G.short_basis_gadget_block(k, base, q)
+        got = G.gso_small(blk)
+        ex = np.array(O.gso_exact(blk.tolist()), dtype=np.float64)
+        assert np.allclose(got, ex, rtol=1e-15, atol=0)
+        assert np.allclose(got, O.gso_f64(blk.astype(np.float64)), atol=1e-9)
 
 
 def test_library_exports_every_declared_symbol():

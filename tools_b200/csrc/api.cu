@@ -894,6 +894,59 @@ qf_status pert_lg_i8(qf_ctx* ctx, const int8_t* gp, long gplane, int Bc, double*
     return QF_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Unnormalised Gram-Schmidt of the columns of S (MatQ::gso, gpv.rs:91) in fp64 on the device: blocked classical
+// Gram-Schmidt with re-orthogonalisation (two projection passes against the finished vectors, GEMMs on the DMMA
+// path) and two Cholesky-QR passes inside each 64-vector block (Gram matrix + potrf_diag + triangular solve as a
+// GEMM).  dS, dG: D x ld, S[t][j] = coordinate t of b_j, G[t][j] = coordinate t of b~_j.
+// ---------------------------------------------------------------------------
+qf_status gso_device(qf_ctx* ctx, const double* dS, double* dG) {
+    constexpr long NB = 64;
+    const long D = ctx->dim, ld = ctx->ld_dim;
+    Dev dBt, dQt, dQ, dPw, dPwT, dC, dGm, dLinv, dR, dInfo;
+    CK(dBt.ensure((size_t)D * ld * 8));
+    CK(dQt.ensure((size_t)D * ld * 8));
+    CK(dQ.ensure((size_t)D * ld * 8));
+    CK(dPw.ensure((size_t)NB * ld * 8));
+    CK(dPwT.ensure((size_t)D * NB * 8));
+    CK(dC.ensure((size_t)NB * ld * 8));
+    CK(dGm.ensure((size_t)NB * NB * 8));
+    CK(dLinv.ensure((size_t)NB * NB * 8));
+    CK(dR.ensure((size_t)D * 8));
+    CK(dInfo.ensure(sizeof(int)));
+    CK(cudaMemsetAsync(dInfo.p, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(dQt.p, 0, (size_t)D * ld * 8, ctx->stream));
+    CK(cudaMemsetAsync(dQ.p, 0, (size_t)D * ld * 8, ctx->stream));
+    double *Bt = dBt.as<double>(), *Qt = dQt.as<double>(), *Q = dQ.as<double>(), *Pw = dPw.as<double>(),
+           *PwT = dPwT.as<double>(), *C = dC.as<double>(), *Gm = dGm.as<double>(), *Linv = dLinv.as<double>(),
+           *R = dR.as<double>();
+    LAUNCH(qf_launch_transpose_scale(dS, ld, Bt, ld, (int)D, (int)D, nullptr, ctx->stream));  // rows = basis vectors
+    for (long j0 = 0; j0 < D; j0 += NB) {
+        const int nb = (int)std::min(NB, D - j0);
+        LAUNCH(qf_launch_copy_block(Bt + j0 * ld, ld, Pw, ld, nb, (int)D, ctx->stream));
+        if (j0 > 0)
+            for (int pass = 0; pass < 2; ++pass) {  // Pw -= (Pw Q_prev) Q_prev^t, twice
+                LAUNCH(ctx_gemm(ctx, Pw, ld, Qt, ld, C, ld, nb, (int)j0, (int)D, 1.0, 0.0, 0));
+                LAUNCH(ctx_gemm(ctx, C, ld, Q, ld, Pw, ld, nb, (int)D, (int)j0, -1.0, 1.0, 0));
+            }
+        for (int pass = 0; pass < 2; ++pass) {  // Cholesky-QR of the block: Pw = L Q_block, r_jj = L_jj
+            LAUNCH(ctx_gemm(ctx, Pw, ld, Pw, ld, Gm, NB, nb, nb, (int)D, 1.0, 0.0, 0));
+            LAUNCH(qf_launch_potrf_diag(Gm, NB, nb, Linv, dInfo.as<int>(), ctx->stream));
+            LAUNCH(qf_launch_gso_rdiag(R + j0, Gm, NB, nb, pass == 0, ctx->stream));
+            LAUNCH(qf_launch_transpose_scale(Pw, ld, PwT, NB, nb, (int)D, nullptr, ctx->stream));
+            LAUNCH(ctx_gemm(ctx, Linv, NB, PwT, NB, Pw, ld, nb, (int)D, nb, 1.0, 0.0, 0));
+        }
+        LAUNCH(qf_launch_copy_block(Pw, ld, Qt + j0 * ld, ld, nb, (int)D, ctx->stream));
+        LAUNCH(qf_launch_transpose_scale(Pw, ld, Q + j0, ld, nb, (int)D, nullptr, ctx->stream));
+    }
+    LAUNCH(qf_launch_scale_cols(Q, ld, dG, ld, D, D, R, ctx->stream));
+    int info = 0;
+    CK(cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (info) return ctx->fail(QF_ERR_INVALID, "gso: the basis is (numerically) rank deficient");
+    return QF_OK;
+}
+
 template <typename F>
 qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
     for (int64_t b0 = 0; b0 < batch; b0 += ctx->chunk) {
@@ -1201,8 +1254,21 @@ qf_status qf_compute_sqrt_sigma_2(qf_ctx* ctx, const int8_t* r, const double* si
     return QF_OK;
 }
 
+qf_status qf_gso(qf_ctx* ctx, const int64_t* s, double* gso_out) {
+    if (!ctx || !s || !gso_out) return QF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const long D = ctx->dim, ld = ctx->ld_dim;
+    Dev dS, dG;
+    QF_TRY(upload_as_f64(ctx, s, D, D, ld, dS));
+    CK(dG.ensure((size_t)D * ld * 8));
+    QF_TRY(gso_device(ctx, dS.as<double>(), dG.as<double>()));
+    CK(cudaMemcpy2DAsync(gso_out, (size_t)D * 8, dG.p, (size_t)ld * 8, (size_t)D * 8, (size_t)D, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QF_OK;
+}
+
 qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
-    if (!ctx || !s || !sg) return QF_ERR_INVALID;
+    if (!ctx || !s) return QF_ERR_INVALID;
     if (ctx->prm.kind == QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a GPV context");
     CK(cudaSetDevice(ctx->device));
     const long D = ctx->dim, ld = ctx->ld_dim;
@@ -1243,7 +1309,12 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     for (long i = 0; i < D * D; ++i) smax = std::max<int64_t>(smax, s[i] < 0 ? -s[i] : s[i]);
     QF_TRY(upload_as_f64(ctx, s, D, D, ld, ctx->dS));
     Dev dG, dMt, dSt, dD;
-    QF_TRY(upload_as_f64(ctx, sg, D, D, ld, dG));
+    if (sg) {
+        QF_TRY(upload_as_f64(ctx, sg, D, D, ld, dG));
+    } else {  // GSO not supplied: computed here (gpv.rs:91)
+        CK(dG.ensure((size_t)D * ld * 8));
+        QF_TRY(gso_device(ctx, ctx->dS.as<double>(), dG.as<double>()));
+    }
     CK(dD.ensure((size_t)D * 8));
     CK(dMt.ensure((size_t)D * ld * 8));
     CK(dSt.ensure((size_t)D * ld * 8));

@@ -123,6 +123,9 @@ cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams
 cudaError_t qf_launch_potrf_diag(double* A, long ld, int nb, double* Linv, int* info, cudaStream_t stream);
 cudaError_t qf_launch_fixed_rows_prepare(const double* L, long ld, int rows, int cols, int Ldig, double mult, double* scale,
                                          int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
+cudaError_t qf_launch_gso_rdiag(double* rdiag, const double* L, long ldl, int nb, int first, cudaStream_t stream);
+cudaError_t qf_launch_scale_cols(const double* in, long ldin, double* out, long ldout, long rows, long cols,
+                                 const double* colscale, cudaStream_t stream);
 cudaError_t qf_launch_tril(double* A, long ld, long n, cudaStream_t stream);
 cudaError_t qf_launch_copy_block(const double* in, long ldin, double* out, long ldout, long rows, int cols, cudaStream_t stream);
 cudaError_t qf_launch_sigma2_assemble(double* C, long ldc, long n, int full, const double* Gin, long ldg, const double* R,

@@ -324,3 +324,32 @@ cudaError_t qf_launch_fixed_rows_prepare(const double* L, long ld, int rows, int
     scale_vec_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(scale, rows, mult);
     return cudaGetLastError();
 }
+
+// ---- GSO building blocks (MatQ::gso, gpv.rs:91) ------------------------------------------------------------
+namespace {
+// rdiag[i] = (first ? 1 : rdiag[i]) * L[i][i] for the nb diagonal entries of a 64-wide Cholesky block
+__global__ void gso_rdiag_kernel(double* __restrict__ rdiag, const double* __restrict__ L, long ldl, int nb, int first) {
+    const int i = threadIdx.x;
+    if (i < nb) rdiag[i] = (first ? 1.0 : rdiag[i]) * L[(long)i * ldl + i];
+}
+// out[t][j] = in[t][j] * colscale[j]
+__global__ void scale_cols_kernel(const double* __restrict__ in, long ldin, double* __restrict__ out, long ldout, long rows,
+                                  long cols, const double* __restrict__ colscale) {
+    const long total = rows * cols;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / cols, j = t - i * cols;
+        out[i * ldout + j] = in[i * ldin + j] * colscale[j];
+    }
+}
+}  // namespace
+
+cudaError_t qf_launch_gso_rdiag(double* rdiag, const double* L, long ldl, int nb, int first, cudaStream_t stream) {
+    gso_rdiag_kernel<<<1, 64, 0, stream>>>(rdiag, L, ldl, nb, first);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_scale_cols(const double* in, long ldin, double* out, long ldout, long rows, long cols,
+                                 const double* colscale, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    scale_cols_kernel<<<148 * 8, 256, 0, stream>>>(in, ldin, out, ldout, rows, cols, colscale);
+    return cudaGetLastError();
+}

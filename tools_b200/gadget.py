@@ -115,6 +115,27 @@ def short_basis_gadget_block(k: int, base: int, q: int) -> np.ndarray:
     return sk
 
 
+def gso_small(basis: np.ndarray) -> np.ndarray:
+    """Exact-rational unnormalised Gram-Schmidt of the columns of a SMALL integer matrix (the k x k gadget block;
+    MatQ::gso as used at mp_perturbation.rs:234), returned as float64."""
+    from fractions import Fraction
+
+    b = [[Fraction(int(x)) for x in row] for row in np.asarray(basis).tolist()]
+    rows, cols = len(b), len(b[0])
+    out = [[Fraction(0)] * cols for _ in range(rows)]
+    for j in range(cols):
+        v = [b[t][j] for t in range(rows)]
+        for i in range(j):
+            gi = [out[t][i] for t in range(rows)]
+            den = sum(x * x for x in gi)
+            if den:
+                mu = sum(x * y for x, y in zip(v, gi)) / den
+                v = [x - mu * y for x, y in zip(v, gi)]
+        for t in range(rows):
+            out[t][j] = v[t]
+    return np.array([[float(x) for x in row] for row in out], dtype=np.float64)
+
+
 def short_basis_gadget(p: GadgetParameters) -> np.ndarray:
     """gadget_classical.rs:248-287: I_n (x) S_k."""
     return np.kron(np.eye(p.n, dtype=np.int64), short_basis_gadget_block(p.k, p.base, p.q))

@@ -16,7 +16,7 @@ from fractions import Fraction
 
 import numpy as np
 
-from . import _ffi, gadget, linalg
+from . import _ffi, gadget
 from ._ffi import NotInDomain, QfError  # noqa: F401
 
 
@@ -38,6 +38,7 @@ class _PSFBase:
 
     def _make_ctx(self, n, k, m_bar, base, q, s, r, bound, device):
         self.ctx = _ffi.Context(self.kind, n, k, m_bar, base, q, s, r, bound, device)
+        self.ctx_dim = n * (k + 2) if self.kind == _ffi.QF_PSF_GPV_RING else m_bar + n * k
         self._a_id = None
         self._td_id = None
         self._keep = None
@@ -136,18 +137,28 @@ class PSFGPV(_PSFBase):
         if self._td_id is not td:
             s, sg = td
             s = np.ascontiguousarray(s, dtype=np.int64)
-            sg = np.ascontiguousarray(sg, dtype=np.float64)
-            assert s.shape == (self.m, self.m) and sg.shape == (self.m, self.m)
+            # None: the GSO is computed on the device and stays there
+            sg = None if sg is None else np.ascontiguousarray(sg, dtype=np.float64)
+            assert s.shape == (self.m, self.m) and (sg is None or sg.shape == (self.m, self.m))
             self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(s), _ffi.ptr(sg))
             self._td_id = td
 
-    def trap_gen(self, seed=None):
-        """gpv.rs:83-94: uniform A_bar, gen_trapdoor, short basis, GSO."""
+    def trap_gen(self, seed=None, dense_gso: bool = None):
+        """gpv.rs:83-94: uniform A_bar, gen_trapdoor, short basis, GSO -- all on the device.  dense_gso=False
+        leaves the second trapdoor component None (the backend computes the GSO when the trapdoor is installed and
+        keeps it in HBM instead of moving m x m doubles through the host twice); default: the reference's
+        (S, S~) pair up to m = 2048, None above."""
         a, r = _trap_gen_classical(self, seed)
         short_base = self.gen_short_basis_for_trapdoor(r)
-        td = (short_base, linalg.gso(short_base))
+        if dense_gso is None:
+            dense_gso = self.m <= 2048
+        td = (short_base, self.gso(short_base) if dense_gso else None)
         self._a_id = a  # qf_trap_gen installed it
         return a, td
+
+    def gso(self, basis) -> np.ndarray:
+        """MatQ::gso (gpv.rs:91): unnormalised Gram-Schmidt of the columns, float64, on the device."""
+        return _gso(self, basis)
 
 
     def gen_short_basis_for_trapdoor(self, r) -> np.ndarray:
@@ -224,14 +235,24 @@ class PSFPerturbation(_PSFBase):
         k, n = self.gp.k, self.gp.n
         if full_gadget_basis is None:
             full_gadget_basis = n * k <= 1024
+        blk = gadget.short_basis_gadget_block(k, self.gp.base, self.gp.q)
+        gblk = gadget.gso_small(blk)  # k x k: exact rational Gram-Schmidt on the host, like MatQ::gso
         if full_gadget_basis:
             sb = gadget.short_basis_gadget(self.gp)
-            sg = linalg.gso(sb)
+            sg = np.kron(np.eye(n), gblk)
         else:  # one diagonal block; the full matrices are I_n (x) these
-            sb = gadget.short_basis_gadget_block(k, self.gp.base, self.gp.q)
-            sg = linalg.gso(sb)
+            sb, sg = blk, gblk
         self._a_id = a
         return a, (r, sqrt_sigma_2, (sb, sg))
+
+
+def _gso(psf, basis) -> np.ndarray:
+    b = np.ascontiguousarray(basis, dtype=np.int64)
+    d = psf.ctx_dim
+    assert b.shape == (d, d)
+    out = np.empty((d, d), dtype=np.float64)
+    psf.ctx.call("qf_gso", _ffi.ptr(b), _ffi.ptr(out))
+    return out
 
 
 def _trap_gen_classical(psf, seed):
@@ -289,8 +310,7 @@ class PSFGPVRing(_PSFBase):
             r, e = td
             basis = np.ascontiguousarray(
                 gadget.ring_short_basis_embedded(self.gp, np.asarray(a), np.asarray(r), np.asarray(e)), dtype=np.int64)
-            g = np.ascontiguousarray(linalg.gso(basis), dtype=np.float64)  # keep alive across the call
-            self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(basis), _ffi.ptr(g))
+            self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(basis), None)  # GSO computed on the device
             self._td_id = td
 
     def trap_gen(self, seed=None):
