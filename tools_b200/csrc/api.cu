@@ -305,6 +305,28 @@ cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
     }
     I8GemmArgs aa = a;
     aa.mma_units = (ctx->prof && ctx->dMma.p) ? ctx->dMma.as<unsigned long long>() : nullptr;
+    static const bool trace = getenv("QF_TRACE") && getenv("QF_TRACE")[0] == '1';
+    if (trace) {  // diagnostics only: per-launch time and executed digit pairs (synchronises)
+        Dev cnt;
+        cudaEvent_t t0, t1;
+        if (cnt.ensure(8) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(cnt.p, 0, 8, ctx->stream);
+        aa.mma_units = cnt.as<unsigned long long>();
+        cudaEventCreate(&t0); cudaEventCreate(&t1);
+        cudaEventRecord(t0, ctx->stream);
+        cudaError_t e2 = qf_launch_gemm_i8(aa, ctx->stream);
+        cudaEventRecord(t1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        unsigned long long h = 0;
+        cudaMemcpy(&h, cnt.p, 8, cudaMemcpyDeviceToHost);
+        const double nominal = 2.0 * a.B * (double)a.N * a.K;
+        fprintf(stderr, "[i8] B=%d N=%d K=%d LX=%d LW=%d kind=%d  %.3f ms  pairs/mac=%.2f of %d  %.0f TOP/s executed\n", a.B, a.N,
+                a.K, a.LX, a.LW, a.out_kind, ms, (double)h / nominal, a.LX * a.LW, (double)h / (ms * 1e-3) / 1e12);
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+        return e2;
+    }
     cudaError_t e = qf_launch_gemm_i8(aa, ctx->stream);
     if (ctx->prof) {
         cudaEventRecord(rec.b, ctx->stream);

@@ -98,19 +98,19 @@ constexpr int NP_TARGETS = 32;   // targets per CTA
 constexpr int NP_TPB = 128;      // 4 lanes per target
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = NP_NB_MAX + 1;   // centre tile is target-major: ts[t * NP_TS + i]
-constexpr int NP_RS = NP_NB_MAX + 1;   // proposal tile likewise: rng[t * NP_RS + i] (65 float4: conflict-free reads)
 
 // One nb-wide diagonal block.  Three phases per CTA of 32 targets:
 //  0. stage the mu-block (transposed) and the 32 x nb tile of centres through shared memory (coalesced);
-//  1. ALL threads pre-generate, for every (target, coordinate), the first Philox block of that coordinate's
-//     stream turned into two proposals (two normals and the logs of two uniforms): the expensive
-//     transcendental work does not depend on the centres, so it leaves the sequential chain;
+//  1. the proposals of every (target, coordinate) -- the first Philox block of that coordinate's stream turned into
+//     two normals and the logs of two uniforms by np_propose_kernel at full occupancy -- are NOT staged through
+//     shared memory: each quad prefetches the four proposals of the next coordinate group into registers one
+//     group ahead, which keeps the CTA at ~50 KB of shared memory and four CTAs per SM;
 //  2. the recursion i = nb-1 .. 0 with 4 lanes per target: accept / reject on the pre-generated proposals
 //     (a handful of flops), then a right-looking update c'_j -= mu_ji z_i of the remaining centres, the
 //     j's strided over the 4 lanes (independent FMAs instead of one dependent dot product).
 // Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
 // one-thread-per-target formulation.
-__global__ void __launch_bounds__(NP_TPB, 2)
+__global__ void __launch_bounds__(NP_TPB, 4)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
                int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
@@ -118,8 +118,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
     const int us_ld = nb + 1;                             // padded: the transposing store is (almost) conflict-free
     double* ust = np_sm;                                  // ust[c * us_ld + r] = U[j0+r][j0+c], c > r
     double* ts = ust + ((nb * us_ld + 1) & ~1);           // ts[t * NP_TS + i]  (16-byte aligned)
-    float4* rng = reinterpret_cast<float4*>(ts + ((NP_TARGETS * NP_TS + 1) & ~1));  // rng[t * NP_RS + i]
-    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(rng + NP_TARGETS * NP_RS);
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(ts + ((NP_TARGETS * NP_TS + 1) & ~1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbe = min(nb, dim - j0);
     const long b0 = (long)blockIdx.x * NP_TARGETS;
@@ -132,12 +131,6 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         const long b = b0 + r;
         if (b < B)
             for (int c = lane; c < nbe; c += 32) ts[r * NP_TS + c] = T[b * ldt + j0 + c];
-    }
-    // phase 1: stage this block's pre-generated proposals (np_propose_kernel); prop points at column j0
-    for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
-        const long b = b0 + r;
-        if (b < B)
-            for (int c = lane; c < nbe; c += 32) rng[r * NP_RS + c] = prop[b * ldprop + c];
     }
     __syncthreads();
     // phase 2 (first 4 warps; the others wait at the barrier below).  Lane qd of a target's quad keeps the
@@ -153,15 +146,28 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         for (int k = 0; k < NG; ++k) c[k] = (4 * k + qd < nbe) ? ts[t * NP_TS + 4 * k + qd] : 0.0;
         // the group being sampled always sits in c[NG-1]; after each group the register file is rotated by one,
         // so all register indices are static while the loop over groups stays rolled (small code footprint)
+        // proposals of this target (pre-generated by np_propose_kernel; prop points at column j0), one group ahead
+        const float4* prow = prop + (live ? b : 0) * ldprop;
+        float4 pcur[4], pnxt[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int ii = 4 * (NG - 1) + o;
+            pcur[o] = (ii < nbe) ? prow[ii] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int kidx = 0; kidx < NG; ++kidx) {
             const int g = NG - 1 - kidx;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int ii = 4 * (g - 1) + o;
+                pnxt[o] = (g > 0 && ii < nbe) ? prow[ii] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int owner = 3; owner >= 0; --owner) {
                 const int ii = 4 * g + owner;
                 if (ii >= nbe) continue;  // uniform
                 const double cp = __shfl_sync(0xffffffffu, c[NG - 1], (lane & ~3) | owner);
                 const DGaussParams dgp = dgs[ii];
-                const float4 pr = rng[t * NP_RS + ii];
+                const float4 pr = pcur[owner];
                 const double c_int = rint(cp);
                 const float c_frac = (float)(cp - c_int);
                 double z = 0.0;
@@ -193,6 +199,8 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
             if (4 * g + qd < nbe) ts[t * NP_TS + 4 * g + qd] = c[NG - 1];
 #pragma unroll
             for (int kk = NG - 1; kk > 0; --kk) c[kk] = c[kk - 1];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) pcur[o] = pnxt[o];
         }
     }
     __syncthreads();
@@ -242,7 +250,7 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
     size_t smem = (size_t)(((nb * (nb + 1) + 1) & ~1) + ((NP_TARGETS * NP_TS + 1) & ~1)) * sizeof(double) +
-                  (size_t)NP_TARGETS * NP_RS * sizeof(float4) + (size_t)nb * sizeof(DGaussParams);
+                  (size_t)nb * sizeof(DGaussParams);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
