@@ -367,8 +367,11 @@ def main():
         # executes that once per digit pair (`issued`), which is what is compared with the int8 peak in `frac`.
         roofline = {
             "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z and exact e = sol + S*z",
-            "bound": "tensor", "achieved": algo, "achieved_issued": issued, "peak": i8_peak, "unit": "TOP/s",
-            "frac": issued / i8_peak, "frac_algorithmic": algo / i8_peak,
+            "bound": "tensor", "achieved": algo, "peak": i8_peak, "unit": "TOP/s", "frac": algo / i8_peak,
+            "achieved_issued": issued, "frac_issued": issued / i8_peak,
+            "algorithmic_ops": "2*B*N*K per launch (B targets x N coordinates x K contraction length), summed over the "
+                               "launches of the timed region; `issued` multiplies by the digit pairs the tensor pipe "
+                               "actually executed (zero digit planes skipped), counted by the kernel",
             "traffic": 8.77e9, "traffic_note": "dram read+write of the S*z launch (the largest one) from the ncu --set full "
                                               "capture profiles/prof_i8_sz_r1.ncu-rep; algorithmic 2.0 GB per launch "
                                               "(z digits 0.97 + S digits 0.31 + e 0.77)",
