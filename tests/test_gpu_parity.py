@@ -525,6 +525,34 @@ def test_samp_p_gpv_preimage_and_domain(T, n, q, s):
     assert np.array_equal(e, e_split)
 
 
+@pytest.mark.parametrize("n,q,s", [(8, 2**16, 120.0), (16, 65521, 200.0), (24, 2**16, 300.0), (32, 2**12 - 3, 300.0)])
+def test_samp_p_gpv_structured_basis_matches_dense(T, n, q, s, monkeypatch):
+    """A short basis built by gen_short_basis_for_trapdoor has the form [[R S', I + R W],[S', W]]; the backend
+    recovers and verifies (R, W) exactly and evaluates e = sol + S z through the two thin factors.  Integer
+    arithmetic on the same z: the preimages must be bit-identical to the dense S z path."""
+    gp = T.GadgetParameters.init_default(n, q)
+    assert (n * gp.k) % 128 == 0
+    rng = np.random.default_rng(n)
+    u = rng.integers(0, q, (700, n), dtype=np.int64)
+    psf = T.PSFGPV(gp, s)
+    a, td = psf.trap_gen(seed=11)
+    e_struct = psf.samp_p_batch(a, td, u, seed=6)
+    assert np.array_equal(O.f_a_classical_batch(a, e_struct, q), u) and psf.check_domain_batch(e_struct).all()
+    monkeypatch.setenv("QF_DISABLE_GPV_STRUCT", "1")
+    psf2 = T.PSFGPV(gp, s)
+    psf2._install_a(a)
+    e_dense = psf2.samp_p_batch(a, td, u, seed=6)
+    assert np.array_equal(e_struct, e_dense)
+    # a basis that is NOT of that form (two columns swapped -- still a basis of the same lattice) takes the dense path
+    monkeypatch.delenv("QF_DISABLE_GPV_STRUCT")
+    sb = td[0].copy()
+    sb[:, [0, 1]] = sb[:, [1, 0]]
+    psf3 = T.PSFGPV(gp, s)
+    psf3._install_a(a)
+    e3 = psf3.samp_p_batch(a, (sb, None), u, seed=6)
+    assert np.array_equal(O.f_a_classical_batch(a, e3, q), u) and psf3.check_domain_batch(e3).all()
+
+
 def test_samp_p_gpv_distribution(T):
     """GPV08 SampleD outputs D_{Lambda_u^perp(A), s}: spherical, variance s^2/(2 pi) per coordinate;
     compared with the oracle's restatement of the reference loop on the same key."""

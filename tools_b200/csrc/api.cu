@@ -140,6 +140,13 @@ struct qf_ctx {
     Dev dRl;               // R as one s8 plane m_bar x ldk_nk
     Dev dSl;               // S as s_limbs planes of dim x ldk_dim
     int s_limbs = 0, z_limbs = 0;
+    // G-trapdoor structure of the short basis, S = [[R S', I + R W],[S', W]] (short_basis_classical.rs:54-110),
+    // recovered and verified exactly when the trapdoor is installed: e = S z then costs two thin contractions
+    // (W z2 and R (S' z1 + W z2)) instead of the dense m x m one
+    bool gpv_struct = false;
+    int gpv_rev = 0, i2_limbs = 2;
+    Dev dWl, dSkf;         // W as nk x ldk_mb u8 plane; S_k (k x k, fp64)
+    long ldk_mb = 0;
     // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
     bool use_ozaki = false;
     int u_limbs = 7;
@@ -702,13 +709,46 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
             LAUNCH(qf_launch_split_f64_limbs(Z, ldD, zp, plane, ldk, Bc, (int)D, ctx->z_limbs, ctx->dFlag.as<int>(), nullptr, 0,
                                              0, 0, ctx->stream));
         }
-        g.x = zp; g.ldx = ldk; g.x_plane = plane;
-        g.w = ctx->dSl.p; g.ldw = ldk; g.w_plane = D * ldk;
-        g.LX = ctx->z_limbs; g.LW = ctx->s_limbs; g.w_signed = 1;
-        g.B = Bc; g.N = (int)D; g.K = (int)D;
-        g.out_kind = 1; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = dE; g.ldout = D;
-        g.flag = ctx->dFlag.as<int>();
-        LAUNCH(ctx_gemm_i8(ctx, g));
+        if (ctx->gpv_struct) {
+            // S z = [z2 + R i2 ; i2],  i2 = S' z1 + W z2  (z1 = z[0:nk], z2 = z[nk:m])
+            const long nk = ctx->nk, mb = ctx->m_bar, ldnk = ctx->ld_nk, ldk_nk = ctx->ldk_nk;
+            CK(ctx->w[4].ensure((size_t)C * ldnk * 8));
+            double* I2 = ctx->w[4].as<double>();
+            CK(cudaMemsetAsync(I2, 0, (size_t)Bc * ldnk * 8, ctx->stream));
+            g.x = zp + nk; g.ldx = ldk; g.x_plane = plane;
+            g.w = ctx->dWl.p; g.ldw = ctx->ldk_mb; g.w_plane = nk * ctx->ldk_mb;
+            g.LX = ctx->z_limbs; g.LW = 1; g.w_signed = 0;
+            g.B = Bc; g.N = (int)nk; g.K = (int)mb;
+            g.out_kind = 2; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = I2; g.ldout = ldnk;
+            g.flag = ctx->dFlag.as<int>();
+            if (g.x_nz) g.nz_kb_off = (int)(nk / 128);
+            LAUNCH(ctx_gemm_i8(ctx, g));
+            LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev,
+                                          ctx->stream));
+            const long plane2 = C * ldk_nk;
+            CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->i2_limbs * plane2, C * ldD * 8)));  // T is dead: digits of i2
+            int8_t* ip = ctx->w[2].as<int8_t>();
+            LAUNCH(qf_launch_split_f64_limbs(I2, ldnk, ip, plane2, ldk_nk, Bc, (int)nk, ctx->i2_limbs, ctx->dFlag.as<int>(),
+                                             nullptr, 0, 0, 0, ctx->stream));
+            I8GemmArgs h{};
+            h.x = ip; h.ldx = ldk_nk; h.x_plane = plane2;
+            h.w = ctx->dRl.p; h.ldw = ldk_nk; h.w_plane = mb * ldk_nk;
+            h.LX = ctx->i2_limbs; h.LW = 1; h.w_signed = 1;
+            h.B = Bc; h.N = (int)mb; h.K = (int)nk;
+            h.out_kind = 1; h.sign = 1; h.q = 0; h.out = dE; h.ldout = D;
+            h.flag = ctx->dFlag.as<int>();
+            LAUNCH(ctx_gemm_i8(ctx, h));
+            LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, (int)nk, ctx->dFlag.as<int>(),
+                                                 ctx->stream));
+        } else {
+            g.x = zp; g.ldx = ldk; g.x_plane = plane;
+            g.w = ctx->dSl.p; g.ldw = ldk; g.w_plane = D * ldk;
+            g.LX = ctx->z_limbs; g.LW = ctx->s_limbs; g.w_signed = 1;
+            g.B = Bc; g.N = (int)D; g.K = (int)D;
+            g.out_kind = 1; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = dE; g.ldout = D;
+            g.flag = ctx->dFlag.as<int>();
+            LAUNCH(ctx_gemm_i8(ctx, g));
+        }
         LAUNCH(qf_launch_add_cols_i32(dE, D, Sol, ldp, ctx->dPiv.as<int>(), np, Bc, ctx->stream));
     } else {
         double* acc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -966,6 +1006,114 @@ qf_status gso_device(qf_ctx* ctx, const double* dS, double* dG) {
     CK(cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (info) return ctx->fail(QF_ERR_INVALID, "gso: the basis is (numerically) rank deficient");
+    return QF_OK;
+}
+
+// Recover (R, W) from a short basis of the form gen_short_basis_for_trapdoor builds (tag = I) and verify the
+// factorisation exactly; on success e = S z runs in structured form.  Any mismatch leaves the dense path in place.
+qf_status detect_gpv_structure(qf_ctx* ctx, const int64_t* s, const std::vector<int>& piv) {
+    ctx->gpv_struct = false;
+    const char* env = getenv("QF_DISABLE_GPV_STRUCT");
+    if (ctx->prm.kind != QF_PSF_GPV || !ctx->use_i8 || (env && env[0] == '1')) return QF_OK;
+    const long n = ctx->n, k = ctx->k, mb = ctx->m_bar, nk = ctx->nk, m = ctx->m;
+    const uint64_t q = ctx->prm.q, base = (uint64_t)ctx->prm.base;
+    if (nk % 128 != 0 || mb < nk || base > 256) return QF_OK;  // plane offsets / zero-tile map need 128-column alignment
+    u128 pw = 1;
+    for (long i = 0; i < k; ++i) pw *= base;
+    if (pw < q) return QF_OK;
+    const bool exact_pow = pw == (u128)q;
+    std::vector<int64_t> sk((size_t)k * k, 0), qd(k, 0);
+    for (long j = 0; j < k; ++j) sk[j * k + j] = (int64_t)base;
+    for (long i = 0; i + 1 < k; ++i) sk[(i + 1) * k + i] = -1;
+    if (!exact_pow) {
+        uint64_t qq = q;
+        for (long i = 0; i < k; ++i) { qd[i] = (int64_t)(qq % base); sk[i * k + (k - 1)] = qd[i]; qq /= base; }
+    }
+    auto colmap = [&](long cc) { return exact_pow ? nk - 1 - cc : cc; };  // column of I (x) S_k -> column of S'
+    // bottom-left block must be S', bottom-right block W must hold base-b digits
+    for (long row = 0; row < nk; ++row) {
+        const int64_t* sr = s + (size_t)(mb + row) * m;
+        const long blk = row / k, t = row % k;
+        for (long cc = 0; cc < nk; ++cc) {
+            const int64_t want = (cc / k == blk) ? sk[t * k + (cc % k)] : 0;
+            if (sr[colmap(cc)] != want) return QF_OK;
+        }
+        for (long c = 0; c < mb; ++c)
+            if (sr[nk + c] < 0 || (uint64_t)sr[nk + c] >= base) return QF_OK;
+    }
+    // R from the top-left block: Y[i][cc] = sum_t R[i][blk k + t] S_k[t][cc % k]
+    std::vector<int8_t> R((size_t)mb * nk);
+    std::vector<i128> x(k), P(k);
+    for (long i = 0; i < mb; ++i) {
+        const int64_t* sr = s + (size_t)i * m;
+        for (long blk = 0; blk < n; ++blk) {
+            auto Y = [&](long c) -> i128 { return (i128)sr[colmap(blk * k + c)]; };
+            if (exact_pow) {
+                i128 v = Y(k - 1);
+                if (v % (i128)base) return QF_OK;
+                x[k - 1] = v / (i128)base;
+                for (long c = k - 2; c >= 0; --c) {
+                    v = Y(c) + x[c + 1];
+                    if (v % (i128)base) return QF_OK;
+                    x[c] = v / (i128)base;
+                }
+            } else {
+                // x_t = base^t x_0 - P_t, P_0 = 0, P_{t+1} = base P_t + Y_t;  sum_t q_t x_t = Y_{k-1}
+                P[0] = 0;
+                for (long t = 0; t + 1 < k; ++t) P[t + 1] = (i128)base * P[t] + Y(t);
+                i128 acc = Y(k - 1);
+                for (long t = 0; t < k; ++t) acc += (i128)qd[t] * P[t];
+                if (acc % (i128)q) return QF_OK;
+                const i128 x0 = acc / (i128)q;
+                i128 pwt = 1;
+                for (long t = 0; t < k; ++t) { x[t] = pwt * x0 - P[t]; pwt *= (i128)base; }
+            }
+            for (long t = 0; t < k; ++t) {
+                if (x[t] > 127 || x[t] < -127) return QF_OK;
+                R[(size_t)i * nk + blk * k + t] = (int8_t)x[t];
+            }
+        }
+    }
+    // top-right block must be I + R W: the product on the tensor cores, compared exactly
+    const long ldk = ctx->ldk_nk;
+    ctx->ldk_mb = (mb + 127) / 128 * 128;
+    std::vector<int64_t> r64((size_t)mb * nk), wt((size_t)mb * nk), w64((size_t)nk * mb);
+    for (size_t i = 0; i < r64.size(); ++i) r64[i] = R[i];
+    for (long row = 0; row < nk; ++row)
+        for (long c = 0; c < mb; ++c) {
+            const int64_t d = s[(size_t)(mb + row) * m + nk + c];
+            wt[(size_t)c * nk + row] = d;
+            w64[(size_t)row * mb + c] = d;
+        }
+    Dev dWt, dOut;
+    QF_TRY(upload_limbs(ctx, r64.data(), mb, nk, ldk, 1, true, ctx->dRl));
+    QF_TRY(upload_limbs(ctx, wt.data(), mb, nk, ldk, 1, false, dWt));
+    CK(dOut.ensure((size_t)mb * mb * 4));
+    {
+        I8GemmArgs g{};
+        g.x = ctx->dRl.as<int8_t>(); g.ldx = ldk; g.x_plane = mb * ldk;
+        g.w = dWt.p; g.ldw = ldk; g.w_plane = mb * ldk;
+        g.LX = 1; g.LW = 1; g.w_signed = 0;
+        g.B = (int)mb; g.N = (int)mb; g.K = (int)nk;
+        g.out_kind = 1; g.sign = 1; g.q = 0; g.out = dOut.p; g.ldout = mb;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    }
+    std::vector<int32_t> rw((size_t)mb * mb);
+    CK(cudaMemcpyAsync(rw.data(), dOut.p, rw.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (long i = 0; i < mb; ++i)
+        for (long c = 0; c < mb; ++c)
+            if (s[(size_t)i * m + nk + c] != (int64_t)rw[(size_t)i * mb + c] + (i == c ? 1 : 0)) return QF_OK;
+    // verified: install W (nk x m_bar, key of the first contraction) and S_k
+    QF_TRY(upload_limbs(ctx, w64.data(), nk, mb, ctx->ldk_mb, 1, false, ctx->dWl));
+    QF_TRY(upload_as_f64(ctx, sk.data(), k, k, k, ctx->dSkf));
+    ctx->gpv_rev = exact_pow ? 1 : 0;
+    // |S' z1 + W z2| = |e - sol| on the gadget block: 6 s tail cut, plus q if a pivot column lies there
+    bool piv_low = false;
+    for (int pc : piv) piv_low = piv_low || pc >= mb;
+    ctx->i2_limbs = limbs_for(8.0 * ctx->prm.s + 64.0 + (piv_low ? (double)q : 0.0));
+    ctx->gpv_struct = true;
     return QF_OK;
 }
 
@@ -1377,7 +1525,9 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     if (ctx->use_i8) {
         if (ctx->z_limbs + ctx->s_limbs - 1 > 16) return ctx->fail(QF_ERR_UNSUPPORTED, "too many digits for the int8 S*z product");
         ctx->zlimit = std::min(ctx->zlimit, limb_capacity(ctx->z_limbs));
-        QF_TRY(upload_limbs(ctx, s, D, D, ctx->ldk_dim, ctx->s_limbs, true, ctx->dSl));
+        QF_TRY(detect_gpv_structure(ctx, s, piv));
+        if (ctx->gpv_struct) ctx->dSl.release();
+        else QF_TRY(upload_limbs(ctx, s, D, D, ctx->ldk_dim, ctx->s_limbs, true, ctx->dSl));
         const char* env = getenv("QF_DISABLE_OZAKI");
         const char* envmin = getenv("QF_OZAKI_MIN_DIM");
         const long min_dim = envmin ? atol(envmin) : 2 * NP_SIZES[2];

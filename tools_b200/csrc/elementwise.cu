@@ -556,6 +556,53 @@ cudaError_t qf_launch_pert_normal_digits(int B, int M, int split, uint64_t seed,
         sqrt_beta, bscale, flag);
     return cudaGetLastError();
 }
+namespace {
+// I2[b][row] += sum_c S'[row][c] z1[b][c] for the block-diagonal gadget basis S' = (I_n (x) S_k), columns reversed
+// when `reversed` (short_basis_classical.rs:80-82): only the k columns of the row's own block contribute.
+__global__ void sprime_apply_kernel(const double* __restrict__ Z, long ldz, double* __restrict__ I2, long ldi, int B, int nk,
+                                    int k, const double* __restrict__ sk, int reversed) {
+    const long total = (long)B * nk;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / nk;
+        const int row = (int)(i - b * nk);
+        const int blk = row / k, t = row - blk * k;
+        const double* zr = Z + b * ldz;
+        double acc = 0.0;
+        for (int c = 0; c < k; ++c) {
+            const int cc = blk * k + c;                      // column of I_n (x) S_k
+            const int col = reversed ? nk - 1 - cc : cc;     // where that column sits in S'
+            acc = fma(sk[t * k + c], zr[col], acc);
+        }
+        I2[b * ldi + row] += acc;
+    }
+}
+// e[b][i] += z2[b][i] (i < mb),  e[b][mb + row] = I2[b][row]: the structured form of e = S z
+__global__ void gpv_struct_finalize_kernel(int32_t* __restrict__ e, long lde, const double* __restrict__ Z2, long ldz,
+                                           const double* __restrict__ I2, long ldi, int B, int mb, int nk, int* flag) {
+    const int m = mb + nk;
+    const long total = (long)B * m;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / m;
+        const int j = (int)(i - b * m);
+        double v = j < mb ? (double)e[b * lde + j] + Z2[b * ldz + j] : I2[b * ldi + (j - mb)];
+        if (!(fabs(v) < 2147483647.0)) { if (flag) atomicOr(flag, 4); v = 0.0; }
+        e[b * lde + j] = (int32_t)__double2ll_rn(v);
+    }
+}
+}  // namespace
+cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long ldi, int B, int nk, int k, const double* sk,
+                                   int reversed, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    sprime_apply_kernel<<<grid_for((long long)B * nk, TPB), TPB, 0, stream>>>(Z, ldz, I2, ldi, B, nk, k, sk, reversed);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2, long ldz, const double* I2, long ldi, int B,
+                                          int mb, int nk, int* flag, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    gpv_struct_finalize_kernel<<<grid_for((long long)B * (mb + nk), TPB), TPB, 0, stream>>>(e, lde, Z2, ldz, I2, ldi, B, mb, nk,
+                                                                                           flag);
+    return cudaGetLastError();
+}
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
                               int B, int mb, int nk, double sqrt_beta, double fscale, int L, int* flag, cudaStream_t stream) {
     if (B <= 0 || nk <= 0) return cudaSuccess;

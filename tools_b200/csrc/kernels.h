@@ -55,6 +55,11 @@ cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t s
 cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32,
                              long ldoi, int B, int M, double s, uint64_t seed, uint64_t first_target,
                              uint32_t tag, cudaStream_t stream);
+// structured e = S z for the G-trapdoor short basis S = [[R S', I + R W],[S', W]] (api.cu detect_gpv_structure)
+cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long ldi, int B, int nk, int k, const double* sk,
+                                   int reversed, cudaStream_t stream);
+cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2, long ldz, const double* I2, long ldi, int B,
+                                          int mb, int nk, int* flag, cudaStream_t stream);
 // structured perturbation (api.cu setup_structured_sigma2): X2[b][mb+j] = sqrt_beta * G[b][mb+j] and the balanced
 // base-256 digits of rint(that * fscale) into L planes of B x ldk bytes
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
