@@ -208,7 +208,7 @@ def main():
     n, q, desc = WORKLOADS[args.workload]
     gp = T.GadgetParameters.init_default(n, q)
     s = gpv_s(gp)
-    batch = args.batch or (37888 if args.workload == "c2" else 65536)  # c2: two internal chunks of 148 x 128 targets
+    batch = args.batch or (75776 if args.workload == "c2" else 65536)  # c2: four internal chunks of 148 x 128 targets
     t0 = time.time()
     psf = T.PSFGPV(gp, s, device=local)
     a, td = psf.trap_gen(seed=2)  # same seed on every rank: the key is replicated, not communicated

@@ -771,3 +771,79 @@ def test_full_size_c5_compression_properties(T):
         assert np.array_equal(T.lossy_compress(back % 3329, d, 3329), c)  # Compress(Decompress(y)) = y
         sample = x[::4099]
         assert np.array_equal(c[::4099].astype(np.uint64), O.lossy_compress_np(sample, d, 3329))
+
+
+def test_full_size_c3_ring_properties(T):
+    """BASELINE.json configs[2] at full key size (PSFGPVRing over X^256 + 1, q = 3329, 14 polynomials, embedded
+    dimension 3584): ring f_a against the exact negacyclic product on the host, additivity, A e = u for every
+    preimage (exact host arithmetic), check_domain, the spherical second moment, and batch splitting."""
+    n, q = 256, 3329
+    gp = T.GadgetParametersRing.init_default(n, q)
+    s = float(_ring_s(n))
+    psf = T.PSFGPVRing(gp, s, 1.005)
+    a, td = psf.trap_gen(seed=3)
+    # the exact ring product via the negacyclic matrix rot^-(a_j) in int64 (entries < 2^12, |sigma| < 2^13, 3584 terms)
+    rot = np.concatenate([T.gadget._rot_i64(a[j]) for j in range(gp.k + 2)], axis=1)  # n x n(k+2)
+    sig = psf.samp_d_batch(4096, seed=5)
+    u, flags = psf.f_a_batch(a, sig)
+    assert flags.all()
+    assert np.array_equal((sig.reshape(4096, -1).astype(np.int64) @ rot.T) % q, u)
+    half = (sig // 2).astype(np.int32)
+    u1, _ = psf.f_a_batch(a, half)
+    u2, _ = psf.f_a_batch(a, (sig - half).astype(np.int32))
+    assert np.array_equal((u1 + u2) % q, u)
+    rng = np.random.default_rng(4)
+    B = 4096
+    tg = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, tg, seed=7)
+    assert e.shape == (B, gp.k + 2, n)
+    assert np.array_equal((e.reshape(B, -1).astype(np.int64) @ rot.T) % q, tg)
+    assert psf.check_domain_batch(e).all()
+    D = n * (gp.k + 2)
+    ratio = (e.astype(np.float64) ** 2).sum((1, 2)).mean() / (D * s * s / (2 * np.pi))
+    assert abs(ratio - 1) < 0.01, ratio
+    e2 = np.concatenate([psf.samp_p_batch(a, td, tg[:1000], seed=7), psf.samp_p_batch(a, td, tg[1000:], seed=7, first_index=1000)])
+    assert np.array_equal(e, e2)
+
+
+def test_full_size_c4_shard_properties(T):
+    """BASELINE.json configs[3] at full key size (PSFPerturbation n = 512, q = 2^32 - 5, k = 32, m = 32849, r = 9),
+    one GPU's shard: TrapGen A [R; I] = G exactly, A e = u for every preimage in exact host arithmetic (object
+    integers on a sample, int64 with a 16-bit split of A for all), check_domain, the second moment, batch splitting."""
+    import math
+
+    n, q, r = 512, 2**32 - 5, 9.0
+    gp = T.GadgetParameters.init_default(n, q)
+    assert (gp.k, gp.m_bar, gp.m) == (32, 16465, 32849)
+    s1 = (math.sqrt(gp.m_bar) + math.sqrt(n * gp.k)) / math.sqrt(2)
+    s = float(math.ceil(1.15 * math.sqrt(5 * (s1 * s1 + 1) + 1)))
+    psf = T.PSFPerturbation(gp, r, s)
+    a, td = psf.trap_gen(seed=4)
+    assert td[1] is None  # block-structured square root of the default Sigma_2, built on the device
+    rmat = td[0]
+    # A [R; I] = G mod q: exact via two 16-bit halves of A in float64 BLAS (|sum| < 2^16 * 16465 < 2^53)
+    a_bar, a_g = a[:, :gp.m_bar], a[:, gp.m_bar:]
+    rf = rmat.astype(np.float64)
+    lo = np.rint((a_bar & 0xFFFF).astype(np.float64) @ rf).astype(np.int64)
+    hi = np.rint((a_bar >> 16).astype(np.float64) @ rf).astype(np.int64)
+    prod = (lo % q + ((hi % q) << 16) % q + a_g) % q
+    g = np.zeros((n, n * gp.k), dtype=np.int64)
+    for j in range(n):
+        g[j, j * gp.k:(j + 1) * gp.k] = [(1 << t) % q for t in range(gp.k)]
+    assert np.array_equal(prod, g)
+    rng = np.random.default_rng(6)
+    B = 2048
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    e = psf.samp_p_batch(a, td, u, seed=9)
+    ef = e.astype(np.float64)
+    lo = np.rint(ef @ (a & 0xFFFF).astype(np.float64).T).astype(np.int64)      # |e| < 2^16, 32849 terms: < 2^47
+    hi = np.rint(ef @ (a >> 16).astype(np.float64).T).astype(np.int64)
+    assert np.array_equal((lo % q + ((hi % q) << 16) % q) % q, u)
+    assert [int(x) for x in (e[:2].astype(object) @ a.T.astype(object) % q).ravel()] == u[:2].ravel().tolist()
+    assert psf.check_domain_batch(e).all()
+    ratio = (ef**2).sum(1).mean() / (gp.m * (s * r) ** 2 / (2 * math.pi))
+    assert abs(ratio - 1) < 0.01, ratio
+    e2 = np.concatenate([psf.samp_p_batch(a, td, u[:700], seed=9), psf.samp_p_batch(a, td, u[700:], seed=9, first_index=700)])
+    assert np.array_equal(e, e2)
+    uu, flags = psf.f_a_batch(a, e)
+    assert flags.all() and np.array_equal(uu, u)
