@@ -22,7 +22,11 @@ def _run(x, w, w_signed, lx, lw, q):
     (300, 70, 517, 2, 3, 0, 2**24 - 3), (64, 256, 4096, 3, 2, 1, 0), (257, 300, 12352, 2, 3, 0, 2**24),
     (200, 96, 2500, 2, 4, 0, 2**32 - 5), (100, 48, 700, 5, 2, 1, 0), (33, 40, 300, 2, 8, 0, 2**61 - 1),
 ])
-def test_gemm_i8_exact(B, N, K, lx, lw, w_signed, q):
+@pytest.mark.parametrize("bk", [0, 64, 128])
+def test_gemm_i8_exact(B, N, K, lx, lw, w_signed, q, bk, monkeypatch):
+    """bk: K block of the shared-memory operand tiles (128: SWIZZLE_128B, 64: SWIZZLE_64B, 0: the launcher's choice)."""
+    if bk:
+        monkeypatch.setenv("QF_I8_BLOCK_K", str(bk))
     rng = np.random.default_rng(B * N + K)
     xmax = 127 * (256**lx - 1) // 255  # largest value with lx balanced digits in [-128,127]
     x = rng.integers(-xmax, xmax + 1, (B, K), dtype=np.int64)

@@ -20,6 +20,8 @@
 // so one tile per CTA (no TMEM double buffering).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
@@ -34,6 +36,7 @@ struct I8Params {
     int LX, LW;
     int nt;        // N tile (multiple of 16)
     int stages;
+    int bk;        // K block in bytes: 128 (SWIZZLE_128B tiles) or 64 (SWIZZLE_64B, twice the pipeline depth)
     int w_signed;  // b_format: 1 = s8 limbs, 0 = u8 limbs
     // epilogue
     int out_kind;  // 0: int64 (optionally mod q, optional base, sign), 1: int32 store, 2: fp64 accumulate (+=)
@@ -57,7 +60,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand ring
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int x_tile = TILE_M * BLOCK_K, w_tile = p.nt * BLOCK_K;
+    const int BK = p.bk;
+    const int x_tile = TILE_M * BK, w_tile = p.nt * BK;
     const int stage_bytes = p.LX * x_tile + p.LW * w_tile;
     uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
@@ -67,7 +71,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int num_kb = (p.K + BK - 1) / BK;
     const int ND = p.LX + p.LW - 1;
     const int total_tiles = p.m_tiles * p.n_tiles;
     // tile rasterisation: consecutive tiles walk group_m target tiles for one n tile, then the next n tile
@@ -83,7 +87,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (!p.x_nz) return (1u << p.LX) - 1u;
         uint32_t mk = 0;
         for (int j = 0; j < p.LX; ++j)
-            if (p.x_nz[((size_t)j * p.nz_m_tiles + (p.nz_m_off + tile_m)) * p.nz_kb_total + p.nz_kb_off + kb]) mk |= 1u << j;
+            if (p.x_nz[((size_t)j * p.nz_m_tiles + (p.nz_m_off + tile_m)) * p.nz_kb_total + p.nz_kb_off + ((kb * BK) >> 7)]) mk |= 1u << j;
         return mk;
     };
 
@@ -135,8 +139,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     } else {
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mk) * x_tile + p.LW * w_tile));
                         for (int j = 0; j < p.LX; ++j)
-                            if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BLOCK_K, m0, j);
-                        for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
+                            if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BK, m0, j);
+                        for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BK, n0, i);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -148,7 +152,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // N = g * nt covers g adjacent digit planes of w (their smem tiles and their accumulators are contiguous)
         const uint32_t idesc0 = (2u << 4) | (1u << 7) | ((uint32_t)(p.w_signed ? 1 : 0) << 10) | ((uint32_t)(TILE_M >> 4) << 24);
         const int G = max(1, min(p.LW, 256 / p.nt));
-        const uint64_t desc0 = make_desc(smem_u32(smem));
+        const uint64_t desc0 = make_desc(smem_u32(smem), BK);
         int stage = 0;
         uint32_t phase = 0;
         unsigned long long units = 0;  // executed (x digit, w digit, k block) products, for the profiler
@@ -176,7 +180,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
                             const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
 #pragma unroll
-                            for (int kk = 0; kk < BLOCK_K / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
+                            for (int kk = 0; kk < BK / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
                                 mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
                             units += (unsigned long long)g;
                         }
@@ -189,7 +193,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
         }
         if (lane == 0 && p.mma_units && units)
-            atomicAdd(p.mma_units, units * (2ull * TILE_M * BLOCK_K) * (unsigned long long)p.nt);  // int8 operations
+            atomicAdd(p.mma_units, units * (2ull * TILE_M * BK) * (unsigned long long)p.nt);  // int8 operations
     } else {
         // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
         const int lg = warp & 3;
@@ -326,16 +330,25 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     }
     p.x_nz = a.x_nz; p.nz_m_tiles = a.nz_m_tiles; p.nz_kb_total = a.nz_kb_total; p.nz_kb_off = a.nz_kb_off;
     p.nz_m_off = a.nz_m_off;
-    const int stage_bytes = a.LX * TILE_M * BLOCK_K + a.LW * nt * BLOCK_K;
+    // K block: 128-byte rows (SWIZZLE_128B).  QF_I8_BLOCK_K=64 selects 64-byte rows (SWIZZLE_64B): twice the pipeline
+    // depth in the same shared memory, but measured 30 % slower on B200 (round-1 profile notes) -- the kernel is bound by
+    // L2 -> shared-memory operand traffic, not by pipeline depth, and the 64-byte layout feeds the tensor core worse.
     const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;  // barriers + tmem slot + inited mask
+    int bk = BLOCK_K;
+    {
+        const char* env = getenv("QF_I8_BLOCK_K");
+        if (env && atoi(env) == 64) bk = 64;
+    }
+    p.bk = bk;
+    const int stage_bytes = a.LX * TILE_M * bk + a.LW * nt * bk;
     int stages = budget / stage_bytes;
     if (stages < 2) return cudaErrorInvalidValue;
     if (stages > 8) stages = 8;
     p.stages = stages;
     const int smem = stages * stage_bytes + 1024 + 256;
     CUtensorMap mx, mw;
-    if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M)) return cudaErrorInvalidValue;
-    if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
+    if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M, bk)) return cudaErrorInvalidValue;
+    if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt, bk)) return cudaErrorInvalidValue;
     static int configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"

@@ -7,7 +7,7 @@
 namespace tc05 {
 
 constexpr int TILE_M = 128;
-constexpr int BLOCK_K = 128;  // bytes = int8 elements
+constexpr int BLOCK_K = 128;  // bytes = int8 elements (default K block; 64 selects SWIZZLE_64B tiles, see make_desc)
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -37,13 +37,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem, 
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// K-major, SWIZZLE_128B operand tile (rows of 128 bytes, 8-row atoms of 1024 bytes)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+// K-major swizzled operand tile: rows of bk bytes (bk = 128: SWIZZLE_128B, 8-row atoms of 1024 bytes;
+// bk = 64: SWIZZLE_64B, 8-row atoms of 512 bytes)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int bk = BLOCK_K) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);      // start address
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset (8 rows x 128 B)
+    d |= (uint64_t)((8 * bk) >> 4) << 32;             // stride byte offset (8 rows x bk bytes)
     d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)(bk == 64 ? 4 : 2) << 61;          // SWIZZLE_64B / SWIZZLE_128B
     return d;
 }
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -107,15 +108,17 @@ inline EncodeTiledFn get_encode() {
 }
 
 // planes: `limbs` matrices of rows x K bytes (row stride ld, plane stride plane_bytes)
-inline bool make_map(CUtensorMap* map, const void* base, int K, int rows, int limbs, long ld, long plane_bytes, int box_rows) {
+inline bool make_map(CUtensorMap* map, const void* base, int K, int rows, int limbs, long ld, long plane_bytes, int box_rows,
+                     int bk = BLOCK_K) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)limbs};
     cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane_bytes};
-    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
