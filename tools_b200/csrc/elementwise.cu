@@ -567,11 +567,19 @@ __global__ void sprime_apply_kernel(const double* __restrict__ Z, long ldz, doub
         const int row = (int)(i - b * nk);
         const int blk = row / k, t = row - blk * k;
         const double* zr = Z + b * ldz;
+        // row t of S_k has at most three non-zeros: the diagonal, the sub-diagonal -1 and (q not a power of the base)
+        // the digit of q in the last column
         double acc = 0.0;
-        for (int c = 0; c < k; ++c) {
+        const int cand[3] = {t - 1, t, k - 1};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int c = cand[e];
+            if (c < 0 || (e == 2 && (c == t || c == t - 1))) continue;
+            const double sv = sk[t * k + c];
+            if (sv == 0.0) continue;
             const int cc = blk * k + c;                      // column of I_n (x) S_k
             const int col = reversed ? nk - 1 - cc : cc;     // where that column sits in S'
-            acc = fma(sk[t * k + c], zr[col], acc);
+            acc = fma(sv, zr[col], acc);
         }
         I2[b * ldi + row] += acc;
     }
