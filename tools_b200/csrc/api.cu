@@ -316,9 +316,10 @@ cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
     if (trace) {  // diagnostics only: per-launch time and executed digit pairs (synchronises)
         Dev cnt;
         cudaEvent_t t0, t1;
-        if (cnt.ensure(8) != cudaSuccess) return cudaErrorMemoryAllocation;
-        cudaMemsetAsync(cnt.p, 0, 8, ctx->stream);
+        if (cnt.ensure(40) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(cnt.p, 0, 40, ctx->stream);
         aa.mma_units = cnt.as<unsigned long long>();
+        aa.tim = cnt.as<unsigned long long>() + 1;
         cudaEventCreate(&t0); cudaEventCreate(&t1);
         cudaEventRecord(t0, ctx->stream);
         cudaError_t e2 = qf_launch_gemm_i8(aa, ctx->stream);
@@ -326,8 +327,11 @@ cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
         cudaStreamSynchronize(ctx->stream);
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
-        unsigned long long h = 0;
-        cudaMemcpy(&h, cnt.p, 8, cudaMemcpyDeviceToHost);
+        unsigned long long hh[5] = {0, 0, 0, 0, 0};
+        cudaMemcpy(hh, cnt.p, 40, cudaMemcpyDeviceToHost);
+        const unsigned long long h = hh[0];
+        fprintf(stderr, "     per-CTA Mclk: mma-wait-tmem_empty %.2f  mma-wait-full %.2f  epi-wait-tmem_full %.2f  epi-body %.2f\n",
+                hh[1] / 148e6, hh[2] / 148e6, hh[3] / 148e6, hh[4] / 148e6);
         const double nominal = 2.0 * a.B * (double)a.N * a.K;
         fprintf(stderr, "[i8] B=%d N=%d K=%d LX=%d LW=%d kind=%d  %.3f ms  pairs/mac=%.2f of %d  %.0f TOP/s executed\n", a.B, a.N,
                 a.K, a.LX, a.LW, a.out_kind, ms, (double)h / nominal, a.LX * a.LW, (double)h / (ms * 1e-3) / 1e12);
@@ -1119,8 +1123,11 @@ qf_status detect_gpv_structure(qf_ctx* ctx, const int64_t* s, const std::vector<
 
 template <typename F>
 qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
-    for (int64_t b0 = 0; b0 < batch; b0 += ctx->chunk) {
-        int Bc = (int)std::min<int64_t>(ctx->chunk, batch - b0);
+    // balanced chunks: a batch slightly above the chunk size is split evenly instead of into a full and a tiny chunk
+    const int64_t nch = std::max<int64_t>(1, (batch + ctx->chunk - 1) / ctx->chunk);
+    const int64_t per = std::min<int64_t>(ctx->chunk, ((batch + nch - 1) / nch + 127) / 128 * 128);
+    for (int64_t b0 = 0; b0 < batch; b0 += per) {
+        int Bc = (int)std::min<int64_t>(per, batch - b0);
         QF_TRY(f(b0, Bc));
     }
     return QF_OK;

@@ -51,10 +51,77 @@ struct I8Params {
     // optional zero-tile map of the x digit planes: nz[(j * m_tiles_total + m_tile) * kb_total + kb_off + kb]
     const uint8_t* x_nz; int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
     unsigned long long* mma_units;  // optional device counter of executed int8 operations (tensor pipe work)
+    // optional diagnostics (QF_TRACE): cycles the MMA warp waited for [0] drained accumulators, [1] operand tiles, and the
+    // epilogue spent [2] waiting for the accumulators, [3] draining them (summed over CTAs)
+    unsigned long long* tim;
 };
+
+// s32 -> f64 without the conversion unit: 2^52 + 2^31 + x is exactly representable, built by bit insertion
+__device__ __forceinline__ double s32_to_f64(int32_t x) {
+    return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// Epilogue of one 128 x 32 tile of the scaled fp64 update out[b][n] = old - V * scale[n], V = sum_d 256^d D_d:
+// NDT accumulators of 32 columns each (NDT compile time: straight-line Horner, no predication), 4 columns per TMEM
+// trip, the old values `pre` already in registers.
+template <int NDT>
+__device__ __forceinline__ void epi_update32(uint32_t lane_addr, const double2 (&pre)[16], double* orow,
+                                             const double* __restrict__ scale, int nd_rt = NDT) {
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 4) {
+        int32_t t[NDT][4];
+#pragma unroll
+        for (int d = 0; d < NDT; ++d)
+            if (d < nd_rt) tmem_ld4(lane_addr + (uint32_t)(d * 32 + c0), t[d]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // Horner in fp64 from the top digit: rounding stays at 2^-53 of the running value
+            double dv = 0.0;
+#pragma unroll
+            for (int d = NDT - 1; d >= 0; --d)
+                if (d < nd_rt) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
+            const double old = (c & 1) ? pre[(c0 + c) >> 1].y : pre[(c0 + c) >> 1].x;
+            r[c] = fma(-dv, scale[c0 + c], old);
+        }
+        *reinterpret_cast<double2*>(orow + c0) = make_double2(r[0], r[1]);
+        *reinterpret_cast<double2*>(orow + c0 + 2) = make_double2(r[2], r[3]);
+    }
+}
+
+// General tile width / ragged edges: COLS columns per TMEM trip, at most NDT accumulators (nd of them live),
+// old values fetched before the accumulators are read.
+template <int NDT, int COLS>
+__device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow, const double* __restrict__ scale, int n0,
+                                               int nt, int N, bool rv, int nd) {
+    for (int c0 = 0; c0 < nt; c0 += COLS) {
+        double told[COLS];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) told[c] = (rv && n0 + c0 + c < N) ? orow[n0 + c0 + c] : 0.0;
+        int32_t t[NDT][COLS];
+#pragma unroll
+        for (int d = 0; d < NDT; ++d)
+            if (d < nd) {
+                if (COLS == 8) tmem_ld8(lane_addr + (uint32_t)(d * nt + c0), t[d]);
+                else tmem_ld4(lane_addr + (uint32_t)(d * nt + c0), t[d]);
+            }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            double dv = 0.0;
+#pragma unroll
+            for (int d = NDT - 1; d >= 0; --d)
+                if (d < nd) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
+            const int n = n0 + c0 + c;
+            if (rv && n < N) orow[n] = told[c] - dv * scale[n];
+        }
+    }
+}
 
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM and the barriers are set up
 // once; the TMA producer runs ahead into the next tile while the epilogue of the current one drains TMEM.
+template <int OK3>  // OK3 = 1: the scaled fp64 update epilogue (out_kind 3) only; 0: the integer epilogues
 __global__ void __launch_bounds__(I8_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -156,17 +223,24 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         unsigned long long units = 0;  // executed (x digit, w digit, k block) products, for the profiler
+        long long tw_empty = 0, tw_full = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int tile_m, tile_n;
             tile_coords(tile, tile_m, tile_n);
             if (it > 0) {  // the epilogue must have drained (and re-zeroed) the accumulators of the previous tile
+                const long long t0_ = p.tim ? clock64() : 0;
                 mbar_wait(tmem_empty, (uint32_t)((it - 1) & 1));
+                if (p.tim) tw_empty += clock64() - t0_;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             for (int kb = 0; kb < num_kb; ++kb) {
                 const uint32_t mk = plane_mask(tile_m, kb);
-                mbar_wait(&full_bar[stage], phase);
+                {
+                    const long long t0_ = p.tim ? clock64() : 0;
+                    mbar_wait(&full_bar[stage], phase);
+                    if (p.tim) tw_full += clock64() - t0_;
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
@@ -192,50 +266,48 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
+        if (lane == 0 && p.tim) { atomicAdd(p.tim + 0, (unsigned long long)tw_empty); atomicAdd(p.tim + 1, (unsigned long long)tw_full); }
         if (lane == 0 && p.mma_units && units)
             atomicAdd(p.mma_units, units * (2ull * TILE_M * BK) * (unsigned long long)p.nt);  // int8 operations
     } else {
         // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
         const int lg = warp & 3;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        long long te_wait = 0, te_body = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int tile_m, tile_n;
             tile_coords(tile, tile_m, tile_n);
             const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
-            mbar_wait(tmem_full, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + lg * 32 + lane;
-            if (p.out_kind == 3) {
-                // scaled fp64 update  out[b][n] -= V * scale[n]:  8 columns per trip, the old values are fetched
-                // first, all digit accumulators are read with one wait, and V = sum 256^d D_d is assembled from
-                // four exact 64-bit partial sums (4 digits each) instead of 128-bit arithmetic.
+            // out_kind 3, 32-column tiles: this thread's 32 old values (one 256-byte row segment) are fetched NOW, while
+            // the tile's MMAs are still running, so the DRAM latency of the read-modify-write is off the serial
+            // MMA -> epilogue -> MMA chain (TMEM holds one tile: the next tile's MMAs wait for this epilogue)
+            const bool pre_ok = OK3 && p.nt == 32 && row < p.B && n0 + 32 <= p.N && (p.ldout & 1) == 0 &&
+                                ((((uintptr_t)p.out) & 15) == 0);
+            double2 pre[16];
+            if (OK3 && pre_ok) {
+                const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pre[i] = src[i];
+            }
+            const long long te0_ = p.tim ? clock64() : 0;
+            mbar_wait(tmem_full, (uint32_t)(it & 1));
+            const long long te1_ = p.tim ? clock64() : 0;
+            te_wait += te1_ - te0_;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (OK3 && pre_ok) {
+                double* orow = (double*)p.out + (long)row * p.ldout + n0;
+                if (ND == 11) epi_update32<11>(lane_addr, pre, orow, p.scale + n0);
+                else if (ND == 6) epi_update32<6>(lane_addr, pre, orow, p.scale + n0);
+                else epi_update32<16>(lane_addr, pre, orow, p.scale + n0, ND);
+            } else if (OK3) {
+                // ragged / wider tiles
                 double* orow = (double*)p.out + (long)row * p.ldout;
-                for (int c0 = 0; c0 < p.nt; c0 += 8) {
-                    double told[8];
-                    const bool rv = row < p.B;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) told[c] = (rv && n0 + c0 + c < p.N) ? orow[n0 + c0 + c] : 0.0;
-                    int32_t t[16][8];
-#pragma unroll
-                    for (int d = 0; d < 16; ++d)
-                        if (d < ND) tmem_ld8(lane_addr + (uint32_t)(d * p.nt + c0), t[d]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        long long part[4] = {0, 0, 0, 0};
-#pragma unroll
-                        for (int d = 0; d < 16; ++d)
-                            if (d < ND) part[d >> 2] += ((long long)t[d][c]) << (8 * (d & 3));
-                        double dv = (double)part[3];
-                        dv = fma(dv, 4294967296.0, (double)part[2]);
-                        dv = fma(dv, 4294967296.0, (double)part[1]);
-                        dv = fma(dv, 4294967296.0, (double)part[0]);
-                        const int n = n0 + c0 + c;
-                        if (rv && n < p.N) orow[n] = told[c] - dv * p.scale[n];
-                    }
-                }
-            } else {
+                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
+                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
+                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
+            } else if (!OK3) {
                 for (int c0 = 0; c0 < p.nt; c0 += 16) {
                     __int128 v[16];
 #pragma unroll
@@ -276,6 +348,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
             }
+            if (p.tim) te_body += clock64() - te1_;
             // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
             if (tile + (int)gridDim.x < total_tiles) {
                 for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
@@ -285,6 +358,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (lane == 0) mbar_arrive(tmem_empty);
             }
         }
+        if (warp == 2 && lane == 0 && p.tim) { atomicAdd(p.tim + 2, (unsigned long long)te_wait); atomicAdd(p.tim + 3, (unsigned long long)te_body); }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -351,11 +425,13 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt, bk)) return cudaErrorInvalidValue;
     static int configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     p.mma_units = a.mma_units;
+    p.tim = a.tim;
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
@@ -364,6 +440,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     }
     const int total_tiles = p.m_tiles * p.n_tiles;
     dim3 grid((unsigned)(total_tiles < sm_count ? total_tiles : sm_count));  // persistent: one CTA per SM
-    gemm_i8_kernel<<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
+    if (a.out_kind == 3) gemm_i8_kernel<1><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
+    else gemm_i8_kernel<0><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
     return cudaGetLastError();
 }

@@ -160,6 +160,7 @@ struct I8GemmArgs {
     int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
     // optional device counter: += int8 operations the tensor pipe actually executed (zero digit tiles are skipped)
     unsigned long long* mma_units;
+    unsigned long long* tim;  // optional: 4 phase cycle counters (diagnostics)
 };
 int qf_i8_tile_n(int LX, int LW, int N);
 // gemm_i8_fused.cu: out = X W^t mod q with X read as int32 (digit split fused into the contraction) and the
