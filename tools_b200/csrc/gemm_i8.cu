@@ -283,7 +283,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // out_kind 3, 32-column tiles: this thread's 32 old values (one 256-byte row segment) are fetched NOW, while
             // the tile's MMAs are still running, so the DRAM latency of the read-modify-write is off the serial
             // MMA -> epilogue -> MMA chain (TMEM holds one tile: the next tile's MMAs wait for this epilogue)
-            const bool pre_ok = OK3 && p.nt == 32 && row < p.B && n0 + 32 <= p.N && (p.ldout & 1) == 0 &&
+            // (warp-uniform: tcgen05.ld is .aligned, every lane of the warp must take the same path)
+            const bool pre_ok = OK3 && p.nt == 32 && m0 + lg * 32 + 31 < p.B && n0 + 32 <= p.N && (p.ldout & 1) == 0 &&
                                 ((((uintptr_t)p.out) & 15) == 0);
             double2 pre[16];
             if (OK3 && pre_ok) {
