@@ -157,6 +157,50 @@ def test_f_a_classical_bit_exact(T, n, q, s, r):
     assert f3.all() and np.array_equal(u3, O.f_a_classical_batch(a, mixed, q))
 
 
+def _exact_f_a_int64(a, sig, q):
+    """A sigma mod q in exact int64 arithmetic: A split into 16-bit halves so that no partial sum leaves int64
+    (|sigma| < 2^16, m < 2^15).  Tied to the oracle on the first rows by the caller."""
+    a = np.asarray(a, dtype=np.int64)
+    sg = np.asarray(sig, dtype=np.int64)
+    lo, hi = a & 0xFFFF, a >> 16
+    out = ((sg @ lo.T) % q).astype(object)
+    sh = 1
+    for _ in range(3):  # hi may itself have up to 46 bits: peel 16 bits at a time
+        sh = (sh << 16) % q
+        part, hi = hi & 0xFFFF, hi >> 16
+        out = (out + ((sg @ part.T) % q).astype(object) * sh) % q  # B x n Python integers: no overflow
+    return out.astype(np.int64)
+
+
+@pytest.mark.parametrize("n,q,s,r,B", [(160, 2**24 - 3, 300.0, 4.0, 300), (300, 2**32 - 5, 467.0, 9.0, 150),
+                                         (256, 3329, 40.0, 2.0, 515)])
+def test_f_a_fused_cta_pairs(T, n, q, s, r, B, monkeypatch):
+    """Shapes with an even number of coordinate tiles: the fused f_a kernel runs as clusters of two CTAs that share the
+    converted sigma tiles through distributed shared memory.  Bit-exact against the oracle, ragged batch (B not a
+    multiple of 128) and ragged contraction length (m not a multiple of 128), identical to the unpaired kernel,
+    norms (check_domain) from both halves of the pair."""
+    rng = np.random.default_rng(n)
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, r, s)
+    a = rng.integers(0, q, (n, gp.m), dtype=np.int64)
+    sig = psf.samp_d_batch(B, seed=11)
+    sig[B // 2] = 0  # one out-of-domain row in the second half of a tile, one in the first
+    sig[B // 2, 1] = int(s * r * gp.m)
+    sig[3] = 0
+    sig[3, gp.m - 1] = -int(s * r * gp.m)
+    want = _exact_f_a_int64(a, sig, q)
+    assert np.array_equal(want[:3], O.f_a_classical_batch(a, sig[:3], q))
+    want_flags = np.array([O.check_domain_perturbation(row.tolist(), gp.m, s, r) for row in sig])
+    assert not want_flags[3] and not want_flags[B // 2] and want_flags.sum() == B - 2
+    monkeypatch.delenv("QF_FA_PAIR", raising=False)
+    u, flags = psf.f_a_batch(a, sig, strict=False)
+    assert np.array_equal(flags, want_flags)
+    assert np.array_equal(u[want_flags], want[want_flags])  # (the value of an out-of-domain row is unspecified)
+    monkeypatch.setenv("QF_FA_PAIR", "0")
+    u0, flags0 = psf.f_a_batch(a, sig, strict=False)
+    assert np.array_equal(u0[want_flags], want[want_flags]) and np.array_equal(flags0, want_flags)
+
+
 def test_f_a_domain_errors(T):
     # gpv.rs:287-368 / mp_perturbation.rs:466-554
     gp = T.GadgetParameters.init_default(8, 128)

@@ -4,10 +4,10 @@
 // the squared norms of check_domain (gpv.rs:219-224) are accumulated from the same registers.  No digit planes
 // ever touch HBM (the unfused path writes and re-reads them: 2x the algorithmic traffic plus a second launch).
 //
-// CTA = 10 warps: warps 0..7 convert (one 128-byte digit row per warp instruction: coalesced 512-byte global reads,
+// CTA = 18 warps: warps 0..15 convert (one 128-byte digit row per warp instruction: coalesced 512-byte global reads,
 // conflict-free 4-byte shared stores; the 16 rows of the NEXT k block are already in flight in registers while the
 // current ones are converted, i.e. 64 KB of loads outstanding per SM) and later run the epilogue (TMEM lane group =
-// warp % 4), warp 8 feeds the key digits (A, u8 limbs) through TMA, warp 9 owns TMEM and issues the MMAs.  One 128-target x nt-coordinate tile
+// warp % 4), warp 16 feeds the key digits (A, u8 limbs) through TMA, warp 17 owns TMEM and issues the MMAs.  One 128-target x nt-coordinate tile
 // per CTA, n tiles adjacent in the grid so that the CTAs sharing a block of sigma run together (L2 reuse).
 // Digit planes of sigma that are zero in a whole 128 x 128 block are skipped by the MMA issuer.
 #include <cuda.h>
@@ -40,14 +40,22 @@ struct FusedParams {
 
 // LXT digits of sigma are multiplied.  CHECK: the digits are those of the (LXT+1)-digit representation and the kernel
 // reports through p.overflow when a value has a non-zero digit LXT (the caller then re-runs with one digit more).
-template <int LXT, bool CHECK>
+// PAIR: launched as clusters of two CTAs that own the two adjacent coordinate tiles of the same 128 targets.  Each CTA
+// converts only HALF of the 128 sigma rows and stores the digits into its own operand tile and, through distributed
+// shared memory (st.shared::cluster), into the peer's: every sigma block is read from L2 and converted once per
+// cluster instead of once per CTA (the unpaired kernel is bound by exactly that: converter issue slots and bytes in
+// flight).  A stage is full when the 16 local and the 16 remote converter warps have arrived, and free again when
+// BOTH tensor cores have retired their MMAs on it (tcgen05.commit multicast onto both CTAs' empty barriers).
+template <int LXT, bool CHECK, bool PAIR>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
     if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int x_tile = TILE_M * BLOCK_K, w_tile = p.nt * BLOCK_K;
-    const int stage_bytes = p.LX * x_tile + p.LW * w_tile;
+    constexpr int x_tile = TILE_M * BLOCK_K;
+    constexpr int NCONV = PAIR ? 2 * CONV_WARPS : CONV_WARPS;  // converter warps that feed one stage
+    const int w_tile = p.nt * BLOCK_K;
+    const int stage_bytes = LXT * x_tile + p.LW * w_tile;
     uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
@@ -57,14 +65,15 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int ND = p.LX + p.LW - 1;
-    const int tile_n = blockIdx.x % p.n_tiles, tile_m = blockIdx.x / p.n_tiles;
+    const int ND = LXT + p.LW - 1;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const int tile_n = blockIdx.x % p.n_tiles, tile_m = blockIdx.x / p.n_tiles;  // PAIR: n_tiles even, tile_n & 1 == crank
     const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1 + CONV_WARPS);   // TMA expect_tx arrival + one arrival per converter warp
-            mbar_init(&empty_bar[s], 1);  // tcgen05.commit
+            mbar_init(&full_bar[s], 1 + NCONV);      // TMA expect_tx arrival + one arrival per converter warp
+            mbar_init(&empty_bar[s], PAIR ? 2 : 1);  // tcgen05.commit (of both CTAs of a pair)
         }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -85,6 +94,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is stored to / arrives at them
 
     if (warp == CONV_WARPS) {
         // ===== TMA producer: key digit planes =====
@@ -93,7 +103,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sw = smem + (size_t)stage * stage_bytes + p.LX * x_tile;
+                uint8_t* sw = smem + (size_t)stage * stage_bytes + LXT * x_tile;
                 mbar_expect_tx(&full_bar[stage], (uint32_t)(p.LW * w_tile));
                 for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -108,15 +118,17 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         uint32_t phase = 0;
         unsigned long long units = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+            if (PAIR) mbar_wait_cluster(&full_bar[stage], phase);
+            else mbar_wait(&full_bar[stage], phase);
+            if (PAIR) fence_proxy_async_all();  // the peer's generic-proxy stores, acquired above -> async proxy
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 uint32_t mk = 0;
 #pragma unroll
-                for (int w = 0; w < CONV_WARPS; ++w) mk |= (uint32_t)nzflag[stage * CONV_WARPS + w];
+                for (int w = 0; w < NCONV; ++w) mk |= (uint32_t)nzflag[stage * NCONV + w];
                 const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
-                const uint32_t sw_off = sx_off + ((uint32_t)(p.LX * x_tile) >> 4);
-                for (int j = 0; j < p.LX; ++j) {
+                const uint32_t sw_off = sx_off + ((uint32_t)(LXT * x_tile) >> 4);
+                for (int j = 0; j < LXT; ++j) {
                     if (!((mk >> j) & 1u)) continue;
                     const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
                     for (int i0 = 0; i0 < p.LW; i0 += G) {
@@ -130,7 +142,8 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                         units += (unsigned long long)g;
                     }
                 }
-                mma_commit(&empty_bar[stage]);
+                if (PAIR) mma_commit_mc(&empty_bar[stage], (uint16_t)3);
+                else mma_commit(&empty_bar[stage]);
                 if (kb == num_kb - 1) mma_commit(tmem_full);
             }
             __syncwarp();
@@ -139,56 +152,79 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         if (lane == 0 && p.mma_units && units)
             atomicAdd(p.mma_units, units * (2ull * TILE_M * BLOCK_K) * (unsigned long long)p.nt);
     } else {
-        // ===== converters (warps 0..7): int32 sigma -> digit planes in shared memory; then the epilogue =====
-        const bool do_norm = p.norm2 != nullptr && tile_n == 0;
-        unsigned long long acc[ROWS_PER_WARP];
+        // ===== converters (warps 0..15): int32 sigma -> digit planes in shared memory; then the epilogue =====
+        // A register buffer holds 8 row segments of 128 values (4 per lane): 8 rows of one k block, or (PAIR) 4 rows of
+        // two consecutive k blocks -- the same 64 KB of loads in flight per SM either way.
+        constexpr int R = PAIR ? 4 : 8;  // rows per warp per k block
+        constexpr int U = 8 / R;         // k blocks per register buffer
+        const int rb = (int)crank * (TILE_M / 2) * (PAIR ? 1 : 0) + warp * R;  // first row (within the tile) of this warp
+        const bool do_norm = p.norm2 != nullptr && (PAIR || tile_n == 0);
+        unsigned long long acc[R];
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_WARP; ++i) acc[i] = 0;
-        const int32_t* xrow = p.x + ((long)m0 + warp * ROWS_PER_WARP) * p.ldx + lane * 4;
-        const int rows_here = max(0, min(ROWS_PER_WARP, p.B - (m0 + warp * ROWS_PER_WARP)));
+        for (int i = 0; i < R; ++i) acc[i] = 0;
+        const int32_t* xrow = p.x + ((long)m0 + rb) * p.ldx + lane * 4;
+        const int rows_here = max(0, min(R, p.B - (m0 + rb)));
         // fast path: all rows of this warp exist and are 16-byte aligned -> unpredicated 128-bit loads
-        const bool fast_rows = p.vec && rows_here == ROWS_PER_WARP;
+        const bool fast_rows = p.vec && rows_here == R;
         const long ldx4 = p.ldx >> 2;  // row stride in int4 units (fast path only)
-        auto load_rows = [&](int4 (&dst)[ROWS_PER_WARP], int kb) {
-            if (fast_rows && (kb + 1) * BLOCK_K <= p.K) {
-                const int4* src = reinterpret_cast<const int4*>(xrow) + kb * (BLOCK_K / 4);
+        auto load_buf = [&](int4 (&dst)[8], int kb0) {
 #pragma unroll
-                for (int i = 0; i < ROWS_PER_WARP; ++i) dst[i] = src[i * ldx4];
-                return;
-            }
-            const int col = kb * BLOCK_K + lane * 4;
-#pragma unroll 1
-            for (int i = 0; i < ROWS_PER_WARP; ++i) {
-                int4 v = make_int4(0, 0, 0, 0);
-                if (i < rows_here && kb < num_kb) {
-                    const int32_t* src = xrow + (long)i * p.ldx + kb * BLOCK_K;
-                    if (col + 0 < p.K) v.x = src[0];
-                    if (col + 1 < p.K) v.y = src[1];
-                    if (col + 2 < p.K) v.z = src[2];
-                    if (col + 3 < p.K) v.w = src[3];
+            for (int u = 0; u < U; ++u) {
+                const int kb = kb0 + u;
+                if (fast_rows && (kb + 1) * BLOCK_K <= p.K) {
+                    const int4* src = reinterpret_cast<const int4*>(xrow) + kb * (BLOCK_K / 4);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) dst[u * R + i] = src[i * ldx4];
+                    continue;
                 }
+                const int col = kb * BLOCK_K + lane * 4;
+#pragma unroll 1
+                for (int i = 0; i < R; ++i) {
+                    int4 v = make_int4(0, 0, 0, 0);
+                    if (i < rows_here && kb < num_kb) {
+                        const int32_t* src = xrow + (long)i * p.ldx + kb * BLOCK_K;
+                        if (col + 0 < p.K) v.x = src[0];
+                        if (col + 1 < p.K) v.y = src[1];
+                        if (col + 2 < p.K) v.z = src[2];
+                        if (col + 3 < p.K) v.w = src[3];
+                    }
 #pragma unroll
-                for (int j = 0; j < ROWS_PER_WARP; ++j)
-                    if (j == i) dst[j] = v;  // static register indices
+                    for (int j = 0; j < R; ++j)
+                        if (j == i) dst[u * R + j] = v;  // static register indices
+                }
             }
         };
-        // shared-memory byte offset of this lane's 4 digits in row (warp * R + i): SWIZZLE_128B puts 16-byte chunk c
-        // of row r at chunk c ^ (r & 7); warp * R is a multiple of 8, so r & 7 = i & 7
-        const uint32_t lane_off = (uint32_t)(warp * ROWS_PER_WARP * 128 + (lane & 3) * 4);
-        const uint32_t chunk = (uint32_t)(lane >> 2);
+        // Shared-memory address of this lane's 4 digits in row r = rb + i: SWIZZLE_128B puts 16-byte chunk c of row r at
+        // chunk c ^ (r & 7), and r & 7 = (rb & 7) ^ i (rb is a multiple of R, i < R).  All addresses are 32-bit
+        // shared-window addresses and the stores are st.shared (a generic store costs a 64-bit address computation per
+        // row): row i of stage s sits at ((stage base + warp_base) ^ (i << 4)) + 128 i, the stage bases being
+        // 1024-byte aligned and warp_base carrying the lane's chunk in bits 2..6.
+        const uint32_t lane_const = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t warp_base = smem_base + (uint32_t)(rb * 128) + (lane_const ^ (uint32_t)((rb & 7) << 4));
+        const uint32_t nz_base = smem_u32((const void*)nzflag) + (uint32_t)(crank * CONV_WARPS) * (PAIR ? 1u : 0u) + (uint32_t)warp;
+        // the peer CTA's window: same offsets, shifted by a constant
+        const uint32_t peer_delta = PAIR ? mapa_shared(smem_base, crank ^ 1u) - smem_base : 0u;
         int stage = 0;
         uint32_t phase = 0;
-        auto convert_rows = [&](const int4 (&src)[ROWS_PER_WARP]) {
+        auto convert_unit = [&](const int4 (&buf)[8], const int u) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sx = smem + (size_t)stage * stage_bytes + lane_off;
-            uint32_t nz0 = 0, nz1 = 0, nz2 = 0, nz3 = 0, ovf = 0;
+            const uint32_t sx = warp_base + (uint32_t)(stage * stage_bytes);
+            // plane 0 is never skipped (it is zero only for an all-zero block, which costs one MMA group)
+            uint32_t nz1 = 0, nz2 = 0, nz3 = 0, ovf = 0;
+            if (do_norm) {  // one uniform branch: the n tiles that do not own the norms issue none of these
 #pragma unroll
-            for (int i = 0; i < ROWS_PER_WARP; ++i) {
-                const int w0 = src[i].x, w1 = src[i].y, w2 = src[i].z, w3 = src[i].w;
-                if (do_norm)
+                for (int i = 0; i < R; ++i) {
+                    const int w0 = buf[u * R + i].x, w1 = buf[u * R + i].y, w2 = buf[u * R + i].z, w3 = buf[u * R + i].w;
                     acc[i] += (unsigned long long)((long long)w0 * w0) + (unsigned long long)((long long)w1 * w1) +
                               (unsigned long long)((long long)w2 * w2) + (unsigned long long)((long long)w3 * w3);
-                uint8_t* dst = sx + i * 128 + ((chunk ^ (uint32_t)(i & 7)) << 4);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int w0 = buf[u * R + i].x, w1 = buf[u * R + i].y, w2 = buf[u * R + i].z, w3 = buf[u * R + i].w;
+                const uint32_t dst = (sx ^ (uint32_t)(i << 4)) + (uint32_t)(i * 128);
+                const uint32_t rdst = dst + peer_delta;
                 // Balanced digits d_l of v: v_0 = v, d_l = low byte of v_l (as s8), v_{l+1} = (v_l + 128) >> 8.
                 // With t = v + 0x8080 (0x808080 for four digits): d_0 = byte0(t) ^ 0x80, d_1 = byte1(t) ^ 0x80,
                 // d_2 = byte2(t) [^ 0x80 when a fourth digit follows], d_3 = byte3(t): one add per value, the 4 x 4
@@ -197,61 +233,78 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                 constexpr int BIAS = LB == 1 ? 0 : LB == 2 ? 0x80 : LB == 3 ? 0x8080 : 0x808080;
                 const uint32_t t0 = (uint32_t)(w0 + BIAS), t1 = (uint32_t)(w1 + BIAS), t2 = (uint32_t)(w2 + BIAS),
                                t3 = (uint32_t)(w3 + BIAS);
-                if (CHECK) ovf |= (t0 | t1) | (t2 | t3);
+                if (CHECK) ovf = (ovf | t0 | t1) | (t2 | t3);
                 const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140);  // b0 b0' b1 b1'
                 {
                     const uint32_t pk = __byte_perm(lo01, lo23, 0x5410) ^ (LB > 1 ? 0x80808080u : 0u);
-                    *reinterpret_cast<uint32_t*>(dst) = pk;
-                    nz0 |= pk;
+                    sts32(dst, pk);
+                    if (PAIR) stc32(rdst, pk);
                 }
                 if (LXT > 1) {
                     const uint32_t pk = __byte_perm(lo01, lo23, 0x7632) ^ (LB > 2 ? 0x80808080u : 0u);
-                    *reinterpret_cast<uint32_t*>(dst + x_tile) = pk;
+                    sts32(dst + (uint32_t)x_tile, pk);
+                    if (PAIR) stc32(rdst + (uint32_t)x_tile, pk);
                     nz1 |= pk;
                 }
                 if (LXT > 2) {
                     const uint32_t hi01 = __byte_perm(t0, t1, 0x7362), hi23 = __byte_perm(t2, t3, 0x7362);  // b2 b2' b3 b3'
                     const uint32_t pk = __byte_perm(hi01, hi23, 0x5410) ^ (LB > 3 ? 0x80808080u : 0u);
-                    *reinterpret_cast<uint32_t*>(dst + 2 * x_tile) = pk;
+                    sts32(dst + (uint32_t)(2 * x_tile), pk);
+                    if (PAIR) stc32(rdst + (uint32_t)(2 * x_tile), pk);
                     nz2 |= pk;
                     if (LXT > 3) {
                         const uint32_t pk3 = __byte_perm(hi01, hi23, 0x7632);
-                        *reinterpret_cast<uint32_t*>(dst + 3 * x_tile) = pk3;
+                        sts32(dst + (uint32_t)(3 * x_tile), pk3);
+                        if (PAIR) stc32(rdst + (uint32_t)(3 * x_tile), pk3);
                         nz3 |= pk3;
                     }
                 }
             }
-            uint32_t nzm = (nz0 ? 1u : 0u) | (nz1 ? 2u : 0u) | (nz2 ? 4u : 0u) | (nz3 ? 8u : 0u);
+            uint32_t nzm = 1u | (nz1 ? 2u : 0u) | (nz2 ? 4u : 0u) | (nz3 ? 8u : 0u);
             if (CHECK && (ovf >> (8 * LXT)) != 0u) nzm |= 0x80u;  // a digit beyond LXT is non-zero
             nzm = __reduce_or_sync(0xffffffffu, nzm);
             if (CHECK && (nzm & 0x80u) && lane == 0) atomicOr(p.overflow, 1);
-            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            // generic-proxy stores -> visible to the tensor cores' async-proxy reads (of both CTAs when paired)
+            if (PAIR) fence_proxy_async_all();
+            else fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                nzflag[stage * CONV_WARPS + warp] = (uint8_t)nzm;
-                mbar_arrive(&full_bar[stage]);
+                const uint32_t nza = nz_base + (uint32_t)(stage * NCONV);
+                sts8(nza, nzm);
+                if (PAIR) {
+                    stc8(nza + peer_delta, nzm);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_arrive_cluster(fb);               // release at cluster scope, local barrier
+                    mbar_arrive_cluster(fb + peer_delta);  // and the peer's
+                } else {
+                    mbar_arrive(&full_bar[stage]);
+                }
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         };
-        // two register buffers, the k loop unrolled by two: the 16 row loads of the next k block are in flight while
-        // the current block is converted, without register moves between the buffers
-        int4 buf_a[ROWS_PER_WARP], buf_b[ROWS_PER_WARP];
-        load_rows(buf_a, 0);
-        for (int kb = 0; kb < num_kb; kb += 2) {
-            load_rows(buf_b, kb + 1);
-            convert_rows(buf_a);
-            if (kb + 1 < num_kb) {
-                load_rows(buf_a, kb + 2);
-                convert_rows(buf_b);
+        // two register buffers, the k loop unrolled by two buffers: the 8 row-segment loads of the next buffer are in
+        // flight while the current one is converted, without register moves between the buffers
+        int4 buf_a[8], buf_b[8];
+        load_buf(buf_a, 0);
+        for (int kb = 0; kb < num_kb; kb += 2 * U) {
+            load_buf(buf_b, kb + U);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (kb + u < num_kb) convert_unit(buf_a, u);
+            if (kb + U < num_kb) {
+                load_buf(buf_a, kb + 2 * U);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (kb + U + u < num_kb) convert_unit(buf_b, u);
             }
         }
         if (do_norm) {
 #pragma unroll
-            for (int i = 0; i < ROWS_PER_WARP; ++i) {
+            for (int i = 0; i < R; ++i) {
                 unsigned long long a = acc[i];
 #pragma unroll
                 for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                const long grow = (long)m0 + warp * ROWS_PER_WARP + i;
+                const long grow = (long)m0 + rb + i;
                 if (lane == 0 && grow < p.B) p.norm2[grow] = a;
             }
         }
@@ -295,6 +348,8 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+    // no CTA of a pair may exit while the peer can still store to its shared memory or arrive on its barriers
+    if (PAIR) cluster_sync_all();
 }
 
 }  // namespace
@@ -305,6 +360,13 @@ static int fused_tile_n(int LX, int LW, int N) {
     if (nt_max < 16) return nt_max;
     const int tiles = (N + nt_max - 1) / nt_max;
     return std::min(nt_max, ((N + tiles - 1) / tiles + 15) / 16 * 16);
+}
+
+template <bool PAIR>
+static void (*pick_kernel(int LX, bool check))(const CUtensorMap, FusedParams) {
+    if (check) return LX == 1 ? f_a_fused_kernel<1, true, PAIR> : LX == 2 ? f_a_fused_kernel<2, true, PAIR> : f_a_fused_kernel<3, true, PAIR>;
+    return LX == 1 ? f_a_fused_kernel<1, false, PAIR> : LX == 2 ? f_a_fused_kernel<2, false, PAIR>
+         : LX == 3 ? f_a_fused_kernel<3, false, PAIR> : f_a_fused_kernel<4, false, PAIR>;
 }
 
 static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const int* run_if, cudaStream_t stream) {
@@ -318,26 +380,37 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     p.n_tiles = (a.N + nt - 1) / nt;
     const int m_tiles = (a.B + tc05::TILE_M - 1) / tc05::TILE_M;
     const int stage_bytes = LX * tc05::TILE_M * tc05::BLOCK_K + a.LW * nt * tc05::BLOCK_K;
-    const int budget = 227 * 1024 - 1024 - 256;
+    const int budget = 227 * 1024 - 1024 - 512;
     int stages = budget / stage_bytes;
     if (stages < 2) return cudaErrorInvalidValue;
     if (stages > 6) stages = 6;
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + 1024 + 512;
     CUtensorMap mw;
     if (!tc05::make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
-    void (*kern)(const CUtensorMap, FusedParams) = nullptr;
-    if (check) kern = LX == 1 ? f_a_fused_kernel<1, true> : LX == 2 ? f_a_fused_kernel<2, true> : f_a_fused_kernel<3, true>;
-    else kern = LX == 1 ? f_a_fused_kernel<1, false> : LX == 2 ? f_a_fused_kernel<2, false>
-              : LX == 3 ? f_a_fused_kernel<3, false> : f_a_fused_kernel<4, false>;
-    static int configured[2][MAX_LX + 1] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
-    if (smem > configured[check ? 1 : 0][LX]) {
+    // CTA pairs (clusters of 2 along the coordinate tiles) whenever the tiles pair up; QF_FA_PAIR=0 keeps single CTAs
+    const char* pair_env = getenv("QF_FA_PAIR");
+    const bool pair = !(pair_env && pair_env[0] == '0') && (p.n_tiles % 2 == 0);
+    void (*kern)(const CUtensorMap, FusedParams) = pair ? pick_kernel<true>(LX, check) : pick_kernel<false>(LX, check);
+    static int configured[2][2][MAX_LX + 1] = {};
+    if (smem > configured[pair ? 1 : 0][check ? 1 : 0][LX]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured[check ? 1 : 0][LX] = smem;
+        configured[pair ? 1 : 0][check ? 1 : 0][LX] = smem;
     }
-    kern<<<dim3((unsigned)(m_tiles * p.n_tiles)), FUSED_THREADS, smem, stream>>>(mw, p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(m_tiles * p.n_tiles));
+    cfg.blockDim = dim3(FUSED_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mw, p);
 }
 
 // LX is the digit count that covers every in-domain value, LX_typical the count that covers what the samplers
