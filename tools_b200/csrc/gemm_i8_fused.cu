@@ -44,7 +44,8 @@ struct FusedParams {
 // converts only HALF of the 128 sigma rows and stores the digits into its own operand tile and, through distributed
 // shared memory (st.shared::cluster), into the peer's: every sigma block is read from L2 and converted once per
 // cluster instead of once per CTA (the unpaired kernel is bound by exactly that: converter issue slots and bytes in
-// flight).  A stage is full when the 16 local and the 16 remote converter warps have arrived, and free again when
+// flight).  A stage is full when the 16 local converter warps have arrived and the peer's bytes have landed
+// (st.async completes the transaction count of the stage's barrier), and free again when
 // BOTH tensor cores have retired their MMAs on it (tcgen05.commit multicast onto both CTAs' empty barriers).
 template <int LXT, bool CHECK, bool PAIR>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
@@ -61,7 +62,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 1);
-    volatile uint8_t* nzflag = (volatile uint8_t*)(tmem_slot + 2);  // [stage][converter warp]: non-zero plane mask
+    volatile uint32_t* nzflag = (volatile uint32_t*)(tmem_slot + 2);  // [stage][converter warp]: non-zero plane mask
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -72,7 +73,9 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1 + NCONV);      // TMA expect_tx arrival + one arrival per converter warp
+            // TMA expect_tx arrival + one arrival per LOCAL converter warp; the peer's half of a stage (and its plane
+            // masks) is accounted in bytes: st.async completes the transaction count that the TMA warp expects
+            mbar_init(&full_bar[s], 1 + CONV_WARPS);
             mbar_init(&empty_bar[s], PAIR ? 2 : 1);  // tcgen05.commit (of both CTAs of a pair)
         }
         mbar_init(tmem_full, 1);
@@ -104,7 +107,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sw = smem + (size_t)stage * stage_bytes + LXT * x_tile;
-                mbar_expect_tx(&full_bar[stage], (uint32_t)(p.LW * w_tile));
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(p.LW * w_tile) + (PAIR ? (uint32_t)(LXT * (x_tile / 2) + CONV_WARPS * 4) : 0u));
                 for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BLOCK_K, n0, i);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -120,12 +123,16 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         for (int kb = 0; kb < num_kb; ++kb) {
             if (PAIR) mbar_wait_cluster(&full_bar[stage], phase);
             else mbar_wait(&full_bar[stage], phase);
-            if (PAIR) fence_proxy_async_all();  // the peer's generic-proxy stores, acquired above -> async proxy
+            // The converters' generic-proxy stores (acquired through the barrier above) -> the tensor core's async-proxy
+            // reads.  The cross-proxy fence sits HERE, on the consumer side of the release/acquire chain, once per k
+            // block: in the converter warps it lowers to MEMBAR.ALL.CTA, which also waits for their prefetched global
+            // loads of the NEXT k block, i.e. it serialised every k block on a full DRAM round trip.
+            fence_proxy_async_smem();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 uint32_t mk = 0;
 #pragma unroll
-                for (int w = 0; w < NCONV; ++w) mk |= (uint32_t)nzflag[stage * NCONV + w];
+                for (int w = 0; w < NCONV; ++w) mk |= nzflag[stage * NCONV + w];
                 const uint32_t sx_off = (uint32_t)(stage * stage_bytes) >> 4;
                 const uint32_t sw_off = sx_off + ((uint32_t)(LXT * x_tile) >> 4);
                 for (int j = 0; j < LXT; ++j) {
@@ -202,7 +209,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         const uint32_t lane_const = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t warp_base = smem_base + (uint32_t)(rb * 128) + (lane_const ^ (uint32_t)((rb & 7) << 4));
-        const uint32_t nz_base = smem_u32((const void*)nzflag) + (uint32_t)(crank * CONV_WARPS) * (PAIR ? 1u : 0u) + (uint32_t)warp;
+        const uint32_t nz_base = smem_u32((const void*)nzflag) + 4u * ((uint32_t)(crank * CONV_WARPS) * (PAIR ? 1u : 0u) + (uint32_t)warp);
         // the peer CTA's window: same offsets, shifted by a constant
         const uint32_t peer_delta = PAIR ? mapa_shared(smem_base, crank ^ 1u) - smem_base : 0u;
         int stage = 0;
@@ -210,6 +217,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         auto convert_unit = [&](const int4 (&buf)[8], const int u) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             const uint32_t sx = warp_base + (uint32_t)(stage * stage_bytes);
+            const uint32_t rbar = smem_u32(&full_bar[stage]) + peer_delta;  // the peer's full barrier of this stage
             // plane 0 is never skipped (it is zero only for an all-zero block, which costs one MMA group)
             uint32_t nz1 = 0, nz2 = 0, nz3 = 0, ovf = 0;
             if (do_norm) {  // one uniform branch: the n tiles that do not own the norms issue none of these
@@ -224,7 +232,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
             for (int i = 0; i < R; ++i) {
                 const int w0 = buf[u * R + i].x, w1 = buf[u * R + i].y, w2 = buf[u * R + i].z, w3 = buf[u * R + i].w;
                 const uint32_t dst = (sx ^ (uint32_t)(i << 4)) + (uint32_t)(i * 128);
-                const uint32_t rdst = dst + peer_delta;
+                const uint32_t rdst = dst + peer_delta;  // same offset in the peer's window
                 // Balanced digits d_l of v: v_0 = v, d_l = low byte of v_l (as s8), v_{l+1} = (v_l + 128) >> 8.
                 // With t = v + 0x8080 (0x808080 for four digits): d_0 = byte0(t) ^ 0x80, d_1 = byte1(t) ^ 0x80,
                 // d_2 = byte2(t) [^ 0x80 when a fourth digit follows], d_3 = byte3(t): one add per value, the 4 x 4
@@ -238,24 +246,24 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                 {
                     const uint32_t pk = __byte_perm(lo01, lo23, 0x5410) ^ (LB > 1 ? 0x80808080u : 0u);
                     sts32(dst, pk);
-                    if (PAIR) stc32(rdst, pk);
+                    if (PAIR) st_async32(rdst, pk, rbar);
                 }
                 if (LXT > 1) {
                     const uint32_t pk = __byte_perm(lo01, lo23, 0x7632) ^ (LB > 2 ? 0x80808080u : 0u);
                     sts32(dst + (uint32_t)x_tile, pk);
-                    if (PAIR) stc32(rdst + (uint32_t)x_tile, pk);
+                    if (PAIR) st_async32(rdst + (uint32_t)x_tile, pk, rbar);
                     nz1 |= pk;
                 }
                 if (LXT > 2) {
                     const uint32_t hi01 = __byte_perm(t0, t1, 0x7362), hi23 = __byte_perm(t2, t3, 0x7362);  // b2 b2' b3 b3'
                     const uint32_t pk = __byte_perm(hi01, hi23, 0x5410) ^ (LB > 3 ? 0x80808080u : 0u);
                     sts32(dst + (uint32_t)(2 * x_tile), pk);
-                    if (PAIR) stc32(rdst + (uint32_t)(2 * x_tile), pk);
+                    if (PAIR) st_async32(rdst + (uint32_t)(2 * x_tile), pk, rbar);
                     nz2 |= pk;
                     if (LXT > 3) {
                         const uint32_t pk3 = __byte_perm(hi01, hi23, 0x7632);
                         sts32(dst + (uint32_t)(3 * x_tile), pk3);
-                        if (PAIR) stc32(rdst + (uint32_t)(3 * x_tile), pk3);
+                        if (PAIR) st_async32(rdst + (uint32_t)(3 * x_tile), pk3, rbar);
                         nz3 |= pk3;
                     }
                 }
@@ -264,21 +272,12 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
             if (CHECK && (ovf >> (8 * LXT)) != 0u) nzm |= 0x80u;  // a digit beyond LXT is non-zero
             nzm = __reduce_or_sync(0xffffffffu, nzm);
             if (CHECK && (nzm & 0x80u) && lane == 0) atomicOr(p.overflow, 1);
-            // generic-proxy stores -> visible to the tensor cores' async-proxy reads (of both CTAs when paired)
-            if (PAIR) fence_proxy_async_all();
-            else fence_proxy_async_smem();
-            __syncwarp();
+            __syncwarp();  // (the cross-proxy fence is issued by the MMA warp after it has acquired the stage)
             if (lane == 0) {
-                const uint32_t nza = nz_base + (uint32_t)(stage * NCONV);
-                sts8(nza, nzm);
-                if (PAIR) {
-                    stc8(nza + peer_delta, nzm);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    mbar_arrive_cluster(fb);               // release at cluster scope, local barrier
-                    mbar_arrive_cluster(fb + peer_delta);  // and the peer's
-                } else {
-                    mbar_arrive(&full_bar[stage]);
-                }
+                const uint32_t nza = nz_base + (uint32_t)(stage * NCONV * 4);
+                sts32(nza, nzm);
+                if (PAIR) st_async32(nza + peer_delta, nzm, rbar);
+                mbar_arrive(&full_bar[stage]);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         };
@@ -380,12 +379,12 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     p.n_tiles = (a.N + nt - 1) / nt;
     const int m_tiles = (a.B + tc05::TILE_M - 1) / tc05::TILE_M;
     const int stage_bytes = LX * tc05::TILE_M * tc05::BLOCK_K + a.LW * nt * tc05::BLOCK_K;
-    const int budget = 227 * 1024 - 1024 - 512;
+    const int budget = 227 * 1024 - 1024 - 1024;  // alignment slack, barriers + plane masks
     int stages = budget / stage_bytes;
     if (stages < 2) return cudaErrorInvalidValue;
     if (stages > 6) stages = 6;
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 512;
+    const int smem = stages * stage_bytes + 1024 + 1024;
     CUtensorMap mw;
     if (!tc05::make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
     // CTA pairs (clusters of 2 along the coordinate tiles) whenever the tiles pair up; QF_FA_PAIR=0 keeps single CTAs

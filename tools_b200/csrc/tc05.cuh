@@ -112,14 +112,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void stc32(uint32_t cluster_addr, uint32_t v) {
-    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v));
-}
-__device__ __forceinline__ void stc8(uint32_t cluster_addr, uint32_t v) {
-    asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Asynchronous store into the peer CTA's shared memory that completes 4 bytes of the transaction count of the peer's
+// mbarrier when it lands: the data needs no release fence on the writer side (a cluster-scope release lowers to
+// MEMBAR.ALL.GPU, which would also wait for every prefetched global load of the warp).
+__device__ __forceinline__ void st_async32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(cluster_addr), "r"(v), "r"(cluster_bar));
 }
 // wait that also acquires writes made by the peer CTA of the cluster
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
