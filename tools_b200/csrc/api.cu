@@ -391,7 +391,23 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
             CK(cudaEventRecord(rec.a, ctx->stream));
             g.mma_units = ctx->dMma.p ? ctx->dMma.as<unsigned long long>() : nullptr;
         }
+        static const bool trace = getenv("QF_TRACE") && getenv("QF_TRACE")[0] == '1';
+        Dev cnt;
+        if (trace) {  // diagnostics only (synchronises): where the CTAs of the fused kernel spend their cycles
+            CK(cnt.ensure(48));
+            CK(cudaMemsetAsync(cnt.p, 0, 48, ctx->stream));
+            g.tim = cnt.as<unsigned long long>();
+        }
         LAUNCH(qf_launch_f_a_fused(g, ctx->stream));
+        if (trace) {
+            unsigned long long hh[6];
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaMemcpy(hh, cnt.p, 48, cudaMemcpyDeviceToHost));
+            const double ctas = (double)((Bc + 127) / 128) * ((ctx->n + 127) / 128), kbs = (double)((ctx->m + 127) / 128);
+            fprintf(stderr, "[f_a fused] B=%d: per CTA kclk: whole %.1f  mma loop %.1f (waiting for operands %.1f)  converter loop %.1f "
+                    "(waiting for free stages %.1f)  epilogue %.1f   per k block: %.0f clk\n", Bc, hh[5] / ctas / 1e3, hh[1] / ctas / 1e3,
+                    hh[0] / ctas / 1e3, hh[3] / ctas / 1e3, hh[2] / ctas / 1e3, hh[4] / ctas / 1e3, hh[1] / ctas / kbs);
+        }
         if (ctx->prof) {
             CK(cudaEventRecord(rec.b, ctx->stream));
             ctx->prof_recs.push_back(rec);
@@ -597,7 +613,14 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
 // GPV / ring samp_p on one chunk: GPV08 SampleD in GSO coordinates (gpv.rs:152-161,
 // gpv_ring.rs:160-212)
 // ---------------------------------------------------------------------------
-constexpr long NP_SIZES[3] = {64, 256, 1024};
+// Block sizes of the recursion: 64-wide diagonal blocks are sequential per target (np_diag); the updates between 64- and
+// 256-blocks run on the fp64 tensor pipe (gemm_f64), the updates between 1024-blocks inside a 4096-block and between
+// 4096-blocks on tcgen05 (fixed-point digits).  The top level contracts K = 4096 coordinates per launch: its epilogue
+// (a read-modify-write of T, serialised with the MMAs because TMEM holds one tile) is paid once per 4096 instead of
+// once per 1024 coordinates.
+constexpr long NP_SIZES[4] = {64, 256, 1024, 4096};
+constexpr int NP_TOP = 4;
+constexpr long NP_SCALE_BLOCK = NP_SIZES[3];  // column block over which the digits of U share one scale per row
 
 // Process coordinates [lo, hi) in descending order.  Precondition: T[:, lo:hi] already carries the
 // updates of every coordinate >= hi.  level 0 = one sequential diagonal block.
@@ -622,15 +645,16 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                                         seed, first, ctx->stream));
         }
         QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, seed, first));
-        if (level == 3 && ctx->use_ozaki) {
-            // digits of the finished block of z (kept: the final S z reuses them), then the update of all rows
-            // above it on the tensor cores:  T[:, 0:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
+        if (level >= 3 && ctx->use_ozaki) {
             const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
             int8_t* zp = ctx->w[8].as<int8_t>();
-            LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
-                                             ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
-                                             ctx->stream));
+            if (level == 3)  // digits of the finished 1024-block of z (kept: the level above and the final S z reuse them)
+                LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
+                                                 ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
+                                                 ctx->stream));
+            // the update of the rows above it (within the enclosing block) on the tensor cores:
+            //   T[:, lo:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
             if (sub_lo > lo && sub_hi - sub_lo < 512) {
                 // a thin block (the ragged last one): per-tile overheads dominate the tensor-core path, use fp64
                 LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
@@ -638,12 +662,12 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             } else if (sub_lo > lo) {
                 I8GemmArgs g{};
                 g.x = zp + sub_lo; g.ldx = ldk; g.x_plane = plane;
-                g.w = ctx->dUl.as<int8_t>() + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;
+                g.w = ctx->dUl.as<int8_t>() + lo * ldk + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;
                 g.LX = ctx->z_limbs; g.LW = ctx->u_limbs; g.w_signed = 1;
-                g.B = Bc; g.N = (int)sub_lo; g.K = (int)(sub_hi - sub_lo);
-                g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = T; g.ldout = ldD;
+                g.B = Bc; g.N = (int)(sub_lo - lo); g.K = (int)(sub_hi - sub_lo);
+                g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = T + lo; g.ldout = ldD;
                 g.flag = ctx->dFlag.as<int>();
-                g.scale = ctx->dUscale.as<double>() + (sub_lo / NP_SIZES[2]) * D;
+                g.scale = ctx->dUscale.as<double>() + (sub_lo / NP_SCALE_BLOCK) * D + lo;
                 g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb;
                 g.nz_kb_off = (int)(sub_lo / 128); g.nz_m_off = 0;
                 LAUNCH(ctx_gemm_i8(ctx, g));
@@ -697,7 +721,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(ctx->dNz.ensure(nzb));
         CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
     }
-    QF_TRY(np_block(ctx, T, Z, Bc, 0, D, 3, seed, first));
+    QF_TRY(np_block(ctx, T, Z, Bc, 0, D, NP_TOP, seed, first));
     // e = sol + S z   (exact integers)
     if (ctx->use_i8) {
         // z -> balanced base-256 digits, S z on the tensor cores, then add sol on its pivot columns
@@ -1540,11 +1564,11 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
         const long min_dim = envmin ? atol(envmin) : 2 * NP_SIZES[2];
         ctx->use_ozaki = D > std::max(min_dim, NP_SIZES[2]) && ctx->z_limbs + ctx->u_limbs - 1 <= 16 && !(env && env[0] == '1');
         if (ctx->use_ozaki) {
-            const long nblk = (D + NP_SIZES[2] - 1) / NP_SIZES[2];
+            const long nblk = (D + NP_SCALE_BLOCK - 1) / NP_SCALE_BLOCK;
             CK(ctx->dUscale.ensure((size_t)nblk * D * 8));
             CK(ctx->dUl.ensure((size_t)ctx->u_limbs * D * ctx->ldk_dim));
             CK(cudaMemsetAsync(ctx->dUl.p, 0, (size_t)ctx->u_limbs * D * ctx->ldk_dim, ctx->stream));
-            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], ctx->u_limbs,
+            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], (int)NP_SCALE_BLOCK, ctx->u_limbs,
                                            ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
                                            ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));

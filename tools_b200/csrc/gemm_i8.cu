@@ -13,8 +13,8 @@
 // (mp_perturbation.rs:318,335), e = sol + S z (gpv.rs:160) and TrapGen's A_bar R
 // (gadget_classical.rs:66).
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 epilogue (tcgen05.ld 32x32b, one TMEM lane = one target row per thread).
+// CTA = 10 warps: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 epilogue (tcgen05.ld 32x32b, one TMEM lane = one target row per thread, two warps per lane group).
 // Tile: 128 targets x NT coordinates x 128-byte K blocks, SWIZZLE_128B K-major operands,
 // multi-stage mbarrier pipeline.  K is long (m ~ 10^4) and the epilogue is < 3 % of a tile,
 // so one tile per CTA (no TMEM double buffering).
@@ -29,7 +29,8 @@
 namespace {
 
 using namespace tc05;
-constexpr int I8_THREADS = 192;
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane group, each draining half of the tile's columns
+constexpr int I8_THREADS = (2 + EPI_WARPS) * 32;
 
 struct I8Params {
     int B, N, K;
@@ -61,18 +62,18 @@ __device__ __forceinline__ double s32_to_f64(int32_t x) {
     return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
 }
 
-// Epilogue of one 128 x 32 tile of the scaled fp64 update out[b][n] = old - V * scale[n], V = sum_d 256^d D_d:
-// NDT accumulators of 32 columns each (NDT compile time: straight-line Horner, no predication), 4 columns per TMEM
-// trip, the old values `pre` already in registers.
+// Epilogue of one 128 x 16 half of a 32-column tile of the scaled fp64 update out[b][n] = old - V * scale[n],
+// V = sum_d 256^d D_d: NDT accumulators of 32 columns each (NDT compile time: straight-line Horner, no predication),
+// 4 columns per TMEM trip, the old values `pre` already in registers.  cb = first column of this warp's half.
 template <int NDT>
-__device__ __forceinline__ void epi_update32(uint32_t lane_addr, const double2 (&pre)[16], double* orow,
+__device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const double2 (&pre)[8], double* orow,
                                              const double* __restrict__ scale, int nd_rt = NDT) {
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 4) {
+    for (int c0 = 0; c0 < 16; c0 += 4) {
         int32_t t[NDT][4];
 #pragma unroll
         for (int d = 0; d < NDT; ++d)
-            if (d < nd_rt) tmem_ld4(lane_addr + (uint32_t)(d * 32 + c0), t[d]);
+            if (d < nd_rt) tmem_ld4(lane_addr + (uint32_t)(d * 32 + cb + c0), t[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         double r[4];
 #pragma unroll
@@ -83,10 +84,10 @@ __device__ __forceinline__ void epi_update32(uint32_t lane_addr, const double2 (
             for (int d = NDT - 1; d >= 0; --d)
                 if (d < nd_rt) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
             const double old = (c & 1) ? pre[(c0 + c) >> 1].y : pre[(c0 + c) >> 1].x;
-            r[c] = fma(-dv, scale[c0 + c], old);
+            r[c] = fma(-dv, scale[cb + c0 + c], old);
         }
-        *reinterpret_cast<double2*>(orow + c0) = make_double2(r[0], r[1]);
-        *reinterpret_cast<double2*>(orow + c0 + 2) = make_double2(r[2], r[3]);
+        *reinterpret_cast<double2*>(orow + cb + c0) = make_double2(r[0], r[1]);
+        *reinterpret_cast<double2*>(orow + cb + c0 + 2) = make_double2(r[2], r[3]);
     }
 }
 
@@ -94,8 +95,8 @@ __device__ __forceinline__ void epi_update32(uint32_t lane_addr, const double2 (
 // old values fetched before the accumulators are read.
 template <int NDT, int COLS>
 __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow, const double* __restrict__ scale, int n0,
-                                               int nt, int N, bool rv, int nd) {
-    for (int c0 = 0; c0 < nt; c0 += COLS) {
+                                               int nt, int N, bool rv, int nd, int cbeg, int cend) {
+    for (int c0 = cbeg; c0 < cend; c0 += COLS) {
         double told[COLS];
 #pragma unroll
         for (int c = 0; c < COLS; ++c) told[c] = (rv && n0 + c0 + c < N) ? orow[n0 + c0 + c] : 0.0;
@@ -164,7 +165,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
+        mbar_init(tmem_empty, EPI_WARPS);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // allocate all 512 TMEM columns (one CTA per SM)
@@ -180,7 +181,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // accumulators zeroed by the epilogue of the previous tile.
     if (warp >= 2) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
+        for (int c = ((warp - 2) >> 2) * 16; c < ND * p.nt; c += 16 * (EPI_WARPS / 4)) tmem_st16_zero(lane_addr + (uint32_t)c);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -270,8 +271,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0 && p.mma_units && units)
             atomicAdd(p.mma_units, units * (2ull * TILE_M * BK) * (unsigned long long)p.nt);  // int8 operations
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
-        const int lg = warp & 3;
+        // ===== epilogue: warps 2..9, TMEM lane group = warp % 4; the two warps of a lane group split the columns =====
+        const int lg = warp & 3, half = (warp - 2) >> 2;
+        // column range of this warp for tiles of any width: whole 16-column groups, the first half rounded up
+        const int cmid = ((p.nt / 16 + 1) / 2) * 16;
+        const int cbeg = half ? cmid : 0, cend = half ? p.nt : cmid;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
         long long te_wait = 0, te_body = 0;
         int it = 0;
@@ -286,11 +290,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // (warp-uniform: tcgen05.ld is .aligned, every lane of the warp must take the same path)
             const bool pre_ok = OK3 && p.nt == 32 && m0 + lg * 32 + 31 < p.B && n0 + 32 <= p.N && (p.ldout & 1) == 0 &&
                                 ((((uintptr_t)p.out) & 15) == 0);
-            double2 pre[16];
+            double2 pre[8];
             if (OK3 && pre_ok) {
-                const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0);
+                const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0 + half * 16);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pre[i] = src[i];
+                for (int i = 0; i < 8; ++i) pre[i] = src[i];
             }
             const long long te0_ = p.tim ? clock64() : 0;
             mbar_wait(tmem_full, (uint32_t)(it & 1));
@@ -299,17 +303,17 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (OK3 && pre_ok) {
                 double* orow = (double*)p.out + (long)row * p.ldout + n0;
-                if (ND == 11) epi_update32<11>(lane_addr, pre, orow, p.scale + n0);
-                else if (ND == 6) epi_update32<6>(lane_addr, pre, orow, p.scale + n0);
-                else epi_update32<16>(lane_addr, pre, orow, p.scale + n0, ND);
+                if (ND == 11) epi_update16<11>(lane_addr, half * 16, pre, orow, p.scale + n0);
+                else if (ND == 6) epi_update16<6>(lane_addr, half * 16, pre, orow, p.scale + n0);
+                else epi_update16<16>(lane_addr, half * 16, pre, orow, p.scale + n0, ND);
             } else if (OK3) {
                 // ragged / wider tiles
                 double* orow = (double*)p.out + (long)row * p.ldout;
-                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
-                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
-                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND);
+                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
+                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
+                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
             } else if (!OK3) {
-                for (int c0 = 0; c0 < p.nt; c0 += 16) {
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
                     __int128 v[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) v[c] = 0;
@@ -352,7 +356,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (p.tim) te_body += clock64() - te1_;
             // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
             if (tile + (int)gridDim.x < total_tiles) {
-                for (int c = 0; c < ND * p.nt; c += 16) tmem_st16_zero(lane_addr + (uint32_t)c);
+                for (int c = half * 16; c < ND * p.nt; c += 16 * (EPI_WARPS / 4)) tmem_st16_zero(lane_addr + (uint32_t)c);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();

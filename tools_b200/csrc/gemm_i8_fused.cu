@@ -36,6 +36,10 @@ struct FusedParams {
     unsigned long long* mma_units;
     int* overflow;        // optimistic launch (CHECK): set when some value needs one digit more than LXT
     const int* run_if;    // conditional launch: exit at once unless *run_if != 0
+    // optional diagnostics (QF_TRACE), cycles summed over CTAs: [0] MMA warp waiting for full stages, [1] MMA warp main
+    // loop, [2] converter warp 0 waiting for empty stages, [3] converter warp 0 main loop, [4] its epilogue,
+    // [5] whole CTA (warp 0, kernel entry to exit)
+    unsigned long long* tim;
 };
 
 // LXT digits of sigma are multiplied.  CHECK: the digits are those of the (LXT+1)-digit representation and the kernel
@@ -51,6 +55,7 @@ template <int LXT, bool CHECK, bool PAIR>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
     if (p.run_if != nullptr && *p.run_if == 0) return;
+    const long long t_entry = p.tim ? clock64() : 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int x_tile = TILE_M * BLOCK_K;
@@ -120,9 +125,13 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         int stage = 0;
         uint32_t phase = 0;
         unsigned long long units = 0;
+        long long tw_full = 0;
+        const long long t_loop = p.tim ? clock64() : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
+            const long long t0_ = p.tim ? clock64() : 0;
             if (PAIR) mbar_wait_cluster(&full_bar[stage], phase);
             else mbar_wait(&full_bar[stage], phase);
+            if (p.tim) tw_full += clock64() - t0_;
             // The converters' generic-proxy stores (acquired through the barrier above) -> the tensor core's async-proxy
             // reads.  The cross-proxy fence sits HERE, on the consumer side of the release/acquire chain, once per k
             // block: in the converter warps it lowers to MEMBAR.ALL.CTA, which also waits for their prefetched global
@@ -158,6 +167,10 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         }
         if (lane == 0 && p.mma_units && units)
             atomicAdd(p.mma_units, units * (2ull * TILE_M * BLOCK_K) * (unsigned long long)p.nt);
+        if (lane == 0 && p.tim) {
+            atomicAdd(p.tim + 0, (unsigned long long)tw_full);
+            atomicAdd(p.tim + 1, (unsigned long long)(clock64() - t_loop));
+        }
     } else {
         // ===== converters (warps 0..15): int32 sigma -> digit planes in shared memory; then the epilogue =====
         // A register buffer holds 8 row segments of 128 values (4 per lane): 8 rows of one k block, or (PAIR) 4 rows of
@@ -214,8 +227,12 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         const uint32_t peer_delta = PAIR ? mapa_shared(smem_base, crank ^ 1u) - smem_base : 0u;
         int stage = 0;
         uint32_t phase = 0;
+        long long tw_empty = 0;
+        const bool timed = p.tim != nullptr && warp == 0;
         auto convert_unit = [&](const int4 (&buf)[8], const int u) {
+            const long long t0_ = timed ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (timed) tw_empty += clock64() - t0_;
             const uint32_t sx = warp_base + (uint32_t)(stage * stage_bytes);
             const uint32_t rbar = smem_u32(&full_bar[stage]) + peer_delta;  // the peer's full barrier of this stage
             // plane 0 is never skipped (it is zero only for an all-zero block, which costs one MMA group)
@@ -284,6 +301,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         // two register buffers, the k loop unrolled by two buffers: the 8 row-segment loads of the next buffer are in
         // flight while the current one is converted, without register moves between the buffers
         int4 buf_a[8], buf_b[8];
+        const long long t_conv = timed ? clock64() : 0;
         load_buf(buf_a, 0);
         for (int kb = 0; kb < num_kb; kb += 2 * U) {
             load_buf(buf_b, kb + U);
@@ -306,6 +324,11 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                 const long grow = (long)m0 + rb + i;
                 if (lane == 0 && grow < p.B) p.norm2[grow] = a;
             }
+        }
+        const long long t_epi = timed ? clock64() : 0;
+        if (timed && lane == 0) {
+            atomicAdd(p.tim + 2, (unsigned long long)tw_empty);
+            atomicAdd(p.tim + 3, (unsigned long long)(t_epi - t_conv));
         }
         // ---- epilogue: V = sum_d 256^d D_d, reduce mod q ----
         const int lg = warp & 3;
@@ -341,6 +364,11 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (timed && lane == 0) {
+            const long long t_end = clock64();
+            atomicAdd(p.tim + 4, (unsigned long long)(t_end - t_epi));
+            atomicAdd(p.tim + 5, (unsigned long long)(t_end - t_entry));
+        }
     }
     __syncthreads();
     if (warp == CONV_WARPS + 1) {
@@ -375,7 +403,7 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     p.x = a.x; p.ldx = a.ldx; p.B = a.B; p.N = a.N; p.K = a.K; p.LX = LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
     p.vec = ((a.ldx & 3) == 0 && (((uintptr_t)a.x) & 15) == 0) ? 1 : 0;
     p.q = a.q; p.out = a.out; p.ldout = a.ldout; p.norm2 = a.norm2; p.mma_units = a.mma_units;
-    p.overflow = a.retry_flag; p.run_if = run_if;
+    p.overflow = a.retry_flag; p.run_if = run_if; p.tim = a.tim;
     p.n_tiles = (a.N + nt - 1) / nt;
     const int m_tiles = (a.B + tc05::TILE_M - 1) / tc05::TILE_M;
     const int stage_bytes = LX * tc05::TILE_M * tc05::BLOCK_K + a.LW * nt * tc05::BLOCK_K;

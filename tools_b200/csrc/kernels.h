@@ -176,6 +176,7 @@ struct FaFusedArgs {
     unsigned long long* norm2;
     unsigned long long* mma_units;
     int* retry_flag;   // optional device int: enables the optimistic (LX - 1 digits first) launch pair
+    unsigned long long* tim;  // optional diagnostics (QF_TRACE): 6 cycle counters summed over CTAs, see gemm_i8_fused.cu
 };
 cudaError_t qf_launch_f_a_fused(const FaFusedArgs& a, cudaStream_t stream);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
@@ -194,7 +195,7 @@ cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* plan
 cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
                                    int B, cudaStream_t stream);
 // fixed-point digit planes of U for the tensor-core nearest-plane updates (see setup.cu)
-cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int L, double* scale, int8_t* planes,
+cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int L, double* scale, int8_t* planes,
                                     long plane_stride, long ldk, cudaStream_t stream);
 
 // ---- ring_small.cu : register/shuffle NTT mod q for NTT-friendly primes q < 2^16 ----------------
