@@ -356,7 +356,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (p.tim) te_body += clock64() - te1_;
             // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
             if (tile + (int)gridDim.x < total_tiles) {
-                for (int c = half * 16; c < ND * p.nt; c += 16 * (EPI_WARPS / 4)) tmem_st16_zero(lane_addr + (uint32_t)c);
+                // (each warp zeroes exactly the columns it has just read: the other warp of the lane group may still be
+                // reading its own)
+                for (int d = 0; d < ND; ++d)
+                    for (int c = cbeg; c < cend; c += 16) tmem_st16_zero(lane_addr + (uint32_t)(d * p.nt + c));
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
