@@ -173,7 +173,7 @@ def _exact_f_a_int64(a, sig, q):
 
 
 @pytest.mark.parametrize("n,q,s,r,B", [(160, 2**24 - 3, 300.0, 4.0, 300), (300, 2**32 - 5, 467.0, 9.0, 150),
-                                         (256, 3329, 40.0, 2.0, 515)])
+                                         (256, 3329, 40.0, 2.0, 515), (192, 2**16, 200.0, 3.0, 260)])
 def test_f_a_fused_cta_pairs(T, n, q, s, r, B, monkeypatch):
     """Shapes with an even number of coordinate tiles: the fused f_a kernel runs as clusters of two CTAs that share the
     converted sigma tiles through distributed shared memory.  Bit-exact against the oracle, ragged batch (B not a

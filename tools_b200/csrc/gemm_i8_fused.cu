@@ -29,6 +29,7 @@ constexpr int MAX_LX = 4;
 struct FusedParams {
     const int32_t* x; long ldx;
     int B, N, K, LX, LW, nt, stages, w_signed, vec;
+    int dmax;  // number of digit sums that can contribute to the result (see the kernel)
     unsigned long long q;
     int64_t* out; long ldout;
     unsigned long long* norm2;
@@ -71,7 +72,9 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int ND = LXT + p.LW - 1;
+    // Digit sums D_d that matter: all LX + LW - 1 of them, except that for q = 2^e every D_d with 8 d >= e is a multiple
+    // of q (256^d D_d = 0 mod q) -- neither multiplied nor read back (C2: q = 2^24, 5 of the 6 digit pairs remain).
+    const int ND = min(LXT + p.LW - 1, p.dmax);
     const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     const int tile_n = blockIdx.x % p.n_tiles, tile_m = blockIdx.x / p.n_tiles;  // PAIR: n_tiles even, tile_n & 1 == crank
     const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
@@ -148,7 +151,8 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                     if (!((mk >> j) & 1u)) continue;
                     const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
                     for (int i0 = 0; i0 < p.LW; i0 += G) {
-                        const int g = min(G, p.LW - i0);
+                        const int g = min(min(G, p.LW - i0), ND - (i0 + j));  // planes i0 .. i0+g-1 land in D_{i0+j} ..
+                        if (g <= 0) break;
                         const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
                         const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
                         const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
@@ -404,6 +408,12 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     p.vec = ((a.ldx & 3) == 0 && (((uintptr_t)a.x) & 15) == 0) ? 1 : 0;
     p.q = a.q; p.out = a.out; p.ldout = a.ldout; p.norm2 = a.norm2; p.mma_units = a.mma_units;
     p.overflow = a.retry_flag; p.run_if = run_if; p.tim = a.tim;
+    p.dmax = 64;
+    if (a.q && (a.q & (a.q - 1)) == 0) {
+        int e = 0;
+        while ((1ull << e) < a.q) ++e;
+        p.dmax = e == 0 ? 1 : (e + 7) / 8;
+    }
     p.n_tiles = (a.N + nt - 1) / nt;
     const int m_tiles = (a.B + tc05::TILE_M - 1) / tc05::TILE_M;
     const int stage_bytes = LX * tc05::TILE_M * tc05::BLOCK_K + a.LW * nt * tc05::BLOCK_K;
