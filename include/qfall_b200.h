@@ -165,6 +165,17 @@ qf_status qf_compress_i64(const int64_t* in, int64_t* out, size_t count, uint64_
 qf_status qf_decompress_i64(const int64_t* in, int64_t* out, size_t count, uint64_t q, uint32_t d,
                             int device_ptrs, void* cuda_stream);
 
+/* ---- FIPS 203 ByteEncode_d / ByteDecode_d fused with Compress_d / Decompress_d (the step after
+ * `lossy_compress` in ML-KEM; the reference stops at the unpacked polynomial, lossy_compression_fips203.rs:62,99-113).
+ * Polynomials of degree 256: `in` holds npoly x 256 u16 coefficients, the packed form npoly x 32 d bytes (FIPS 203
+ * Algorithm 5: coefficient i supplies stream bits [i d, (i+1) d), bit k of the stream = bit k % 8 of byte k / 8).
+ * 1 <= d <= 12, q < 2^16.  compress != 0: ByteEncode_d(Compress_d(x)), else ByteEncode_d(x) (d = 12: x < q).
+ * decompress != 0: Decompress_d(ByteDecode_d(b)), else ByteDecode_d(b) (d = 12: reduced mod q, Algorithm 6). */
+qf_status qf_compress_encode_u16(const uint16_t* in, uint8_t* out, size_t npoly, uint32_t q, uint32_t d, int compress,
+                                 int device_ptrs, void* cuda_stream);
+qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npoly, uint32_t q, uint32_t d, int decompress,
+                                   int device_ptrs, void* cuda_stream);
+
 /* ---- Z::sample_discrete_gauss for a batch of (centre) values (qfall-math SampleZ as used at
  * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers. */
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out);

@@ -566,6 +566,46 @@ def lossy_decompress_np(y: np.ndarray, d: int, q: int) -> np.ndarray:
     return (y * np.uint64(q) + np.uint64(1 << (d - 1))) >> np.uint64(d)
 
 
+def byte_encode(f, d: int):
+    """FIPS 203 Algorithm 5 ByteEncode_d, restated literally (the step that follows
+    ``lossy_compress`` in ML-KEM; NOT in the reference crate, whose compressed type stays an unpacked PolyOverZ,
+    lossy_compression_fips203.rs:62 -- so PARITY UNPINNED by the reference; pinned here by hand-computed vectors in
+    tests/test_oracle_golden.py).  f: 256 integers mod m (m = 2^d for d < 12, q for d = 12) -> 32 d bytes."""
+    assert len(f) == 256 and 1 <= d <= 12
+    bits = [0] * (256 * d)
+    for i in range(256):
+        a = int(f[i])
+        for j in range(d):  # b[i d + j] <- a mod 2; a <- (a - b[i d + j]) / 2
+            bits[i * d + j] = a & 1
+            a >>= 1
+    out = bytearray(32 * d)  # BitsToBytes (Algorithm 3): B[floor(i / 8)] += b[i] 2^(i mod 8)
+    for i, b in enumerate(bits):
+        out[i // 8] |= b << (i % 8)
+    return bytes(out)
+
+
+def byte_decode(b, d: int, q: int):
+    """FIPS 203 Algorithm 6 ByteDecode_d: 32 d bytes -> 256 integers mod m (m = 2^d if d < 12 else q)."""
+    assert len(b) == 32 * d and 1 <= d <= 12
+    bits = [(b[i // 8] >> (i % 8)) & 1 for i in range(256 * d)]  # BytesToBits (Algorithm 4)
+    m = (1 << d) if d < 12 else q
+    return [sum(bits[i * d + j] << j for j in range(d)) % m for i in range(256)]
+
+
+def byte_encode_np(x: np.ndarray, d: int) -> np.ndarray:
+    """Vectorised ByteEncode_d for an (npoly, 256) array (same bit order as byte_encode)."""
+    x = np.asarray(x, dtype=np.uint16)
+    bits = ((x[..., None] >> np.arange(d, dtype=np.uint16)) & 1).astype(np.uint8)  # (..., 256, d): bit j of coeff i
+    return np.packbits(bits.reshape(x.shape[:-1] + (256 * d,)), axis=-1, bitorder="little")
+
+
+def byte_decode_np(b: np.ndarray, d: int, q: int) -> np.ndarray:
+    b = np.asarray(b, dtype=np.uint8)
+    bits = np.unpackbits(b, axis=-1, bitorder="little").reshape(b.shape[:-1] + (256, d)).astype(np.uint32)
+    v = (bits << np.arange(d, dtype=np.uint32)).sum(-1)
+    return (v % ((1 << d) if d < 12 else q)).astype(np.uint16)
+
+
 # --------------------------------------------------------------------------
 # f_a / check_domain  (gpv.rs, mp_perturbation.rs, gpv_ring.rs)
 # --------------------------------------------------------------------------

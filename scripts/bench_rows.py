@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 import tools_b200 as T  # noqa: E402
 from tools_b200 import _ffi  # noqa: E402
-from tools_b200.compression import compress_dev  # noqa: E402
+from tools_b200.compression import byte_code_dev, compress_dev  # noqa: E402
 
 dev = torch.device("cuda:0")
 PEAKS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -58,6 +58,24 @@ def row_compress():
                           "compress_GBps": gb / ms_c * 1e3, "decompress_GBps": gb / ms_d * 1e3,
                           "frac_of_measured_hbm": gb / ms_c * 1e3 / HBM, "algorithmic_bytes": count * 4,
                           "polys_per_s": npoly / ms_c * 1e3}), flush=True)
+
+
+def row_encode():
+    """ByteEncode_d(Compress_d(.)) / Decompress_d(ByteDecode_d(.)) on the C5 stream: 512 + 32 d algorithmic bytes / polynomial."""
+    npoly = 16 * 1024 * 1024
+    x = torch.randint(0, 3329, (npoly * 256,), dtype=torch.int32, device=dev).to(torch.int16)
+    z = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    for d in (1, 4, 10, 11):
+        packed = torch.empty(npoly * 32 * d, dtype=torch.uint8, device=dev)
+        ms_e = timeit(lambda: byte_code_dev(x.data_ptr(), packed.data_ptr(), npoly, 3329, d, st))
+        ms_d = timeit(lambda: byte_code_dev(packed.data_ptr(), z.data_ptr(), npoly, 3329, d, st, decode=True))
+        gb = npoly * (512 + 32 * d) / 1e9
+        print(json.dumps({"row": "C5 compress+ByteEncode", "d": d, "polys": npoly, "encode_ms": ms_e, "decode_ms": ms_d,
+                          "encode_GBps": gb / ms_e * 1e3, "decode_GBps": gb / ms_d * 1e3,
+                          "frac_of_measured_hbm": gb / ms_e * 1e3 / HBM, "frac_of_measured_hbm_decode": gb / ms_d * 1e3 / HBM,
+                          "algorithmic_bytes": npoly * (512 + 32 * d), "polys_per_s": npoly / ms_e * 1e3}), flush=True)
+        del packed
 
 
 def row_ring():
@@ -166,6 +184,7 @@ def pert_s(n, q):
 
 ROWS = {
     "compress": row_compress,
+    "encode": row_encode,
     "ring": row_ring,
     "f_a": row_f_a,
     "pert_c1": lambda: row_pert(8, 64, 3.0, 25.0, 262144, "C1 PSFPerturbation n=8 q=64 r=3 s=25"),

@@ -90,6 +90,40 @@ def test_compress_wide_modulus(T):
         assert np.array_equal(T.lossy_decompress(got, d, q), wantd)
 
 
+@pytest.mark.parametrize("npoly", [1, 2, 7, 8, 9, 1185, 4099])
+def test_byte_encode_decode_bit_exact(T, npoly):
+    """Compress_d + ByteEncode_d and ByteDecode_d + Decompress_d (FIPS 203 Algorithms 5 / 6) against
+    the oracle's literal restatement, every d, ragged polynomial counts (not a multiple of the warps per CTA)."""
+    from tools_b200.compression import compress_encode, decode_decompress
+
+    q = 3329
+    rng = np.random.default_rng(npoly)
+    x = rng.integers(0, q, (npoly, 256)).astype(np.uint16)
+    x[0, :4] = [0, q - 1, q // 2, q // 2 + 1]
+    for d in range(1, 13):
+        comp = O.lossy_compress_np(x, d, q).astype(np.uint16)
+        want = O.byte_encode_np(comp, d)
+        got = compress_encode(x, d, q)
+        assert got.shape == (npoly, 32 * d) and got.dtype == np.uint8
+        assert np.array_equal(got, want), d
+        back = decode_decompress(got, d, q)
+        assert np.array_equal(back.astype(np.uint64), O.lossy_decompress_np(comp, d, q)), d
+        # plain ByteEncode_d / ByteDecode_d (no compression): values mod 2^d, d = 12 -> values < q
+        raw = x if d == 12 else (x & ((1 << d) - 1)).astype(np.uint16)
+        enc = compress_encode(raw, d, q, compress=False)
+        assert np.array_equal(enc, O.byte_encode_np(raw, d))
+        assert np.array_equal(decode_decompress(enc, d, q, decompress=False), O.byte_decode_np(enc, d, q))
+    # literal (bit-by-bit) oracle on the first polynomial
+    for d in (1, 4, 5, 10, 11, 12):
+        comp0 = O.lossy_compress(x[0].tolist(), d, q) if d < 12 else x[0].tolist()
+        assert bytes(compress_encode(x[:1], d, q, compress=d < 12)[0]) == O.byte_encode(comp0, d)
+    # ByteDecode_12 reduces mod q (Algorithm 6, m = q)
+    allones = np.full((1, 384), 0xFF, dtype=np.uint8)
+    assert np.array_equal(decode_decompress(allones, 12, q, decompress=False), np.full((1, 256), 4095 % q, dtype=np.uint16))
+    with pytest.raises(AssertionError):
+        compress_encode(x, 0, q)
+
+
 # ----------------------------------------------------------------------------------
 # TrapGen: bit-exact (gadget_classical.rs:56-68)
 # ----------------------------------------------------------------------------------

@@ -224,6 +224,31 @@ def test_compression_round_trip_and_formula():
         O.lossy_decompress([1], 0, 3329)
 
 
+def test_byte_encode_decode_known_vectors():
+    """FIPS 203 Algorithms 5 / 6 (not part of the reference crate): hand-computed byte layouts,
+    inverse property for every d, vectorised form == literal form."""
+    f = [0] * 256
+    f[0], f[1] = 1, 2
+    assert O.byte_encode(f, 4)[:2] == bytes([0x21, 0x00])          # two 4-bit values per byte, low nibble first
+    f[0], f[1] = 0xABC, 0x123
+    assert O.byte_encode(f, 12)[:3] == bytes([0xBC, 0x3A, 0x12])   # the 12-bit layout of ML-KEM's ByteEncode_12
+    f = [0] * 256
+    f[0], f[1], f[2] = 0b101, 0b011, 0b111
+    assert O.byte_encode(f, 3)[:2] == bytes([0xDD, 0x01])
+    rng = np.random.default_rng(5)
+    for d in range(1, 13):
+        m = (1 << d) if d < 12 else 3329
+        g = rng.integers(0, m, (3, 256))
+        for row in g:
+            b = O.byte_encode(row.tolist(), d)
+            assert len(b) == 32 * d and O.byte_decode(b, d, 3329) == row.tolist()
+        enc = O.byte_encode_np(g, d)
+        assert [bytes(r) for r in enc] == [O.byte_encode(row.tolist(), d) for row in g]
+        assert np.array_equal(O.byte_decode_np(enc, d, 3329), g)
+    # ByteDecode_12 reduces mod q
+    assert O.byte_decode(bytes([0xFF] * 384), 12, 3329) == [4095 % 3329] * 256
+
+
 def test_reference_samp_p_restatements():
     """gpv.rs:253-268, mp_perturbation.rs:432-448, gpv_ring.rs:317-334 on the oracle."""
     rng = np.random.default_rng(7)

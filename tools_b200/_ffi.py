@@ -65,6 +65,8 @@ SIGNATURES = {
     "qf_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _vp]),
     "qf_compress_i64": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _vp]),
     "qf_decompress_i64": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _vp]),
+    "qf_compress_encode_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _i32, _vp]),
+    "qf_decode_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _i32, _vp]),
     "qf_sample_z": (_i32, [_vp, _sz, C.c_double, _u64, _vp]),
     "qf_debug_gemm_i8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _u64, _vp]),
     "qf_fill_uniform_modq_dev": (_i32, [_vp, _sz, _u64, _u64, _vp]),

@@ -47,3 +47,42 @@ def compress_dev(in_ptr, out_ptr, count, q, d, stream=None, decompress=False):
             _ffi.ptr(int(stream)) if stream else None)
     if st != _ffi.QF_OK:
         raise _ffi.QfError(st, "compress_dev failed")
+
+
+def _byte_code(fn_name, arr, npoly, out, q, d, flag):
+    d = int(d)
+    if d < 1:
+        raise AssertionError("Performing this function with d < 1 implies reducing mod 1")
+    st = getattr(_ffi.lib(), fn_name)(_ffi.ptr(arr), _ffi.ptr(out), int(npoly), int(q), d, int(flag), 0, None)
+    if st != _ffi.QF_OK:
+        raise _ffi.QfError(st, f"{fn_name} failed")
+    return out
+
+
+def compress_encode(coeffs, d, q, compress=True):
+    """ByteEncode_d(Compress_d(f)) for degree-256 polynomials (FIPS 203 Algorithms 5 and 4.7; what ML-KEM does with the
+    output of `lossy_compress`).  coeffs: (..., 256) u16 in [0, q) -> (..., 32 d) bytes."""
+    a = np.ascontiguousarray(coeffs, dtype=np.uint16)
+    if a.shape[-1] != 256:
+        raise AssertionError("ByteEncode_d is defined on 256 coefficients")
+    out = np.empty(a.shape[:-1] + (32 * int(d),), dtype=np.uint8)
+    return _byte_code("qf_compress_encode_u16", a, a.size // 256, out, q, d, compress)
+
+
+def decode_decompress(packed, d, q, decompress=True):
+    """Decompress_d(ByteDecode_d(b)) (FIPS 203 Algorithm 6 then 4.8): (..., 32 d) bytes -> (..., 256) u16."""
+    b = np.ascontiguousarray(packed, dtype=np.uint8)
+    if b.shape[-1] != 32 * int(d):
+        raise AssertionError("ByteDecode_d expects 32 d bytes per polynomial")
+    out = np.empty(b.shape[:-1] + (256,), dtype=np.uint16)
+    return _byte_code("qf_decode_decompress_u16", b, b.size // (32 * int(d)), out, q, d, decompress)
+
+
+def byte_code_dev(in_ptr, out_ptr, npoly, q, d, stream=None, decode=False, flag=True):
+    """Device-resident streams (pointers are integers): encode (u16 coefficients -> bytes) or decode."""
+    lib = _ffi.lib()
+    fn = lib.qf_decode_decompress_u16 if decode else lib.qf_compress_encode_u16
+    st = fn(_ffi.ptr(int(in_ptr)), _ffi.ptr(int(out_ptr)), int(npoly), int(q), int(d), int(flag), 1,
+            _ffi.ptr(int(stream)) if stream else None)
+    if st != _ffi.QF_OK:
+        raise _ffi.QfError(st, "byte_code_dev failed")

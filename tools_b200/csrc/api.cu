@@ -1999,6 +1999,44 @@ qf_status qf_decompress_i64(const int64_t* in, int64_t* out, size_t count, uint6
     return compress_any(in, out, count, q, d, dev, st, 1, 1);
 }
 
+// ---- Compress_d + ByteEncode_d / ByteDecode_d + Decompress_d (FIPS 203 Algorithms 5, 6) ------------------------------
+static qf_status byte_code_any(const void* in, void* out, size_t npoly, uint32_t q, uint32_t d, int flag, int dev, void* stream,
+                               int decode) {
+    if ((!in || !out) && npoly) return QF_ERR_INVALID;
+    if (d < 1) return QF_ERR_INVALID;  // same contract as lossy_compress (lossy_compression_fips203.rs:91-94)
+    if (d > 12 || q > 65535 || q < 2) return QF_ERR_UNSUPPORTED;
+    if (npoly == 0) return QF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t coeff_bytes = npoly * 512, packed_bytes = npoly * 32 * (size_t)d;
+    const size_t in_bytes = decode ? packed_bytes : coeff_bytes, out_bytes = decode ? coeff_bytes : packed_bytes;
+    auto run = [&](const void* di, void* dout) -> cudaError_t {
+        return decode ? qf_launch_byte_decode((const uint8_t*)di, (uint16_t*)dout, npoly, q, d, flag, st)
+                      : qf_launch_byte_encode((const uint16_t*)di, (uint8_t*)dout, npoly, q, d, flag, st);
+    };
+    auto map_err = [](cudaError_t e) { return e == cudaSuccess ? QF_OK : (e == cudaErrorInvalidValue ? QF_ERR_INVALID : QF_ERR_CUDA); };
+    if (dev) return map_err(run(in, out));
+    void *di = nullptr, *dout = nullptr;
+    if (cudaMalloc(&di, in_bytes) != cudaSuccess) return QF_ERR_CUDA;
+    if (cudaMalloc(&dout, out_bytes) != cudaSuccess) { cudaFree(di); return QF_ERR_CUDA; }
+    qf_status rc = QF_OK;
+    if (cudaMemcpyAsync(di, in, in_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (rc == QF_OK) rc = map_err(run(di, dout));
+    if (rc == QF_OK && cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == QF_OK) rc = QF_ERR_CUDA;
+    cudaFree(di);
+    cudaFree(dout);
+    return rc;
+}
+
+qf_status qf_compress_encode_u16(const uint16_t* in, uint8_t* out, size_t npoly, uint32_t q, uint32_t d, int compress, int dev,
+                                 void* st) {
+    return byte_code_any(in, out, npoly, q, d, compress, dev, st, 0);
+}
+qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npoly, uint32_t q, uint32_t d, int decompress,
+                                   int dev, void* st) {
+    return byte_code_any(in, out, npoly, q, d, decompress, dev, st, 1);
+}
+
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out) {
     if (!centers || !out || !(s > 0)) return QF_ERR_INVALID;
     if (count == 0) return QF_OK;

@@ -94,6 +94,100 @@ __global__ void compress_i64_kernel(const int64_t* __restrict__ in, int64_t* __r
     }
 }
 
+// ---- Compress_d + ByteEncode_d and ByteDecode_d + Decompress_d in one pass (FIPS 203 Algorithms 5 and 6; SURVEY 8f rank
+// 4: the step that follows compression in ML-KEM).  A polynomial is 256 coefficients -> 32 d bytes: coefficient i
+// contributes its d low bits to stream bits [i d, (i + 1) d), bit k of the stream is bit k % 8 of byte k / 8.
+// One warp per polynomial: a lane owns 8 consecutive coefficients (one 128-bit load) = exactly d bytes of the stream,
+// the warp's 32 d bytes are assembled in shared memory and leave as 128-bit stores, so both HBM streams are coalesced
+// and the packed form is the only thing written: 512 + 32 d algorithmic bytes per polynomial instead of 1024.
+constexpr int PK_WARPS = 8;    // warps per CTA
+constexpr int PK_MAXD = 12;
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(PK_WARPS * 32)
+encode_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out, size_t npoly, CParams p) {
+    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * PK_MAXD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t d = p.d;
+    const size_t wstride = (size_t)gridDim.x * PK_WARPS;
+    const uint4* vin = reinterpret_cast<const uint4*>(in);
+    size_t poly = (size_t)blockIdx.x * PK_WARPS + warp;
+    uint4 v = make_uint4(0, 0, 0, 0), vnext = v;
+    if (poly < npoly) v = __ldcs(vin + poly * 32 + lane);
+    for (; poly < npoly; poly += wstride) {
+        const size_t nxt = poly + wstride;
+        if (nxt < npoly) vnext = __ldcs(vin + nxt * 32 + lane);  // next polynomial in flight while this one is packed
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // the lane's 8 d-bit values, little-endian, into a 96-bit accumulator
+        unsigned long long lo = 0;
+        uint32_t hi = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t x = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            x = COMPRESS ? comp1(x, p) : (x & p.mask);
+            const uint32_t pos = (uint32_t)k * d;
+            if (pos < 64) {
+                lo |= (unsigned long long)x << pos;
+                if (pos + d > 64) hi |= x >> (64 - pos);
+            } else {
+                hi |= x << (pos - 64);
+            }
+        }
+        uint8_t* dst = &stage[warp][lane * d];
+        for (uint32_t b = 0; b < d; ++b) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
+        __syncwarp();
+        if ((uint32_t)lane < 2 * d)
+            __stcs(reinterpret_cast<uint4*>(out + poly * 32 * d) + lane, reinterpret_cast<const uint4*>(stage[warp])[lane]);
+        __syncwarp();
+        v = vnext;
+    }
+}
+
+template <bool DECOMPRESS>
+__global__ void __launch_bounds__(PK_WARPS * 32)
+decode_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out, size_t npoly, CParams p, uint32_t modq) {
+    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * PK_MAXD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t d = p.d;
+    const size_t wstride = (size_t)gridDim.x * PK_WARPS;
+    uint4* vout = reinterpret_cast<uint4*>(out);
+    size_t poly = (size_t)blockIdx.x * PK_WARPS + warp;
+    uint4 raw = make_uint4(0, 0, 0, 0), rnext = raw;
+    if (poly < npoly && (uint32_t)lane < 2 * d) raw = __ldcs(reinterpret_cast<const uint4*>(in + poly * 32 * d) + lane);
+    for (; poly < npoly; poly += wstride) {
+        const size_t nxt = poly + wstride;
+        if (nxt < npoly && (uint32_t)lane < 2 * d) rnext = __ldcs(reinterpret_cast<const uint4*>(in + nxt * 32 * d) + lane);
+        if ((uint32_t)lane < 2 * d) reinterpret_cast<uint4*>(stage[warp])[lane] = raw;
+        __syncwarp();
+        const uint8_t* src = &stage[warp][lane * d];
+        unsigned long long lo = 0;
+        uint32_t hi = 0;
+        for (uint32_t b = 0; b < d; ++b) {
+            if (b < 8) lo |= (unsigned long long)src[b] << (8 * b);
+            else hi |= (uint32_t)src[b] << (8 * (b - 8));
+        }
+        __syncwarp();
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t pos = (uint32_t)k * d;
+            uint32_t y;
+            if (pos < 64) {
+                y = (uint32_t)(lo >> pos);
+                if (pos + d > 64) y |= hi << (64 - pos);
+            } else {
+                y = hi >> (pos - 64);
+            }
+            y &= p.mask;
+            if (DECOMPRESS) y = decomp1(y, p);
+            else if (modq) y %= modq;  // ByteDecode_12: integers mod q (FIPS 203 Algorithm 6, m = q)
+            w[k >> 1] |= (y & 0xffffu) << ((k & 1) * 16);
+        }
+        __stcs(vout + poly * 32 + lane, make_uint4(w[0], w[1], w[2], w[3]));
+        raw = rnext;
+    }
+}
+
 }  // namespace
 
 cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
@@ -134,5 +228,52 @@ cudaError_t qf_launch_compress_i64(const int64_t* in, int64_t* out, size_t count
     size_t want = (count + 255) / 256;
     int grid = (int)(want > 148 * 16 ? 148 * 16 : want);
     compress_i64_kernel<<<grid, 256, 0, stream>>>(in, out, count, q, d, decompress);
+    return cudaGetLastError();
+}
+
+static void fill_cparams(CParams& p, uint32_t q, uint32_t d) {
+    p.q = q; p.d = d; p.half_q = q / 2; p.mask = (d >= 32) ? 0xffffffffu : ((1u << d) - 1);
+    p.round = 1u << (d - 1);
+    p.magic = ~0ull / q + 1;
+    uint32_t sh = 0;
+    while ((2u << sh) <= q) ++sh;
+    const unsigned long long pw = 1ull << (32 + sh);
+    const unsigned long long m32 = (pw + q - 1) / q;
+    const unsigned long long e = m32 * q - pw;
+    const unsigned long long num_max = ((unsigned long long)(q - 1) << d) + q / 2;
+    p.sh = sh;
+    p.magic32 = (uint32_t)m32;
+    p.narrow = (m32 <= 0xffffffffull && num_max <= 0xffffffffull && e * num_max < pw) ? 1u : 0u;
+}
+
+// in: npoly x 256 coefficients (u16), out: npoly x 32 d bytes.  compress != 0: ByteEncode_d(Compress_d(x)); else
+// ByteEncode_d(x mod 2^d) (d = 12: the caller's coefficients are already < q < 2^12).
+cudaError_t qf_launch_byte_encode(const uint16_t* in, uint8_t* out, size_t npoly, uint32_t q, uint32_t d, int compress,
+                                  cudaStream_t stream) {
+    if (npoly == 0) return cudaSuccess;
+    if (q < 2 || q > 65535 || d < 1 || d > PK_MAXD) return cudaErrorInvalidValue;
+    if ((((uintptr_t)in) & 15) || (((uintptr_t)out) & 15)) return cudaErrorMisalignedAddress;
+    CParams p;
+    fill_cparams(p, q, d);
+    size_t want = (npoly + PK_WARPS - 1) / PK_WARPS;
+    int grid = (int)(want > 148 * 8 ? 148 * 8 : want);
+    if (compress) encode_kernel<true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
+    else encode_kernel<false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
+    return cudaGetLastError();
+}
+
+// in: npoly x 32 d bytes, out: npoly x 256 coefficients.  decompress != 0: Decompress_d(ByteDecode_d(b)); else
+// ByteDecode_d(b) (values mod 2^d; d = 12: mod q, FIPS 203 Algorithm 6).
+cudaError_t qf_launch_byte_decode(const uint8_t* in, uint16_t* out, size_t npoly, uint32_t q, uint32_t d, int decompress,
+                                  cudaStream_t stream) {
+    if (npoly == 0) return cudaSuccess;
+    if (q < 2 || q > 65535 || d < 1 || d > PK_MAXD) return cudaErrorInvalidValue;
+    if ((((uintptr_t)in) & 15) || (((uintptr_t)out) & 15)) return cudaErrorMisalignedAddress;
+    CParams p;
+    fill_cparams(p, q, d);
+    size_t want = (npoly + PK_WARPS - 1) / PK_WARPS;
+    int grid = (int)(want > 148 * 8 ? 148 * 8 : want);
+    if (decompress) decode_kernel<true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, 0u);
+    else decode_kernel<false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, d == 12 ? q : 0u);
     return cudaGetLastError();
 }

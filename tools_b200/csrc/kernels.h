@@ -98,6 +98,11 @@ cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int wid
 // ---- compress.cu -----------------------------------------------------------
 cudaError_t qf_launch_compress_u16(const uint16_t* in, uint16_t* out, size_t count, uint32_t q, uint32_t d,
                                    int decompress, cudaStream_t stream);
+// Compress_d + ByteEncode_d / ByteDecode_d + Decompress_d, one warp per degree-256 polynomial (compress.cu)
+cudaError_t qf_launch_byte_encode(const uint16_t* in, uint8_t* out, size_t npoly, uint32_t q, uint32_t d, int compress,
+                                  cudaStream_t stream);
+cudaError_t qf_launch_byte_decode(const uint8_t* in, uint16_t* out, size_t npoly, uint32_t q, uint32_t d, int decompress,
+                                  cudaStream_t stream);
 cudaError_t qf_launch_compress_i64(const int64_t* in, int64_t* out, size_t count, unsigned long long q,
                                    uint32_t d, int decompress, cudaStream_t stream);
 
