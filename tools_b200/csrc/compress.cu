@@ -103,12 +103,42 @@ __global__ void compress_i64_kernel(const int64_t* __restrict__ in, int64_t* __r
 constexpr int PK_WARPS = 8;    // warps per CTA
 constexpr int PK_MAXD = 12;
 
-template <bool COMPRESS>
+// store / load the lane's D bytes at byte offset lane * D of the warp's staging row with the widest accesses the
+// alignment of lane * D allows (D % 4 == 0: words, D even: half-words, else bytes); r[] = the 8 D bits, little-endian
+template <int D>
+__device__ __forceinline__ void put_bytes(uint8_t* dst, const uint32_t (&r)[3]) {
+    if (D % 4 == 0) {
+#pragma unroll
+        for (int w = 0; w < D / 4; ++w) reinterpret_cast<uint32_t*>(dst)[w] = r[w];
+    } else if (D % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < D / 2; ++h) reinterpret_cast<uint16_t*>(dst)[h] = (uint16_t)(r[h >> 1] >> ((h & 1) * 16));
+    } else {
+#pragma unroll
+        for (int b = 0; b < D; ++b) dst[b] = (uint8_t)(r[b >> 2] >> ((b & 3) * 8));
+    }
+}
+template <int D>
+__device__ __forceinline__ void get_bytes(const uint8_t* src, uint32_t (&r)[3]) {
+    r[0] = r[1] = r[2] = 0;
+    if (D % 4 == 0) {
+#pragma unroll
+        for (int w = 0; w < D / 4; ++w) r[w] = reinterpret_cast<const uint32_t*>(src)[w];
+    } else if (D % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < D / 2; ++h) r[h >> 1] |= (uint32_t)reinterpret_cast<const uint16_t*>(src)[h] << ((h & 1) * 16);
+    } else {
+#pragma unroll
+        for (int b = 0; b < D; ++b) r[b >> 2] |= (uint32_t)src[b] << ((b & 3) * 8);
+    }
+}
+
+// D compile time: every bit position is a constant, the 8 values of a lane are packed with 32-bit shifts only.
+template <int D, bool COMPRESS>
 __global__ void __launch_bounds__(PK_WARPS * 32)
 encode_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out, size_t npoly, CParams p) {
-    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * PK_MAXD];
+    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t d = p.d;
     const size_t wstride = (size_t)gridDim.x * PK_WARPS;
     const uint4* vin = reinterpret_cast<const uint4*>(in);
     size_t poly = (size_t)blockIdx.x * PK_WARPS + warp;
@@ -118,74 +148,71 @@ encode_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out, size_t
         const size_t nxt = poly + wstride;
         if (nxt < npoly) vnext = __ldcs(vin + nxt * 32 + lane);  // next polynomial in flight while this one is packed
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        // the lane's 8 d-bit values, little-endian, into a 96-bit accumulator
-        unsigned long long lo = 0;
-        uint32_t hi = 0;
+        uint32_t r[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            uint32_t x = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-            x = COMPRESS ? comp1(x, p) : (x & p.mask);
-            const uint32_t pos = (uint32_t)k * d;
-            if (pos < 64) {
-                lo |= (unsigned long long)x << pos;
-                if (pos + d > 64) hi |= x >> (64 - pos);
-            } else {
-                hi |= x << (pos - 64);
-            }
+            uint32_t x = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+            x = COMPRESS ? comp1(x, p) : (x & ((1u << D) - 1));
+            const int pos = k * D, wi = pos >> 5, sh = pos & 31;
+            r[wi] |= x << sh;
+            if (sh + D > 32) r[wi + 1] |= x >> (32 - sh);
         }
-        uint8_t* dst = &stage[warp][lane * d];
-        for (uint32_t b = 0; b < d; ++b) dst[b] = (uint8_t)(b < 8 ? (lo >> (8 * b)) : (hi >> (8 * (b - 8))));
+        put_bytes<D>(&stage[warp][lane * D], r);
         __syncwarp();
-        if ((uint32_t)lane < 2 * d)
-            __stcs(reinterpret_cast<uint4*>(out + poly * 32 * d) + lane, reinterpret_cast<const uint4*>(stage[warp])[lane]);
+        if (lane < 2 * D)
+            __stcs(reinterpret_cast<uint4*>(out + poly * 32 * D) + lane, reinterpret_cast<const uint4*>(stage[warp])[lane]);
         __syncwarp();
         v = vnext;
     }
 }
 
-template <bool DECOMPRESS>
+template <int D, bool DECOMPRESS>
 __global__ void __launch_bounds__(PK_WARPS * 32)
 decode_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out, size_t npoly, CParams p, uint32_t modq) {
-    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * PK_MAXD];
+    __shared__ __align__(16) uint8_t stage[PK_WARPS][32 * D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t d = p.d;
     const size_t wstride = (size_t)gridDim.x * PK_WARPS;
     uint4* vout = reinterpret_cast<uint4*>(out);
     size_t poly = (size_t)blockIdx.x * PK_WARPS + warp;
     uint4 raw = make_uint4(0, 0, 0, 0), rnext = raw;
-    if (poly < npoly && (uint32_t)lane < 2 * d) raw = __ldcs(reinterpret_cast<const uint4*>(in + poly * 32 * d) + lane);
+    if (poly < npoly && lane < 2 * D) raw = __ldcs(reinterpret_cast<const uint4*>(in + poly * 32 * D) + lane);
     for (; poly < npoly; poly += wstride) {
         const size_t nxt = poly + wstride;
-        if (nxt < npoly && (uint32_t)lane < 2 * d) rnext = __ldcs(reinterpret_cast<const uint4*>(in + nxt * 32 * d) + lane);
-        if ((uint32_t)lane < 2 * d) reinterpret_cast<uint4*>(stage[warp])[lane] = raw;
+        if (nxt < npoly && lane < 2 * D) rnext = __ldcs(reinterpret_cast<const uint4*>(in + nxt * 32 * D) + lane);
+        if (lane < 2 * D) reinterpret_cast<uint4*>(stage[warp])[lane] = raw;
         __syncwarp();
-        const uint8_t* src = &stage[warp][lane * d];
-        unsigned long long lo = 0;
-        uint32_t hi = 0;
-        for (uint32_t b = 0; b < d; ++b) {
-            if (b < 8) lo |= (unsigned long long)src[b] << (8 * b);
-            else hi |= (uint32_t)src[b] << (8 * (b - 8));
-        }
+        uint32_t r[3];
+        get_bytes<D>(&stage[warp][lane * D], r);
         __syncwarp();
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t pos = (uint32_t)k * d;
-            uint32_t y;
-            if (pos < 64) {
-                y = (uint32_t)(lo >> pos);
-                if (pos + d > 64) y |= hi << (64 - pos);
-            } else {
-                y = hi >> (pos - 64);
-            }
-            y &= p.mask;
+            const int pos = k * D, wi = pos >> 5, sh = pos & 31;
+            uint32_t y = r[wi] >> sh;
+            if (sh + D > 32) y |= r[wi + 1] << (32 - sh);
+            y &= (1u << D) - 1;
             if (DECOMPRESS) y = decomp1(y, p);
-            else if (modq) y %= modq;  // ByteDecode_12: integers mod q (FIPS 203 Algorithm 6, m = q)
+            else if (D == 12 && modq) y = y >= modq ? y % modq : y;  // ByteDecode_12: integers mod q (Algorithm 6, m = q)
             w[k >> 1] |= (y & 0xffffu) << ((k & 1) * 16);
         }
         __stcs(vout + poly * 32 + lane, make_uint4(w[0], w[1], w[2], w[3]));
         raw = rnext;
     }
+}
+
+template <int D>
+cudaError_t launch_encode_d(const uint16_t* in, uint8_t* out, size_t npoly, const CParams& p, int compress, int grid,
+                            cudaStream_t stream) {
+    if (compress) encode_kernel<D, true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
+    else encode_kernel<D, false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
+    return cudaGetLastError();
+}
+template <int D>
+cudaError_t launch_decode_d(const uint8_t* in, uint16_t* out, size_t npoly, const CParams& p, int decompress, uint32_t q,
+                            int grid, cudaStream_t stream) {
+    if (decompress) decode_kernel<D, true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, 0u);
+    else decode_kernel<D, false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, D == 12 ? q : 0u);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -257,9 +284,13 @@ cudaError_t qf_launch_byte_encode(const uint16_t* in, uint8_t* out, size_t npoly
     fill_cparams(p, q, d);
     size_t want = (npoly + PK_WARPS - 1) / PK_WARPS;
     int grid = (int)(want > 148 * 8 ? 148 * 8 : want);
-    if (compress) encode_kernel<true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
-    else encode_kernel<false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p);
-    return cudaGetLastError();
+    switch (d) {
+#define QF_CASE(D) case D: return launch_encode_d<D>(in, out, npoly, p, compress, grid, stream);
+        QF_CASE(1) QF_CASE(2) QF_CASE(3) QF_CASE(4) QF_CASE(5) QF_CASE(6) QF_CASE(7) QF_CASE(8) QF_CASE(9) QF_CASE(10)
+        QF_CASE(11) QF_CASE(12)
+#undef QF_CASE
+    }
+    return cudaErrorInvalidValue;
 }
 
 // in: npoly x 32 d bytes, out: npoly x 256 coefficients.  decompress != 0: Decompress_d(ByteDecode_d(b)); else
@@ -273,7 +304,11 @@ cudaError_t qf_launch_byte_decode(const uint8_t* in, uint16_t* out, size_t npoly
     fill_cparams(p, q, d);
     size_t want = (npoly + PK_WARPS - 1) / PK_WARPS;
     int grid = (int)(want > 148 * 8 ? 148 * 8 : want);
-    if (decompress) decode_kernel<true><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, 0u);
-    else decode_kernel<false><<<grid, PK_WARPS * 32, 0, stream>>>(in, out, npoly, p, d == 12 ? q : 0u);
-    return cudaGetLastError();
+    switch (d) {
+#define QF_CASE(D) case D: return launch_decode_d<D>(in, out, npoly, p, decompress, q, grid, stream);
+        QF_CASE(1) QF_CASE(2) QF_CASE(3) QF_CASE(4) QF_CASE(5) QF_CASE(6) QF_CASE(7) QF_CASE(8) QF_CASE(9) QF_CASE(10)
+        QF_CASE(11) QF_CASE(12)
+#undef QF_CASE
+    }
+    return cudaErrorInvalidValue;
 }
