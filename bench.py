@@ -366,15 +366,17 @@ def main():
         # (the exact integer / fixed-point product the reference computes in big-number arithmetic); the tensor pipe
         # executes that once per digit pair (`issued`), which is what is compared with the int8 peak in `frac`.
         roofline = {
-            "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z and exact e = sol + S*z",
+            "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z (K = 1024 / 4096) and exact e = sol + S*z",
             "bound": "tensor", "achieved": algo, "peak": i8_peak, "unit": "TOP/s", "frac": algo / i8_peak,
             "achieved_issued": issued, "frac_issued": issued / i8_peak,
             "algorithmic_ops": "2*B*N*K per launch (B targets x N coordinates x K contraction length), summed over the "
                                "launches of the timed region; `issued` multiplies by the digit pairs the tensor pipe "
                                "actually executed (zero digit planes skipped), counted by the kernel",
-            "traffic": 8.77e9, "traffic_note": "dram read+write of the S*z launch (the largest one) from the ncu --set full "
-                                              "capture profiles/prof_i8_sz_r1.ncu-rep; algorithmic 2.0 GB per launch "
-                                              "(z digits 0.97 + S digits 0.31 + e 0.77)",
+            "traffic": 8.62e9, "traffic_note": "dram read+write of the largest launch (fixed-point update N = 8192 rows, "
+                                              "K = 4096, 12.7 ms) from the ncu --set full capture "
+                                              "profiles/prof_i8_update4096_r1.ncu-rep; algorithmic 2.95 GB for that launch "
+                                              "(T read+write 2.48 + z digits 0.23 + U digits 0.23): the U digit planes are "
+                                              "re-read per target tile (L2 hit rate 88 %)",
             "peak_source": i8_src, "digit_pairs_per_mac": issued / algo if algo else None,
             "kernel_ms_per_step": ims.value / args.steps, "kernel_share_of_step": ims.value / ms, "launches": int(iln.value),
         }
