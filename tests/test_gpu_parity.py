@@ -763,13 +763,15 @@ def test_device_entry_points_and_midsize(T):
     assert psf.ctx.launch_count() > 0
 
 
-def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch):
+@pytest.mark.parametrize("n,q", [(40, 2**16), (64, 2**16), (128, 2**12)])
+def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
     """The fixed-point (int8 tcgen05) nearest-plane updates against the fp64 DMMA path on the same key and
     seed: both must give exact preimages with the same second moment; with identical Philox streams almost
-    every preimage is identical (centres agree to ~2^-40)."""
+    every preimage is identical (centres agree to ~2^-40).  m = 1316: digits and S z only; m = 2084 = 2 * 1024 + 36:
+    one tensor-core update whose block has absorbed the thin ragged top (K = 1060); m = 3121 = 3 * 1024 + 49: two
+    updates (K = 1073 with the merged top, then K = 1024)."""
     import math
 
-    n, q = 40, 2**16
     gp = T.GadgetParameters.init_default(n, q)
     assert gp.m > 1024
     s = float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))

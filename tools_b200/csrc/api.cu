@@ -621,31 +621,47 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
 constexpr long NP_SIZES[4] = {64, 256, 1024, 4096};
 constexpr int NP_TOP = 4;
 constexpr long NP_SCALE_BLOCK = NP_SIZES[3];  // column block over which the digits of U share one scale per row
+constexpr long NP_THIN = 512;                 // a ragged top block narrower than this is merged into the block below it
+constexpr long NP_PROP_LD = NP_SIZES[2] + NP_THIN;  // proposals of one (possibly merged) 1024-block, per target
+
+// Blocks of step S over [0, D): [b S, (b+1) S), except that a ragged remainder narrower than NP_THIN at the top joins the
+// last full block (a thin block would cost a whole read-modify-write pass over T for a handful of coordinates:
+// D = 12352 = 3 * 4096 + 64).  Returns the start of the last block.
+static long np_last_block_start(long D, long S) {
+    long top = (D - 1) / S * S;
+    if (top > 0 && D - top < NP_THIN) top -= S;
+    return top;
+}
 
 // Process coordinates [lo, hi) in descending order.  Precondition: T[:, lo:hi] already carries the
-// updates of every coordinate >= hi.  level 0 = one sequential diagonal block.
-qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, int level, uint64_t seed, uint64_t first) {
+// updates of every coordinate >= hi.  level 0 = one sequential diagonal block.  prop0 = first coordinate of the
+// enclosing 1024-level block (origin of the pre-generated proposals).
+qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, int level, long prop0, uint64_t seed,
+                   uint64_t first) {
     const long D = ctx->dim, ldD = ctx->ld_dim;
     const double* U = ctx->dU.as<double>();
     if (level == 0) {
-        // proposals of the enclosing 1024-block start at column (lo / 1024) * 1024
-        const long blk0 = lo / NP_SIZES[2] * NP_SIZES[2];
         LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
-                                 ctx->w[9].as<float4>() + (lo - blk0), NP_SIZES[2], Bc, (int)lo, (int)(hi - lo), (int)D,
+                                 ctx->w[9].as<float4>() + (lo - prop0), NP_PROP_LD, Bc, (int)lo, (int)(hi - lo), (int)D,
                                  seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
         return QF_OK;
     }
     const long step = NP_SIZES[level - 1];
+    const bool i8_level = level >= 3 && ctx->use_ozaki;
     for (long sub_hi = hi; sub_hi > lo;) {
-        const long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
+        long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
+        // tensor-core levels: the ragged top of the whole recursion joins the block below it (the digit planes of U are
+        // masked and scaled for exactly this partition, see setup: np_last_block_start)
+        if (i8_level && sub_hi == D && sub_lo > lo && sub_hi - sub_lo < NP_THIN) sub_lo = std::max(lo, sub_lo - step);
         if (level == 3) {
             // the rejection-sampling proposals of this 1024-block for all targets, at full occupancy
-            CK(ctx->w[9].ensure((size_t)ctx->chunk * NP_SIZES[2] * sizeof(float4)));
-            LAUNCH(qf_launch_np_propose(ctx->w[9].as<float4>(), NP_SIZES[2], Bc, (int)sub_lo, (int)(sub_hi - sub_lo), (int)D,
+            CK(ctx->w[9].ensure((size_t)ctx->chunk * NP_PROP_LD * sizeof(float4)));
+            LAUNCH(qf_launch_np_propose(ctx->w[9].as<float4>(), NP_PROP_LD, Bc, (int)sub_lo, (int)(sub_hi - sub_lo), (int)D,
                                         seed, first, ctx->stream));
+            prop0 = sub_lo;
         }
-        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, seed, first));
-        if (level >= 3 && ctx->use_ozaki) {
+        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, prop0, seed, first));
+        if (i8_level) {
             const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
             int8_t* zp = ctx->w[8].as<int8_t>();
@@ -655,8 +671,8 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                                                  ctx->stream));
             // the update of the rows above it (within the enclosing block) on the tensor cores:
             //   T[:, lo:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
-            if (sub_lo > lo && sub_hi - sub_lo < 512) {
-                // a thin block (the ragged last one): per-tile overheads dominate the tensor-core path, use fp64
+            if (sub_lo > lo && sub_hi - sub_lo < NP_THIN) {
+                // a thin block: per-tile overheads dominate the tensor-core path, use fp64
                 LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
                                 (int)(sub_hi - sub_lo), -1.0, 1.0, 0));
             } else if (sub_lo > lo) {
@@ -721,7 +737,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(ctx->dNz.ensure(nzb));
         CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
     }
-    QF_TRY(np_block(ctx, T, Z, Bc, 0, D, NP_TOP, seed, first));
+    QF_TRY(np_block(ctx, T, Z, Bc, 0, D, NP_TOP, 0, seed, first));
     // e = sol + S z   (exact integers)
     if (ctx->use_i8) {
         // z -> balanced base-256 digits, S z on the tensor cores, then add sol on its pivot columns
@@ -1568,7 +1584,9 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
             CK(ctx->dUscale.ensure((size_t)nblk * D * 8));
             CK(ctx->dUl.ensure((size_t)ctx->u_limbs * D * ctx->ldk_dim));
             CK(cudaMemsetAsync(ctx->dUl.p, 0, (size_t)ctx->u_limbs * D * ctx->ldk_dim, ctx->stream));
-            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], (int)NP_SCALE_BLOCK, ctx->u_limbs,
+            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], (int)NP_SCALE_BLOCK,
+                                           (int)np_last_block_start(D, NP_SIZES[2]), (int)np_last_block_start(D, NP_SCALE_BLOCK),
+                                           ctx->u_limbs,
                                            ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
                                            ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));

@@ -200,8 +200,8 @@ cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* plan
 cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
                                    int B, cudaStream_t stream);
 // fixed-point digit planes of U for the tensor-core nearest-plane updates (see setup.cu)
-cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int L, double* scale, int8_t* planes,
-                                    long plane_stride, long ldk, cudaStream_t stream);
+cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int fs_last, int ss_last, int L,
+                                    double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
 
 // ---- ring_small.cu : register/shuffle NTT mod q for NTT-friendly primes q < 2^16 ----------------
 #ifdef __cplusplus
