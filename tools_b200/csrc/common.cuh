@@ -148,4 +148,16 @@ __device__ __forceinline__ uint64_t mod_i128(__int128 v, uint64_t q) {
     return (uint64_t)r;
 }
 
+// v mod q in [0, q) for |v| < 2^63, q < 2^63, with magic = floor(2^64 / q): the quotient estimate
+// umul64hi(|v|, magic) is at most 2 below the true one (|v| / 2^64 < 1), so two conditional subtractions finish it.
+// (A 128-bit `%` is a library call of a few hundred instructions; the contraction epilogues reduce 16 K values per tile.)
+__device__ __forceinline__ uint64_t mod_i64_barrett(long long v, uint64_t q, uint64_t magic) {
+    const uint64_t a = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+    uint64_t r = a - __umul64hi(a, magic) * q;
+    if (r >= q) r -= q;
+    if (r >= q) r -= q;
+    return (v < 0 && r) ? q - r : r;
+}
+static inline uint64_t qf_barrett_magic(uint64_t q) { return q ? (uint64_t)((((unsigned __int128)1) << 64) / q) : 0; }
+
 static inline int qf_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -43,6 +43,7 @@ struct I8Params {
     int out_kind;  // 0: int64 (optionally mod q, optional base, sign), 1: int32 store, 2: fp64 accumulate (+=)
     int sign;      // +1 / -1 applied to V
     unsigned long long q;  // 0: no reduction
+    unsigned long long qmagic;  // floor(2^64 / q): Barrett reduction of the 64-bit epilogue
     const int64_t* base; long ldbase;
     void* out; long ldout;
     int* flag;
@@ -314,6 +315,44 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
             } else if (!OK3) {
                 for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                    if (ND <= 4) {
+                        // |V| < 2^56 (+ base < 2^62): 64-bit recombination, Barrett reduction
+                        long long v[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) v[c] = 0;
+                        for (int d = 0; d < ND; ++d) {
+                            int32_t t[16];
+                            tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) v[c] += (long long)t[c] * (1ll << (8 * d));
+                        }
+                        if (row < p.B) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const int n = n0 + c0 + c;
+                                if (n >= p.N) continue;
+                                long long val = p.sign < 0 ? -v[c] : v[c];
+                                if (p.out_kind == 0) {
+                                    if (p.base) val += p.base[(long)row * p.ldbase + n];
+                                    long long r;
+                                    if (!p.q) r = val;
+                                    else if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)val & (p.q - 1));
+                                    else r = (long long)mod_i64_barrett(val, p.q, p.qmagic);
+                                    ((int64_t*)p.out)[(long)row * p.ldout + n] = r;
+                                } else if (p.out_kind == 1) {
+                                    if (val > 2147483647 || val < -2147483647) {
+                                        if (p.flag) atomicOr(p.flag, 4);
+                                        val = 0;
+                                    }
+                                    ((int32_t*)p.out)[(long)row * p.ldout + n] = (int32_t)val;
+                                } else {
+                                    ((double*)p.out)[(long)row * p.ldout + n] += (double)val;
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     __int128 v[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) v[c] = 0;
@@ -397,7 +436,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (nt < 16) return cudaErrorInvalidValue;
     I8Params p{};
     p.B = a.B; p.N = a.N; p.K = a.K; p.LX = a.LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
-    p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
+    p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.qmagic = qf_barrett_magic(a.q); p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
     p.ldout = a.ldout; p.flag = a.flag; p.scale = a.scale;
     p.m_tiles = (a.B + TILE_M - 1) / TILE_M;
     p.n_tiles = (a.N + nt - 1) / nt;

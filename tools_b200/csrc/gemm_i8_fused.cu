@@ -30,7 +30,7 @@ struct FusedParams {
     const int32_t* x; long ldx;
     int B, N, K, LX, LW, nt, stages, w_signed, vec;
     int dmax;  // number of digit sums that can contribute to the result (see the kernel)
-    unsigned long long q;
+    unsigned long long q, qmagic;  // qmagic = floor(2^64 / q) for the Barrett reduction of the epilogue
     int64_t* out; long ldout;
     unsigned long long* norm2;
     int n_tiles;
@@ -340,7 +340,34 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + lg * 32 + lane;
+        const bool pow2 = (p.q & (p.q - 1)) == 0;
         for (int c0 = (warp >> 2) * 16; c0 < p.nt; c0 += 16 * (CONV_WARPS / 4)) {
+            if (ND <= 4) {
+                // |V| < 2^(31 + 8 (ND - 1) + 1) <= 2^56: 64-bit recombination, Barrett reduction
+                long long v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = 0;
+                for (int d = 0; d < ND; ++d) {
+                    int32_t t[16];
+                    tmem_ld16(lane_addr + (uint32_t)(d * p.nt + c0), t);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] += (long long)t[c] * (1ll << (8 * d));
+                }
+                if (row < p.B) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int n = n0 + c0 + c;
+                        if (n >= p.N) continue;
+                        long long r;
+                        if (!p.q) r = v[c];
+                        else if (pow2) r = (long long)((unsigned long long)v[c] & (p.q - 1));
+                        else r = (long long)mod_i64_barrett(v[c], p.q, p.qmagic);
+                        p.out[(long)row * p.ldout + n] = r;
+                    }
+                }
+                continue;
+            }
             __int128 v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0;
@@ -358,7 +385,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
                     if (n >= p.N) continue;
                     long long r;
                     if (p.q) {
-                        if ((p.q & (p.q - 1)) == 0) r = (long long)((unsigned long long)v[c] & (p.q - 1));
+                        if (pow2) r = (long long)((unsigned long long)v[c] & (p.q - 1));
                         else r = (long long)mod_i128(v[c], p.q);
                     } else {
                         r = (long long)v[c];
@@ -406,7 +433,7 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     FusedParams p{};
     p.x = a.x; p.ldx = a.ldx; p.B = a.B; p.N = a.N; p.K = a.K; p.LX = LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
     p.vec = ((a.ldx & 3) == 0 && (((uintptr_t)a.x) & 15) == 0) ? 1 : 0;
-    p.q = a.q; p.out = a.out; p.ldout = a.ldout; p.norm2 = a.norm2; p.mma_units = a.mma_units;
+    p.q = a.q; p.qmagic = qf_barrett_magic(a.q); p.out = a.out; p.ldout = a.ldout; p.norm2 = a.norm2; p.mma_units = a.mma_units;
     p.overflow = a.retry_flag; p.run_if = run_if; p.tim = a.tim;
     p.dmax = 64;
     if (a.q && (a.q & (a.q - 1)) == 0) {
