@@ -119,3 +119,28 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f"{f} mentions the oracle"
+
+
+def test_rust_shim_matches_header():
+    """rust/qfall-tools-b200/src/ffi.rs (the host side in the reference's own language, shipped as source: no Rust
+    toolchain in this image) declares exactly the functions of include/qfall_b200.h, with the same parameter counts."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "qfall_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_funcs = {}
+    for m in re.finditer(r"\b(qf_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        c_funcs[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    rs = open(os.path.join(root, "rust", "qfall-tools-b200", "src", "ffi.rs")).read()
+    rs_funcs = {}
+    for m in re.finditer(r"pub fn (qf_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S):
+        args = m.group(2).strip()
+        rs_funcs[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    assert len(c_funcs) >= 30
+    assert c_funcs == rs_funcs, (sorted(set(c_funcs) ^ set(rs_funcs)), {k: (c_funcs[k], rs_funcs.get(k)) for k in c_funcs if c_funcs[k] != rs_funcs.get(k)})
+    # struct layout: same field order as qf_params
+    fields_c = re.findall(r"^\s*(?:int32_t|int64_t|uint64_t|double)\s+(\w+);", re.search(r"typedef struct \{(.*?)\} qf_params;", hdr, flags=re.S).group(1), flags=re.M)
+    fields_rs = re.findall(r"pub (\w+):", re.search(r"pub struct qf_params \{(.*?)\}", rs, flags=re.S).group(1))
+    assert fields_c == fields_rs
