@@ -116,6 +116,10 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* s_gso
 /* MatQ::gso as used at gpv.rs:91: unnormalised Gram-Schmidt of the columns of S (dim x dim) in fp64 on the
  * device (blocked Gram-Schmidt with re-orthogonalisation).  gso_out: dim x dim, host. */
 qf_status qf_gso(qf_ctx* ctx, const int64_t* s, double* gso_out);
+/* gen_short_basis_for_trapdoor_ring (short_basis_ring.rs:64-166) for the installed ring key and the trapdoor (r, e),
+ * k x n small coefficients each, in the coefficient embedding: s_out is dim x dim (host), dim = n (k + 2), row =
+ * polynomial row * n + coefficient, columns are the basis vectors.  Exact; feed it to qf_set_trapdoor_gpv. */
+qf_status qf_ring_gen_short_basis(qf_ctx* ctx, const int32_t* r, const int32_t* e, int64_t* s_out);
 /* ring key: (k+2) polynomials of n coefficients (gpv_ring.rs:70) */
 qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a);
 

@@ -51,6 +51,7 @@ extern "C" {
     pub fn qf_compute_sqrt_sigma_2(ctx: *mut qf_ctx, r: *const i8, sigma: *const f64, sqrt_sigma_2_out: *mut f64) -> i32;
     pub fn qf_set_trapdoor_gpv(ctx: *mut qf_ctx, s: *const i64, s_gso: *const f64) -> i32;
     pub fn qf_gso(ctx: *mut qf_ctx, s: *const i64, gso_out: *mut f64) -> i32;
+    pub fn qf_ring_gen_short_basis(ctx: *mut qf_ctx, r: *const i32, e: *const i32, s_out: *mut i64) -> i32;
     pub fn qf_ring_set_a(ctx: *mut qf_ctx, a: *const i64) -> i32;
 
     pub fn qf_trap_gen_from(ctx: *mut qf_ctx, a_bar: *const i64, r: *const i8, tag: *const i64, a_out: *mut i64) -> i32;

@@ -709,6 +709,28 @@ def test_ring_trap_gen_bit_exact(T, n, q):
     assert got.tolist() == want
 
 
+
+@pytest.mark.parametrize("n,q", [(4, 16), (16, 257), (64, 3329), (32, 2**10)])
+def test_ring_short_basis_device_bit_exact(T, n, q):
+    """qf_ring_gen_short_basis (short_basis_ring.rs:64-166, coefficient embedding) against the oracle's restatement and
+    the host assembly, for a power-of-base modulus (reversed S_k) and general ones; every column is in Lambda^perp(a)."""
+    from tools_b200 import gadget
+
+    rng = np.random.default_rng(n)
+    gp, po = T.GadgetParametersRing.init_default(n, q), O.GadgetParametersRing.init_default(n, q)
+    psf = T.PSFGPVRing(gp, 100.0, 1.005)
+    a_bar = rng.integers(0, q, n, dtype=np.int64)
+    r = rng.integers(-3, 4, (gp.k, n)).astype(np.int32)
+    e = rng.integers(-3, 4, (gp.k, n)).astype(np.int32)
+    a = psf.gen_trapdoor_ring_lwe(a_bar, r, e)
+    got = psf.gen_short_basis_for_trapdoor_ring(a, r, e)
+    assert np.array_equal(got, gadget.ring_short_basis_embedded(gp, a, r, e))
+    want = O.coeff_embed(O.gen_short_basis_for_trapdoor_ring(po, a.tolist(), r.tolist(), e.tolist()), n)
+    assert got.tolist() == want
+    # rot^-(a) * basis = 0 mod q: the columns lie in the kernel lattice (short_basis_ring.rs:183-341)
+    rot_a = np.hstack([gadget.rot_minus(a[c]) for c in range(gp.k + 2)]).astype(object)
+    assert not ((rot_a.dot(got.astype(object))) % q).any()
+
 @pytest.mark.parametrize("n,q", [(5, 2**31 - 1 - 57), (6, 2**31 - 1), (8, 1024), (64, 3329)])
 def test_ring_samp_p_preimage_and_domain(T, n, q):
     gp = T.GadgetParametersRing.init_default(n, q)

@@ -1371,6 +1371,86 @@ qf_status qf_set_trapdoor_perturbation(qf_ctx* ctx, const int8_t* r, const doubl
     return QF_OK;
 }
 
+// gen_short_basis_for_trapdoor_ring (short_basis_ring.rs:64-166) in the coefficient embedding: D x D, D = n (k + 2),
+// row = polynomial row * n + coefficient, column = basis vector.  sa_l * sa_r reduced by X^n + 1:
+//   column i k + c (i < n, c < k)   = X^i [ sum_j e_j s'_jc ; sum_j r_j s'_jc ; s'_0c ; ... ; s'_{k-1,c} ]
+//   column n k + 2 i + c (c = 0, 1) = X^i [ sum_j e_j w_cj + (c == 0) ; sum_j r_j w_cj + (c == 1) ; w_c0 ; ... ; w_c,k-1 ]
+// with w_c = base-b digit polynomials of -a_c (a_0 = 1, a_1 = a_bar) and s' = S_k (columns reversed iff base^k = q).
+// The polynomial products and sums run on the device; the host only places X^i-rotations (rot^-, rotation_matrix.rs:41-63).
+qf_status qf_ring_gen_short_basis(qf_ctx* ctx, const int32_t* r, const int32_t* e, int64_t* s_out) {
+    if (!ctx || !r || !e || !s_out) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "not a ring context");
+    if (!ctx->has_ring) return ctx->fail(QF_ERR_NO_KEY, "install the ring key first (qf_ring_set_a / qf_ring_trap_gen_from)");
+    CK(cudaSetDevice(ctx->device));
+    const long n = ctx->n, k = ctx->k, D = n * (k + 2);
+    const uint64_t q = ctx->prm.q, base = (uint64_t)ctx->prm.base;
+    u128 pw = 1;
+    for (long i = 0; i < k; ++i) pw *= base;
+    if (pw < q) return ctx->fail(QF_ERR_INVALID, "base^k < q");
+    const bool exact_pow = pw == (u128)q;
+    // S_k (gadget_classical.rs:248-272), columns reversed when base^k == q (short_basis_ring.rs, as the classical :80-82)
+    std::vector<int64_t> sk0((size_t)k * k, 0), sk((size_t)k * k, 0);
+    for (long j = 0; j < k; ++j) sk0[j * k + j] = (int64_t)base;
+    for (long i = 0; i + 1 < k; ++i) sk0[(i + 1) * k + i] = -1;
+    if (!exact_pow) {
+        uint64_t qq = q;
+        for (long i = 0; i < k; ++i) { sk0[i * k + (k - 1)] = (int64_t)(qq % base); qq /= base; }
+    }
+    for (long j = 0; j < k; ++j)
+        for (long c = 0; c < k; ++c) sk[j * k + c] = sk0[j * k + (exact_pow ? k - 1 - c : c)];
+    // w[c][j][t] = digit j of coefficient t of -a_c mod q
+    std::vector<int32_t> w((size_t)2 * k * n);
+    for (long c = 0; c < 2; ++c)
+        for (long t = 0; t < n; ++t) {
+            uint64_t v = (q - (uint64_t)ctx->hAring[(size_t)c * n + t]) % q;
+            for (long j = 0; j < k; ++j) { w[((size_t)c * k + j) * n + t] = (int32_t)(v % base); v /= base; }
+        }
+    Dev dE, dR, dW, dSk, dP, dQ;
+    CK(dE.ensure((size_t)k * n * 4)); CK(dR.ensure((size_t)k * n * 4)); CK(dW.ensure(w.size() * 4)); CK(dSk.ensure(sk.size() * 8));
+    CK(dP.ensure((size_t)4 * n * 8)); CK(dQ.ensure((size_t)2 * k * n * 8));
+    CK(cudaMemcpyAsync(dE.p, e, (size_t)k * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dR.p, r, (size_t)k * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dW.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dSk.p, sk.data(), sk.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(qf_launch_ring_basis_polys(dE.as<int32_t>(), dR.as<int32_t>(), dW.as<int32_t>(), dSk.as<int64_t>(), (int)n, (int)k,
+                                      dP.as<int64_t>(), dQ.as<int64_t>(), ctx->stream));
+    std::vector<int64_t> P((size_t)4 * n), Q((size_t)2 * k * n);
+    CK(cudaMemcpyAsync(P.data(), dP.p, P.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(Q.data(), dQ.p, Q.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // placement: entry (t, i) of rot^-(p) = coefficient t of p X^i = p[t - i] (t >= i) or -p[n + t - i]
+    auto rot = [&](const int64_t* p, long t, long i) -> int64_t { return t >= i ? p[t - i] : -p[n + t - i]; };
+    std::fill(s_out, s_out + (size_t)D * D, (int64_t)0);
+    for (long i = 0; i < n; ++i) {
+        for (long c = 0; c < k; ++c) {
+            const long col = i * k + c;
+            const int64_t* qe = &Q[((size_t)c * 2 + 0) * n];
+            const int64_t* qr = &Q[((size_t)c * 2 + 1) * n];
+            for (long t = 0; t < n; ++t) {
+                s_out[(size_t)t * D + col] = rot(qe, t, i);
+                s_out[(size_t)(n + t) * D + col] = rot(qr, t, i);
+            }
+            for (long j = 0; j < k; ++j)
+                if (sk[j * k + c]) s_out[(size_t)((2 + j) * n + i) * D + col] = sk[j * k + c];
+        }
+        for (long c = 0; c < 2; ++c) {
+            const long col = n * k + 2 * i + c;
+            const int64_t* pe = &P[((size_t)c * 2 + 0) * n];
+            const int64_t* pr = &P[((size_t)c * 2 + 1) * n];
+            for (long t = 0; t < n; ++t) {
+                s_out[(size_t)t * D + col] = rot(pe, t, i) + ((c == 0 && t == i) ? 1 : 0);
+                s_out[(size_t)(n + t) * D + col] = rot(pr, t, i) + ((c == 1 && t == i) ? 1 : 0);
+            }
+            std::vector<int64_t> wp(n);
+            for (long j = 0; j < k; ++j) {
+                for (long t = 0; t < n; ++t) wp[t] = w[((size_t)c * k + j) * n + t];
+                for (long t = 0; t < n; ++t) s_out[(size_t)((2 + j) * n + t) * D + col] = rot(wp.data(), t, i);
+            }
+        }
+    }
+    return QF_OK;
+}
+
 qf_status qf_gen_short_basis(qf_ctx* ctx, const int8_t* r, int64_t* s_out) {
     if (!ctx || !r || !s_out) return QF_ERR_INVALID;
     if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "ring context: the ring short basis is built by the host shim");

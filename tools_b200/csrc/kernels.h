@@ -203,6 +203,10 @@ cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long
 cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int fs_last, int ss_last, int L,
                                     double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
 
+// polynomial arithmetic of the ring short basis (setup.cu): P[2][2][n], Q[k][2][n]
+cudaError_t qf_launch_ring_basis_polys(const int32_t* e, const int32_t* r, const int32_t* w, const int64_t* sk, int n, int k,
+                                       int64_t* P, int64_t* Q, cudaStream_t stream);
+
 // ---- ring_small.cu : register/shuffle NTT mod q for NTT-friendly primes q < 2^16 ----------------
 #ifdef __cplusplus
 #include <vector>

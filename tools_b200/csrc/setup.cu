@@ -357,3 +357,41 @@ cudaError_t qf_launch_scale_cols(const double* in, long ldin, double* out, long 
     scale_cols_kernel<<<148 * 8, 256, 0, stream>>>(in, ldin, out, ldout, rows, cols, colscale);
     return cudaGetLastError();
 }
+
+// ---- ring short basis (short_basis_ring.rs:64-166): the polynomial arithmetic of gen_short_basis_for_trapdoor_ring ----
+// P[c][h] = sum_j x^h_j * w_cj mod (X^n + 1)  (c = 0, 1: the digit polynomials of -a_c; h = 0: x = e, h = 1: x = r) and
+// Q[c'][h] = sum_j S_k[j][c'] x^h_j  (c' < k).  One CTA per output polynomial, one thread per coefficient.
+namespace {
+__global__ void ring_basis_polys_kernel(const int32_t* __restrict__ e, const int32_t* __restrict__ r,
+                                        const int32_t* __restrict__ w, const int64_t* __restrict__ sk, int n, int k,
+                                        int64_t* __restrict__ P, int64_t* __restrict__ Q) {
+    const int o = blockIdx.x;  // 0..3: P[c][h]; 4..: Q[c'][h]
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        long long acc = 0;
+        if (o < 4) {
+            const int c = o >> 1, h = o & 1;
+            const int32_t* x = h ? r : e;
+            for (int j = 0; j < k; ++j) {
+                const int32_t* xj = x + (long)j * n;
+                const int32_t* wj = w + ((long)c * k + j) * n;
+                for (int i = 0; i < n; ++i) {  // coefficient t of x_j * w_cj: x_j[i] w_cj[t - i], sign flips on wrap-around
+                    const int d = t - i;
+                    acc += d >= 0 ? (long long)xj[i] * wj[d] : -(long long)xj[i] * wj[d + n];
+                }
+            }
+            P[(long)o * n + t] = acc;
+        } else {
+            const int cc = (o - 4) >> 1, h = (o - 4) & 1;
+            const int32_t* x = h ? r : e;
+            for (int j = 0; j < k; ++j) acc += sk[(long)j * k + cc] * (long long)x[(long)j * n + t];
+            Q[(long)(o - 4) * n + t] = acc;
+        }
+    }
+}
+}  // namespace
+
+cudaError_t qf_launch_ring_basis_polys(const int32_t* e, const int32_t* r, const int32_t* w, const int64_t* sk, int n, int k,
+                                       int64_t* P, int64_t* Q, cudaStream_t stream) {
+    ring_basis_polys_kernel<<<4 + 2 * k, 256, 0, stream>>>(e, r, w, sk, n, k, P, Q);
+    return cudaGetLastError();
+}

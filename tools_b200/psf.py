@@ -308,10 +308,22 @@ class PSFGPVRing(_PSFBase):
     def _install_td(self, a, td):
         if self._td_id is not td:
             r, e = td
-            basis = np.ascontiguousarray(
-                gadget.ring_short_basis_embedded(self.gp, np.asarray(a), np.asarray(r), np.asarray(e)), dtype=np.int64)
+            basis = self.gen_short_basis_for_trapdoor_ring(a, r, e)
             self.ctx.call("qf_set_trapdoor_gpv", _ffi.ptr(basis), None)  # GSO computed on the device
             self._td_id = td
+
+    def gen_short_basis_for_trapdoor_ring(self, a, r, e) -> np.ndarray:
+        """short_basis_ring.rs:64-166 in the coefficient embedding (D x D, D = n (k + 2), columns = basis vectors), built by
+        the library (`qf_ring_gen_short_basis`: polynomial products on the device) for the key `a` and the trapdoor (r, e)."""
+        gp = self.gp
+        self._install_a(a)
+        rr = np.ascontiguousarray(r, dtype=np.int32)
+        ee = np.ascontiguousarray(e, dtype=np.int32)
+        assert rr.shape == (gp.k, gp.n) and ee.shape == (gp.k, gp.n)
+        d = gp.n * (gp.k + 2)
+        basis = np.empty((d, d), dtype=np.int64)
+        self.ctx.call("qf_ring_gen_short_basis", _ffi.ptr(rr), _ffi.ptr(ee), _ffi.ptr(basis))
+        return basis
 
     def trap_gen(self, seed=None):
         """gpv_ring.rs:91-98 -> gen_trapdoor_ring_lwe (gadget_ring.rs:62-81):
