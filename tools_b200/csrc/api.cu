@@ -363,10 +363,10 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
     const long ldm = ctx->ld_dim, ldn = ctx->ld_n;
     if (ctx->use_i8 && ctx->fused_fa && ctx->x_limbs <= 4) {
         // one kernel: sigma (int32) -> digits in shared memory -> tcgen05, norms on the way
-        CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+        CK(ctx->dNorm.ensure((size_t)std::max<int64_t>(ctx->chunk, Bc) * 8));
         int64_t* out = dU;
         if (!out) {  // check_domain only: the contraction still runs (cheap), into scratch
-            CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
+            CK(ctx->w[1].ensure((size_t)std::max<int64_t>(ctx->chunk, Bc) * ctx->n * 8));
             out = ctx->w[1].as<int64_t>();
         }
         FaFusedArgs g{};
@@ -466,11 +466,11 @@ qf_status f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uin
 }
 
 qf_status ring_f_a_chunk(qf_ctx* ctx, const int32_t* dSigma, int Bc, int64_t* dU, uint8_t* dFlags) {
-    CK(ctx->dNorm.ensure((size_t)ctx->chunk * 8));
+    CK(ctx->dNorm.ensure((size_t)std::max<int64_t>(ctx->chunk, Bc) * 8));
     const int npoly = (int)(ctx->k + 2);
     int64_t* out = dU;
     if (!out) {
-        CK(ctx->w[1].ensure((size_t)ctx->chunk * ctx->n * 8));
+        CK(ctx->w[1].ensure((size_t)std::max<int64_t>(ctx->chunk, Bc) * ctx->n * 8));
         out = ctx->w[1].as<int64_t>();
     }
     if (ctx->ring_dense && ctx->x_limbs <= 4) {
@@ -1903,12 +1903,21 @@ qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* 
     CK(cudaSetDevice(ctx->device));
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
     if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
-    return for_chunks(ctx, batch, [&](int64_t b0, int Bc) {
+    auto run = [&](int64_t b0, int Bc) {
         const int32_t* s = sigma + b0 * ctx->dim;
         int64_t* u = u_out ? u_out + b0 * ctx->n : nullptr;
         uint8_t* f = in_domain ? in_domain + b0 : nullptr;
         return ring ? ring_f_a_chunk(ctx, s, Bc, u, f) : f_a_chunk(ctx, s, Bc, u, f);
-    });
+    };
+    // The fused kernel needs no per-chunk workspace (8 bytes of norm per target): the whole device-resident batch goes out
+    // as one grid, so only its last wave can be partial (chunks of 16 K targets are 1.7 waves each at n = 256).
+    const bool fused = ctx->x_limbs <= 4 && (ring ? ctx->ring_dense : (ctx->use_i8 && ctx->fused_fa));
+    if (fused) {
+        constexpr int64_t kMax = 1 << 20;
+        for (int64_t b0 = 0; b0 < batch; b0 += kMax) QF_TRY(run(b0, (int)std::min<int64_t>(kMax, batch - b0)));
+        return QF_OK;
+    }
+    return for_chunks(ctx, batch, run);
 }
 
 qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
