@@ -22,7 +22,7 @@
 namespace {
 
 using namespace tc05;
-constexpr int CONV_WARPS = 16, ROWS_PER_WARP = 128 / CONV_WARPS;
+constexpr int CONV_WARPS = 16;
 constexpr int FUSED_THREADS = (CONV_WARPS + 2) * 32;
 constexpr int MAX_LX = 4;
 

@@ -95,7 +95,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // stores through the shared window (32-bit address): no generic-address arithmetic
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v)); }
-__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // ---- thread-block-cluster helpers (CTA pairs that share converted operand tiles through distributed shared memory) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -139,7 +138,6 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
