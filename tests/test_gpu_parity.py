@@ -756,6 +756,34 @@ def test_ring_samp_p_preimage_and_domain(T, n, q):
 # ----------------------------------------------------------------------------------
 
 
+def test_empty_and_single_target_batches(T):
+    """Edge cases of the batch extension: an empty batch is valid (nothing is launched, empty results), a batch of one
+    is what the trait-shaped single-target calls use."""
+    n, q = 8, 64
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, 3.0, 25.0)
+    a, td = psf.trap_gen(seed=1)
+    assert psf.samp_d_batch(0, seed=1).shape == (0, gp.m)
+    u0, f0 = psf.f_a_batch(a, np.zeros((0, gp.m), dtype=np.int32))
+    assert u0.shape == (0, n) and f0.shape == (0,)
+    assert psf.check_domain_batch(np.zeros((0, gp.m), dtype=np.int32)).shape == (0,)
+    assert psf.samp_p_batch(a, td, np.zeros((0, n), dtype=np.int64), seed=2).shape == (0, gp.m)
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, q, (1, n), dtype=np.int64)
+    e1 = psf.samp_p_batch(a, td, u, seed=3)
+    assert e1.shape == (1, gp.m) and np.array_equal(O.f_a_classical_batch(a, e1, q), u)
+    assert np.array_equal(psf.samp_p(a, td, u[0], seed=3), e1[0])  # trait call == batch of one
+    g = T.PSFGPV(gp, 90.0)
+    a2, td2 = g.trap_gen(seed=4)
+    assert g.samp_p_batch(a2, td2, np.zeros((0, n), dtype=np.int64), seed=5).shape == (0, gp.m)
+    gr = T.GadgetParametersRing.init_default(16, 257)
+    pr = T.PSFGPVRing(gr, 300.0, 1.005)
+    ar, tdr = pr.trap_gen(seed=6)
+    assert pr.samp_d_batch(0, seed=7).shape == (0, gr.k + 2, 16)
+    ur, fr = pr.f_a_batch(ar, np.zeros((0, gr.k + 2, 16), dtype=np.int32))
+    assert ur.shape == (0, 16) and fr.shape == (0,)
+
+
 def test_device_entry_points_and_midsize(T):
     import torch
     from tools_b200 import _ffi

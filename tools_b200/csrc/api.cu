@@ -1899,7 +1899,8 @@ qf_status qf_ring_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int32_t
 
 // ---- f_a / check_domain ------------------------------------------------------
 qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
-    if (!ctx || !sigma || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && !sigma)) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;  // an empty batch is valid and does nothing
     CK(cudaSetDevice(ctx->device));
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
     if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
@@ -1921,7 +1922,8 @@ qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* 
 }
 
 qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
-    if (!ctx || !sigma || !u_out || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && (!sigma || !u_out))) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
     if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
@@ -1947,7 +1949,8 @@ qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_ou
 }
 
 qf_status qf_check_domain(qf_ctx* ctx, const int32_t* sigma, int64_t batch, uint8_t* in_domain) {
-    if (!ctx || !sigma || !in_domain || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && (!sigma || !in_domain))) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     const long C = ctx->chunk;
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
@@ -1967,7 +1970,8 @@ qf_status qf_check_domain(qf_ctx* ctx, const int32_t* sigma, int64_t batch, uint
 
 // ---- samp_d ------------------------------------------------------------------
 qf_status qf_samp_d_dev(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first, int32_t* out) {
-    if (!ctx || !out || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && !out)) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
         LAUNCH(qf_launch_dgauss(nullptr, 0, nullptr, 0, out + b0 * ctx->dim, ctx->dim, Bc, (int)ctx->dim, ctx->s_samp_d, seed,
@@ -1977,7 +1981,8 @@ qf_status qf_samp_d_dev(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t firs
 }
 
 qf_status qf_samp_d(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first, int32_t* out) {
-    if (!ctx || !out || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && !out)) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     const long C = ctx->chunk;
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
@@ -2001,7 +2006,8 @@ static qf_status samp_p_ready(qf_ctx* ctx) {
 }
 
 qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
-    if (!ctx || !u || !e_out || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && (!u || !e_out))) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     QF_TRY(samp_p_ready(ctx));
     return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
@@ -2013,7 +2019,8 @@ qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t s
 }
 
 qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
-    if (!ctx || !u || !e_out || batch < 0) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && (!u || !e_out))) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     QF_TRY(samp_p_ready(ctx));
     for (int64_t i = 0; i < batch * ctx->n; ++i)
