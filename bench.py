@@ -108,6 +108,15 @@ def run_reference(args):
     from oracle import oracle_c as OC
     from tools_b200 import gadget  # host-side numpy key setup only (untimed)
 
+    # torchrun exports OMP_NUM_THREADS=1; the (untimed) numpy key setup below would then run its BLAS calls on one
+    # thread.  The timed part uses the C port's own pthreads (OC.threads()) and is not affected.
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
     n, q, desc = WORKLOADS[args.workload]
     gp = gadget.GadgetParameters.init_default(n, q)
     s = gpv_s(gp)
