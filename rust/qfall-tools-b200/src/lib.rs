@@ -13,6 +13,8 @@
 //! This crate is shipped as SOURCE: the image the backend is built in has no Rust toolchain, so it has not been
 //! compiled there.  The `extern "C"` block (ffi.rs) is checked mechanically against include/qfall_b200.h.
 pub mod ffi;
+pub mod perturbation;
+pub use perturbation::PSFPerturbationB200;
 
 use ffi::*;
 use qfall_math::{
@@ -28,7 +30,7 @@ use std::ffi::CStr;
 /// Owner of one `qf_ctx` (device memory, stream, installed key).  Neither `Send` nor `Sync`, like the reference's PSF
 /// structs (gadget_parameters.rs:51): one caller thread per instance.
 pub struct Context {
-    raw: *mut qf_ctx,
+    pub(crate) raw: *mut qf_ctx,
 }
 
 impl Context {
@@ -44,7 +46,7 @@ impl Context {
         unsafe { CStr::from_ptr(qf_last_error(self.raw)) }.to_string_lossy().into_owned()
     }
     /// status -> the reference's failure mode at that call site (`unwrap()` / `assert!`)
-    fn check(&self, st: i32, what: &str) {
+    pub(crate) fn check(&self, st: i32, what: &str) {
         assert!(st == QF_OK, "{what}: status {st}: {}", self.last_error());
     }
 }
