@@ -138,8 +138,12 @@ qf_status qf_ring_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int32_t
 /* ---- PSF::f_a / check_domain ------------------------------------------------ */
 /* u[b] = A * sigma[b] mod q and in_domain[b] = check_domain(sigma[b])
  * (gpv.rs:190-193,219-224; mp_perturbation.rs:366-369,396-402; gpv_ring.rs:243-247,274-283).
- * Returns QF_ERR_NOT_IN_DOMAIN if any flag is 0 (u rows of such targets are unspecified),
- * the shim turns that into the reference's panic.  in_domain may be NULL. */
+ * qf_f_a (host pointers, synchronous) returns QF_ERR_NOT_IN_DOMAIN if any flag is 0 (u rows of such targets are
+ * unspecified); the shim turns that into the reference's panic.  Its in_domain may be NULL.
+ * qf_f_a_dev is asynchronous and therefore cannot return the verdict: it reports domain failures ONLY through
+ * in_domain (device pointer, B bytes), which is mandatory -- NULL is QF_ERR_INVALID, so the assertion of gpv.rs:191
+ * can never be dropped silently.  u_out may be NULL (flags only).
+ * The squared norm is exact and saturating: entries of any int32 magnitude are handled (no 64-bit wrap-around). */
 qf_status qf_f_a(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain);
 qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain);
 qf_status qf_check_domain(qf_ctx* ctx, const int32_t* sigma, int64_t batch, uint8_t* in_domain);
@@ -154,6 +158,13 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
                     int32_t* e_out);
 qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first_index,
                         int32_t* e_out);
+
+/* ---- PSFPerturbation::randomized_nearest_plane_gadget (mp_perturbation.rs:173-191), the public helper samp_p calls:
+ * z[b] = x0 + SampleD(S, S~, -x0, r sqrt(base^2 + 1)) with x0 = find_solution_gadget_mat(v[b]) -- a preimage of v[b]
+ * under the gadget matrix G, Gaussian over the coset Lambda_v^perp(G).  v: B x n residues, z_out: B x (n k).  The gadget
+ * short basis (and its GSO) is the one installed with qf_set_trapdoor_perturbation.  Host pointers. */
+qf_status qf_randomized_nearest_plane_gadget(qf_ctx* ctx, const int64_t* v, int64_t batch, uint64_t seed,
+                                             uint64_t first_index, int32_t* z_out);
 
 /* ---- LossyCompressionFIPS203 (lossy_compression_fips203.rs:89-114, 143-172) ----------- */
 /* Flat coefficient streams (a polynomial / matrix of polynomials is just `count` coefficients).
@@ -181,7 +192,10 @@ qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npol
                                    int device_ptrs, void* cuda_stream);
 
 /* ---- Z::sample_discrete_gauss for a batch of (centre) values (qfall-math SampleZ as used at
- * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers. */
+ * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers, any count.
+ * Value i draws from its own Philox stream (seed, i) under a stream id that no PSF method uses, so equal seeds
+ * here and in qf_samp_d give independent outputs.  s < 2e6 (QF_ERR_UNSUPPORTED above); a NaN / infinite centre
+ * gives QF_ERR_NUMERIC. */
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out);
 
 /* ---- self-test of the tensor-core integer contraction: out = X W^t (mod q if q != 0), exact.

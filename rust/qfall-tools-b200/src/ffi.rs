@@ -66,6 +66,8 @@ extern "C" {
     pub fn qf_samp_p(ctx: *mut qf_ctx, u: *const i64, batch: i64, seed: u64, first_index: u64, e_out: *mut i32) -> i32;
     pub fn qf_samp_p_dev(ctx: *mut qf_ctx, u: *const i64, batch: i64, seed: u64, first_index: u64, e_out: *mut i32) -> i32;
 
+    pub fn qf_randomized_nearest_plane_gadget(ctx: *mut qf_ctx, v: *const i64, batch: i64, seed: u64, first_index: u64, z_out: *mut i32) -> i32;
+
     pub fn qf_compress_u16(input: *const u16, out: *mut u16, count: usize, q: u32, d: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
     pub fn qf_decompress_u16(input: *const u16, out: *mut u16, count: usize, q: u32, d: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
     pub fn qf_compress_i64(input: *const i64, out: *mut i64, count: usize, q: u64, d: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;

@@ -271,6 +271,94 @@ def test_f_a_domain_errors(T):
         psf.f_a_batch(a, sig)
 
 
+@pytest.mark.parametrize("path", ["fused", "unfused_i8", "fp64"])
+def test_check_domain_norm_does_not_wrap(T, path, monkeypatch):
+    """||sigma||^2 is exact (gpv.rs:219-224): a 64-bit sum of int32 squares wraps (16 entries of 2^30 sum to 2^64 = 0,
+    four entries of INT32_MIN likewise), which would report a vector of norm 2^32 as in-domain.  Every norm kernel
+    saturates instead."""
+    if path == "unfused_i8":
+        monkeypatch.setenv("QF_DISABLE_FUSED_FA", "1")
+    elif path == "fp64":
+        monkeypatch.setenv("QF_DISABLE_I8", "1")
+    n, q = 8, 64
+    gp = T.GadgetParameters.init_default(n, q)
+    psf = T.PSFPerturbation(gp, 3.0, 25.0)
+    a, _ = psf.trap_gen(seed=1)
+    sig = psf.samp_d_batch(6, seed=2)
+    sig[1, :16] = 2**30
+    sig[2, 3:7] = -(2**31)
+    sig[3, :64] = 2**29           # 64 * 2^58 = 2^64
+    sig[4, 5] = 2**31 - 1         # a single huge entry (no wrap, plainly out of domain)
+    flags = psf.check_domain_batch(sig)
+    assert flags.tolist() == [True, False, False, False, False, True]
+    u, fl = psf.f_a_batch(a, sig, strict=False)
+    assert fl.tolist() == [True, False, False, False, False, True]
+    assert np.array_equal(u[[0, 5]], O.f_a_classical_batch(a, sig[[0, 5]], q))
+    with pytest.raises(T.NotInDomain):
+        psf.f_a_batch(a, sig)
+    for row in (1, 2, 3, 4):
+        assert not psf.check_domain(sig[row])
+        with pytest.raises(T.NotInDomain):
+            psf.f_a(a, sig[row])
+    # wider-than-int32 inputs must not wrap in the host cast either (2^32 -> 0)
+    big = sig.astype(np.int64)
+    big[0, 0] = 2**32
+    assert psf.check_domain_batch(big).tolist() == [False, False, False, False, False, True]
+    _, fl = psf.f_a_batch(a, big, strict=False)
+    assert fl.tolist() == [False, False, False, False, False, True]
+    obj = sig[:1].astype(object)
+    obj[0, 2] = 2**70
+    assert not psf.check_domain_batch(obj)[0] and not psf.check_domain(obj[0])
+
+
+@pytest.mark.parametrize("path", ["dense", "small_ntt", "goldilocks", "schoolbook"])
+def test_ring_check_domain_norm_does_not_wrap(T, path, monkeypatch):
+    n, q = (64, 3329) if path != "schoolbook" else (6, 128)
+    if path in ("small_ntt", "goldilocks"):
+        monkeypatch.setenv("QF_DISABLE_RING_DENSE", "1")
+    if path == "goldilocks":
+        monkeypatch.setenv("QF_DISABLE_SMALL_NTT", "1")
+    gr = T.GadgetParametersRing.init_default(n, q)
+    pr = T.PSFGPVRing(gr, 300.0, 1.005)
+    a, _ = pr.trap_gen(seed=6)
+    sig = pr.samp_d_batch(4, seed=7)
+    flat = sig.reshape(4, -1)
+    flat[1, :16] = 2**30
+    flat[2, 1:5] = -(2**31)
+    u, fl = pr.f_a_batch(a, sig, strict=False)
+    assert fl.tolist() == [True, False, False, True]
+    assert u[0].tolist() == O.f_a_ring(a.tolist(), sig[0].tolist(), n, q)
+    assert pr.check_domain_batch(sig).tolist() == [True, False, False, True]
+
+
+def test_key_change_invalidates_trapdoor(T):
+    """C ABI contract: installing a new key drops the trapdoor installed for the old one -- samp_p answers QF_ERR_NO_KEY
+    instead of combining the new A with the old A^-1 / pivots / S / R (which would return QF_OK and A e != u)."""
+    from tools_b200 import _ffi
+
+    n, q = 8, 64
+    gp = T.GadgetParameters.init_default(n, q)
+    for make in (lambda: T.PSFGPV(gp, 90.0), lambda: T.PSFPerturbation(gp, 3.0, 25.0)):
+        psf = make()
+        a, td = psf.trap_gen(seed=4)
+        u = np.random.default_rng(1).integers(0, q, (4, n), dtype=np.int64)
+        e = psf.samp_p_batch(a, td, u, seed=5)
+        assert np.array_equal(O.f_a_classical_batch(a, e, q), u)
+        a2 = np.ascontiguousarray(np.roll(a, 1, axis=0))
+        psf.ctx.call("qf_set_a", _ffi.ptr(a2))  # behind the wrapper's back
+        out = np.empty_like(e)
+        st = psf.ctx.status("qf_samp_p", _ffi.ptr(u), 4, 5, 0, _ffi.ptr(out))
+        assert st == _ffi.QF_ERR_NO_KEY
+    gr = T.GadgetParametersRing.init_default(8, 1024)
+    pr = T.PSFGPVRing(gr, 300.0, 1.005)
+    ar, tdr = pr.trap_gen(seed=1)
+    ur = np.random.default_rng(2).integers(0, 1024, (3, 8), dtype=np.int64)
+    er = pr.samp_p_batch(ar, tdr, ur, seed=3)
+    pr.ctx.call("qf_ring_set_a", _ffi.ptr(np.ascontiguousarray(ar)))
+    st = pr.ctx.status("qf_samp_p", _ffi.ptr(ur), 3, 3, 0, _ffi.ptr(np.empty_like(er)))
+    assert st == _ffi.QF_ERR_NO_KEY
+
+
 # ----------------------------------------------------------------------------------
 # samplers: exact law
 # ----------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ SIGNATURES = {
     "qf_samp_d_dev": (_i32, [_vp, _i64, _u64, _u64, _vp]),
     "qf_samp_p": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
     "qf_samp_p_dev": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
+    "qf_randomized_nearest_plane_gadget": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
     "qf_compress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _vp]),
     "qf_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _vp]),
     "qf_compress_i64": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _vp]),

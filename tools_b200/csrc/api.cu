@@ -554,7 +554,7 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
         LAUNCH(ctx_gemm_i8(ctx, g));
     }
     LAUNCH(qf_launch_dgauss(X2, ldm, P, ldm, nullptr, 0, Bc, (int)ctx->m, ctx->prm.r, seed, first, QF_STREAM_PERT_ROUND,
-                            ctx->stream));
+                            ctx->dFlag.as<int>(), ctx->stream));
     // v = u - A p   (:318)
     if (ctx->use_i8) {
         const long ldk = ctx->ldk_dim, plane = C * ldk;
@@ -585,7 +585,8 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
     // z <- D_{Lambda_v^perp(G), r sqrt(b^2+1)}   (:321-326 -> :173-191)
     const double s_g = ctx->prm.r * std::sqrt((double)(ctx->prm.base * ctx->prm.base + 1));
     LAUNCH(qf_launch_gadget_sample(V, ctx->n, Z, ldnk, Bc, (int)ctx->n, (int)ctx->k, (int)ctx->prm.base, ctx->prm.q,
-                                   ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed, first, ctx->stream));
+                                   ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed, first, ctx->dFlag.as<int>(),
+                                   ctx->stream));
     // e = p + [R; I] z   (:328-335): top block accumulates R z into p in place (exact small integers)
     if (ctx->use_i8) {
         const long ldk = ctx->ldk_nk, plane = C * ldk;
@@ -1175,6 +1176,9 @@ qf_status for_chunks(qf_ctx* ctx, int64_t batch, F&& f) {
 
 qf_status install_a(qf_ctx* ctx, const int64_t* a) {
     if (ctx->prm.kind == QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "qf_set_a on a ring context; use qf_ring_set_a");
+    // a new key invalidates whatever trapdoor was installed for the old one: samp_p answers QF_ERR_NO_KEY until the
+    // trapdoor is installed again (never a preimage of the new A computed from the old A^-1, pivots, S and R)
+    ctx->has_a = false; ctx->has_np = false; ctx->has_pert = false;
     const long n = ctx->n, m = ctx->m;
     for (long i = 0; i < n * m; ++i)
         if (a[i] < 0 || (uint64_t)a[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "A entry outside [0,q)");
@@ -1567,6 +1571,7 @@ qf_status qf_gso(qf_ctx* ctx, const int64_t* s, double* gso_out) {
 qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     if (!ctx || !s) return QF_ERR_INVALID;
     if (ctx->prm.kind == QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a GPV context");
+    ctx->has_np = false;  // stays false if anything below fails half-way (pivots / A^-1 / U are overwritten in place)
     CK(cudaSetDevice(ctx->device));
     const long D = ctx->dim, ld = ctx->ld_dim;
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
@@ -1679,6 +1684,7 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
 qf_status qf_ring_set_a(qf_ctx* ctx, const int64_t* a) {
     if (!ctx || !a) return QF_ERR_INVALID;
     if (ctx->prm.kind != QF_PSF_GPV_RING) return ctx->fail(QF_ERR_INVALID, "not a ring context");
+    ctx->has_ring = false; ctx->has_np = false;  // a new key invalidates the installed trapdoor
     CK(cudaSetDevice(ctx->device));
     const long n = ctx->n, np = ctx->k + 2;
     for (long i = 0; i < n * np; ++i)
@@ -1899,7 +1905,7 @@ qf_status qf_ring_trap_gen_from(qf_ctx* ctx, const int64_t* a_bar, const int32_t
 
 // ---- f_a / check_domain ------------------------------------------------------
 qf_status qf_f_a_dev(qf_ctx* ctx, const int32_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
-    if (!ctx || batch < 0 || (batch > 0 && !sigma)) return QF_ERR_INVALID;
+    if (!ctx || batch < 0 || (batch > 0 && (!sigma || !in_domain))) return QF_ERR_INVALID;
     if (batch == 0) return QF_OK;  // an empty batch is valid and does nothing
     CK(cudaSetDevice(ctx->device));
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
@@ -1975,7 +1981,7 @@ qf_status qf_samp_d_dev(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t firs
     CK(cudaSetDevice(ctx->device));
     return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
         LAUNCH(qf_launch_dgauss(nullptr, 0, nullptr, 0, out + b0 * ctx->dim, ctx->dim, Bc, (int)ctx->dim, ctx->s_samp_d, seed,
-                                first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->stream));
+                                first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->dFlag.as<int>(), ctx->stream));
         return QF_OK;
     });
 }
@@ -1988,7 +1994,7 @@ qf_status qf_samp_d(qf_ctx* ctx, int64_t batch, uint64_t seed, uint64_t first, i
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
     return for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
         LAUNCH(qf_launch_dgauss(nullptr, 0, nullptr, 0, ctx->io_a.as<int32_t>(), ctx->dim, Bc, (int)ctx->dim, ctx->s_samp_d,
-                                seed, first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->stream));
+                                seed, first + (uint64_t)b0, QF_STREAM_SAMP_D, ctx->dFlag.as<int>(), ctx->stream));
         CK(cudaMemcpyAsync(out + b0 * ctx->dim, ctx->io_a.p, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return QF_OK;
@@ -2063,6 +2069,35 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
         return QF_OK;
     }));
     if (overlap) CK(cudaStreamSynchronize(ctx->copy_stream));
+    return check_flag(ctx);
+}
+
+// ---- PSFPerturbation::randomized_nearest_plane_gadget (mp_perturbation.rs:173-191) ----------------------------
+qf_status qf_randomized_nearest_plane_gadget(qf_ctx* ctx, const int64_t* v, int64_t batch, uint64_t seed, uint64_t first,
+                                             int32_t* z_out) {
+    if (!ctx || batch < 0 || (batch > 0 && (!v || !z_out))) return QF_ERR_INVALID;
+    if (ctx->prm.kind != QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a PSFPerturbation context");
+    if (!ctx->has_pert) return ctx->fail(QF_ERR_NO_KEY, "PSFPerturbation: trapdoor missing (gadget short basis)");
+    if (batch == 0) return QF_OK;
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t i = 0; i < batch * ctx->n; ++i)
+        if (v[i] < 0 || (uint64_t)v[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "syndrome entry outside [0,q)");
+    const long C = ctx->chunk, ldnk = ctx->ld_nk;
+    CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    CK(ctx->w[3].ensure((size_t)C * ldnk * 8));
+    const double s_g = ctx->prm.r * std::sqrt((double)(ctx->prm.base * ctx->prm.base + 1));
+    QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        CK(cudaMemcpyAsync(ctx->io_b.p, v + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(qf_launch_gadget_sample(ctx->io_b.as<int64_t>(), ctx->n, ctx->w[3].as<double>(), ldnk, Bc, (int)ctx->n, (int)ctx->k,
+                                       (int)ctx->prm.base, ctx->prm.q, ctx->dSk.as<double>(), ctx->dSkGso.as<double>(), s_g, seed,
+                                       first + (uint64_t)b0, ctx->dFlag.as<int>(), ctx->stream));
+        LAUNCH(qf_launch_f64_to_i32(ctx->w[3].as<double>(), ldnk, ctx->io_a.as<int32_t>(), ctx->nk, Bc, (int)ctx->nk,
+                                    ctx->dFlag.as<int>(), ctx->stream));
+        CK(cudaMemcpyAsync(z_out + b0 * ctx->nk, ctx->io_a.p, (size_t)Bc * ctx->nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    }));
     return check_flag(ctx);
 }
 
@@ -2153,21 +2188,34 @@ qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npol
 
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out) {
     if (!centers || !out || !(s > 0)) return QF_ERR_INVALID;
+    if (!(s < 2.0e6)) return QF_ERR_UNSUPPORTED;  // proposals are rounded in fp32: 7.6 sigma' must stay below 2^24
     if (count == 0) return QF_OK;
+    // one "target" per value so that every value owns its Philox stream (its own stream id: qf_samp_d with the same
+    // seed draws from QF_STREAM_SAMP_D); slabs of 2^24 values bound the device buffers and the int launch arguments
+    const size_t slab = (size_t)1 << 24, cap = count < slab ? count : slab;
     double *dc = nullptr, *dz = nullptr;
-    if (cudaMalloc(&dc, count * 8) != cudaSuccess) return QF_ERR_CUDA;
-    if (cudaMalloc(&dz, count * 8) != cudaSuccess) { cudaFree(dc); return QF_ERR_CUDA; }
-    qf_status rc = QF_OK;
-    std::vector<double> hz(count);
-    if (cudaMemcpy(dc, centers, count * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = QF_ERR_CUDA;
-    // one "target" per value so that every value owns its Philox stream
-    if (rc == QF_OK && qf_launch_dgauss(dc, 1, dz, 1, nullptr, 0, (int)count, 1, s, seed, 0, QF_STREAM_SAMP_D, nullptr) != cudaSuccess)
-        rc = QF_ERR_CUDA;
-    if (rc == QF_OK && cudaMemcpy(hz.data(), dz, count * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
-    if (rc == QF_OK)
-        for (size_t i = 0; i < count; ++i) out[i] = (int64_t)hz[i];
+    int* dflag = nullptr;
+    if (cudaMalloc(&dc, cap * 8) != cudaSuccess) return QF_ERR_CUDA;
+    if (cudaMalloc(&dz, cap * 8) != cudaSuccess) { cudaFree(dc); return QF_ERR_CUDA; }
+    if (cudaMalloc(&dflag, sizeof(int)) != cudaSuccess) { cudaFree(dc); cudaFree(dz); return QF_ERR_CUDA; }
+    qf_status rc = cudaMemset(dflag, 0, sizeof(int)) == cudaSuccess ? QF_OK : QF_ERR_CUDA;
+    std::vector<double> hz(cap);
+    for (size_t o = 0; o < count && rc == QF_OK; o += slab) {
+        const size_t cnt = count - o < slab ? count - o : slab;
+        if (cudaMemcpy(dc, centers + o, cnt * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = QF_ERR_CUDA;
+        if (rc == QF_OK && qf_launch_dgauss(dc, 1, dz, 1, nullptr, 0, (int)cnt, 1, s, seed, (uint64_t)o, QF_STREAM_SAMPLE_Z, dflag,
+                                            nullptr) != cudaSuccess)
+            rc = QF_ERR_CUDA;
+        if (rc == QF_OK && cudaMemcpy(hz.data(), dz, cnt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
+        if (rc == QF_OK)
+            for (size_t i = 0; i < cnt; ++i) out[o + i] = (int64_t)hz[i];
+    }
+    int hflag = 0;
+    if (rc == QF_OK && cudaMemcpy(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (rc == QF_OK && hflag) rc = QF_ERR_NUMERIC;  // a centre was NaN / infinite: the sampler gave up (common.cuh)
     cudaFree(dc);
     cudaFree(dz);
+    cudaFree(dflag);
     return rc;
 }
 

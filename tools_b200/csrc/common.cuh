@@ -23,6 +23,9 @@
 #define QF_STREAM_UNIFORM 6u
 #define QF_STREAM_TERNARY 7u
 #define QF_STREAM_RING_TD 8u
+#define QF_STREAM_SAMPLE_Z 9u
+// bits of the per-context numeric flag (qf_synchronize / qf_samp_p report QF_ERR_NUMERIC when any is set)
+#define QF_FLAG_DGAUSS_BAILOUT 16
 
 struct Philox {
     uint32_t k0, k1;
@@ -64,8 +67,10 @@ struct Philox {
     // two independent N(0,1) (Box-Muller), consumes 2 words
     __device__ __forceinline__ void normal2(float& n0, float& n1) {
         uint32_t b0 = next(), b1 = next();
-        // u in (0,1]: 2^-33 .. 1 (rounds to 1.0f at the top, log -> 0)
-        float u = __uint2float_rn(b0) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+        // u in (0,1]: 40 bits = b0 and the low byte of b1 (the angle below keeps 24 bits of b1 after rounding, so that
+        // byte is otherwise unused): u >= 2^-41, i.e. |n| reaches sqrt(82 ln 2) = 7.54 (a 32-bit u stops at 6.76).
+        // The reference's support is 6 s = 15 sigma; the mass this proposal cannot reach is 4.7e-14 per draw.
+        float u = fmaf(__uint2float_rn(b0), 2.3283064365386963e-10f, ((float)(b1 & 255u) + 0.5f) * 9.094947017729282e-13f);
         float rad = sqrtf(-2.0f * logf(u));
         float ang = __uint2float_rn(b1) * 4.6566128730773926e-10f;  // [0,2) in units of pi
         float s, c;
@@ -110,7 +115,9 @@ __host__ __device__ inline DGaussParams make_dgauss(double s) {
 }
 
 // Returns the sample as a double (exact integer value; centers may exceed 2^31).
-__device__ __forceinline__ double sample_dgauss(const DGaussParams& p, double center, Philox& rng) {
+// flag (optional): device int, QF_FLAG_DGAUSS_BAILOUT is ORed in if 4096 rounds (8192 proposals) were all rejected --
+// probability < 0.4^8192 for valid parameters, so in practice it signals corrupt parameters (NaN centre / width).
+__device__ __forceinline__ double sample_dgauss(const DGaussParams& p, double center, Philox& rng, int* flag = nullptr) {
     double c_int = rint(center);
     float c_frac = (float)(center - c_int);
     for (int it = 0; it < 4096; ++it) {
@@ -130,8 +137,46 @@ __device__ __forceinline__ double sample_dgauss(const DGaussParams& p, double ce
             if (fabsf(d) <= p.tail && __logf(u1) < e) return c_int + (double)x;
         }
     }
-    return c_int;  // unreachable in practice (acceptance >= 0.6 per trial)
+    if (flag) atomicOr(flag, QF_FLAG_DGAUSS_BAILOUT);
+    return c_int;
 }
+
+// ---------------------------------------------------------------------------
+// Squared Euclidean norm of int32 entries for check_domain (gpv.rs:219-224), exact and SATURATING: a square is
+// at most 2^62, so a plain u64 sum wraps after four such entries (16 entries of 2^30 sum to 2^64 = 0, which would
+// pass every bound).  96-bit accumulator (64-bit sum + carry count); value() is the exact sum, or 2^64 - 1 when it
+// does not fit 64 bits (above every admissible bound, which is < 2^62).
+// ---------------------------------------------------------------------------
+struct NormAcc {
+    unsigned long long lo;
+    unsigned int hi;
+    __device__ __forceinline__ void clear() { lo = 0; hi = 0; }
+    __device__ __forceinline__ void add(unsigned long long x) {
+        asm("{\n\t.reg .u32 l0, l1, x0, x1;\n\t"
+            "mov.b64 {l0, l1}, %0;\n\tmov.b64 {x0, x1}, %2;\n\t"
+            "add.cc.u32 l0, l0, x0;\n\taddc.cc.u32 l1, l1, x1;\n\taddc.u32 %1, %1, 0;\n\t"
+            "mov.b64 %0, {l0, l1};\n\t}"
+            : "+l"(lo), "+r"(hi) : "l"(x));
+    }
+    __device__ __forceinline__ void add_sq(int v) { const long long w = v; add((unsigned long long)(w * w)); }
+    // squares of four int32 values: the two pair sums are <= 2^63 each and cannot wrap
+    __device__ __forceinline__ void add_sq4(int a, int b, int c, int d) {
+        const long long la = a, lb = b, lc = c, ld = d;
+        add((unsigned long long)(la * la) + (unsigned long long)(lb * lb));
+        add((unsigned long long)(lc * lc) + (unsigned long long)(ld * ld));
+    }
+    __device__ __forceinline__ void merge(const NormAcc& o) { add(o.lo); hi += o.hi; }
+    __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            NormAcc t;
+            t.lo = __shfl_xor_sync(0xffffffffu, lo, o);
+            t.hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            merge(t);
+        }
+    }
+    __device__ __forceinline__ unsigned long long value() const { return hi ? ~0ull : lo; }
+};
 
 // ---------------------------------------------------------------------------
 // modular arithmetic helpers, q < 2^62

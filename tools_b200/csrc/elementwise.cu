@@ -24,17 +24,16 @@ __global__ void i32_to_f64_kernel(const int32_t* __restrict__ in, long ldin, dou
          b += (long)gridDim.x * warps_per_block) {
         const int32_t* src = in + b * ldin;
         double* dst = out + b * ldout;
-        unsigned long long acc = 0;
+        NormAcc acc;
+        acc.clear();
         for (int j = lane; j < M; j += 32) {
             int32_t v = src[j];
             dst[j] = (double)v;
-            long long w = v;
-            acc += (unsigned long long)(w * w);
+            acc.add_sq(v);
         }
         if (norm2) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) norm2[b] = acc;
+            acc.warp_reduce();
+            if (lane == 0) norm2[b] = acc.value();
         }
     }
 }
@@ -187,7 +186,7 @@ __global__ void normal_fill_kernel(double* __restrict__ out, long ld, int B, int
 
 __global__ void dgauss_kernel(const double* __restrict__ center, long ldc, double* __restrict__ out_f64, long ldo,
                               int32_t* __restrict__ out_i32, long ldoi, int B, int M, DGaussParams dg,
-                              uint64_t seed, uint64_t first_target, uint32_t tag) {
+                              uint64_t seed, uint64_t first_target, uint32_t tag, int* flag) {
     long total = (long)B * M;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         long b = i / M;
@@ -195,7 +194,7 @@ __global__ void dgauss_kernel(const double* __restrict__ center, long ldc, doubl
         Philox rng;
         rng.init(seed, (first_target + (uint64_t)b) * (uint64_t)M + (uint64_t)j, tag);
         double c = center ? center[b * ldc + j] : 0.0;
-        double z = sample_dgauss(dg, c, rng);
+        double z = sample_dgauss(dg, c, rng, flag);
         if (out_f64) out_f64[b * ldo + j] = z;
         if (out_i32) out_i32[b * ldoi + j] = (int32_t)z;
     }
@@ -311,12 +310,12 @@ cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t s
     return cudaGetLastError();
 }
 cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32, long ldoi,
-                             int B, int M, double s, uint64_t seed, uint64_t first_target, uint32_t tag,
+                             int B, int M, double s, uint64_t seed, uint64_t first_target, uint32_t tag, int* flag,
                              cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     DGaussParams dg = make_dgauss(s);
     dgauss_kernel<<<grid_for((long long)B * M, TPB), TPB, 0, stream>>>(center, ldc, out_f64, ldo, out_i32, ldoi, B, M,
-                                                                      dg, seed, first_target, tag);
+                                                                      dg, seed, first_target, tag, flag);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_uniform_modq(int64_t* out, long count, unsigned long long q, uint64_t seed,
@@ -459,7 +458,8 @@ split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __rest
     const int iters = (M + 127) >> 7;
     for (long b = (long)blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += (long)gridDim.x * wpb) {
         const int32_t* src = in + b * ldin;
-        unsigned long long acc = 0;
+        NormAcc acc;
+        acc.clear();
         const long nz_plane = (long)nz_m_tiles * nz_kb_total, nz_row = (b >> 7) * nz_kb_total;
         int it = 0;
         // two 128-column tiles per trip: both vector loads are issued before either is consumed
@@ -468,9 +468,8 @@ split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __rest
             const int4 q0 = __ldcs(reinterpret_cast<const int4*>(src + j0));
             const int4 q1 = __ldcs(reinterpret_cast<const int4*>(src + j1));
             const int v0[4] = {q0.x, q0.y, q0.z, q0.w}, v1[4] = {q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                acc += (unsigned long long)((long long)v0[t] * v0[t]) + (unsigned long long)((long long)v1[t] * v1[t]);
+            acc.add_sq4(v0[0], v0[1], v0[2], v0[3]);
+            acc.add_sq4(v1[0], v1[1], v1[2], v1[3]);
             split4_i32(v0, L, planes, plane_stride, b * ldk + j0, nz, nz_plane, nz_row + (j0 >> 7), 4, lane);
             split4_i32(v1, L, planes, plane_stride, b * ldk + j1, nz, nz_plane, nz_row + (j1 >> 7), 4, lane);
         }
@@ -479,14 +478,12 @@ split_i32_limbs_kernel(const int32_t* __restrict__ in, long ldin, int8_t* __rest
             const int valid = max(0, min(4, M - j));
             int v[4] = {0, 0, 0, 0};
             for (int t = 0; t < valid; ++t) v[t] = src[j + t];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) acc += (unsigned long long)((long long)v[t] * v[t]);
+            acc.add_sq4(v[0], v[1], v[2], v[3]);
             split4_i32(v, L, planes, plane_stride, b * ldk + j, nz, nz_plane, nz_row + (j >> 7), valid, lane);
         }
         if (norm2) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) norm2[b] = acc;
+            acc.warp_reduce();
+            if (lane == 0) norm2[b] = acc.value();
         }
     }
 }

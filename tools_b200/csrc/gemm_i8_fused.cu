@@ -183,9 +183,9 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         constexpr int U = 8 / R;         // k blocks per register buffer
         const int rb = (int)crank * (TILE_M / 2) * (PAIR ? 1 : 0) + warp * R;  // first row (within the tile) of this warp
         const bool do_norm = p.norm2 != nullptr && (PAIR || tile_n == 0);
-        unsigned long long acc[R];
+        NormAcc acc[R];  // saturating: a plain u64 sum of int32 squares wraps (common.cuh)
 #pragma unroll
-        for (int i = 0; i < R; ++i) acc[i] = 0;
+        for (int i = 0; i < R; ++i) acc[i].clear();
         const int32_t* xrow = p.x + ((long)m0 + rb) * p.ldx + lane * 4;
         const int rows_here = max(0, min(R, p.B - (m0 + rb)));
         // fast path: all rows of this warp exist and are 16-byte aligned -> unpredicated 128-bit loads
@@ -245,8 +245,7 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
                     const int w0 = buf[u * R + i].x, w1 = buf[u * R + i].y, w2 = buf[u * R + i].z, w3 = buf[u * R + i].w;
-                    acc[i] += (unsigned long long)((long long)w0 * w0) + (unsigned long long)((long long)w1 * w1) +
-                              (unsigned long long)((long long)w2 * w2) + (unsigned long long)((long long)w3 * w3);
+                    acc[i].add_sq4(w0, w1, w2, w3);
                 }
             }
 #pragma unroll
@@ -322,11 +321,10 @@ f_a_fused_kernel(const __grid_constant__ CUtensorMap map_w, FusedParams p) {
         if (do_norm) {
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                unsigned long long a = acc[i];
-#pragma unroll
-                for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                NormAcc a = acc[i];
+                a.warp_reduce();
                 const long grow = (long)m0 + rb + i;
-                if (lane == 0 && grow < p.B) p.norm2[grow] = a;
+                if (lane == 0 && grow < p.B) p.norm2[grow] = a.value();
             }
         }
         const long long t_epi = timed ? clock64() : 0;

@@ -51,10 +51,10 @@ cudaError_t qf_launch_scatter_cols_f64(const double* src, long ldsrc, const int*
 // ---- samplers (elementwise.cu) -------------------------------------------
 cudaError_t qf_launch_normal_fill(double* out, long ld, int B, int M, uint64_t seed, uint64_t first_target,
                                   uint32_t tag, cudaStream_t stream);
-// out[b][j] <- D_{Z, s, center[b][j]} (center == nullptr: centred at 0)
+// out[b][j] <- D_{Z, s, center[b][j]} (center == nullptr: centred at 0); flag (optional): sampler bail-out bit
 cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, long ldo, int32_t* out_i32,
                              long ldoi, int B, int M, double s, uint64_t seed, uint64_t first_target,
-                             uint32_t tag, cudaStream_t stream);
+                             uint32_t tag, int* flag, cudaStream_t stream);
 // structured e = S z for the G-trapdoor short basis S = [[R S', I + R W],[S', W]] (api.cu detect_gpv_structure)
 cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long ldi, int B, int nk, int k, const double* sk,
                                    int reversed, cudaStream_t stream);
@@ -82,7 +82,7 @@ cudaError_t qf_launch_ternary(int8_t* out, long count, uint64_t seed, cudaStream
 // sk: k x k block basis (row-major), gso: k x k GSO (columns are b~_i), both in device memory.
 cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long ldz, int B, int n, int k,
                                     int base, unsigned long long q, const double* sk, const double* gso,
-                                    double s_g, uint64_t seed, uint64_t first_target, cudaStream_t stream);
+                                    double s_g, uint64_t seed, uint64_t first_target, int* flag, cudaStream_t stream);
 // One diagonal block of the randomized nearest-plane recursion in GSO coordinates:
 // for i = j0+nb-1 .. j0:  c' = T[b][i] - sum_{j>i in block} U[i][j] z_j ;  z_i <- D_{Z, s/||b~_i||, c'}
 // writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).

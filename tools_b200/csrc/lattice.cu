@@ -23,7 +23,7 @@ constexpr int KMAX = 64;
 __global__ void __launch_bounds__(GADGET_TPB)
 gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict__ Z, long ldz, int B, int n, int k,
                      int base, unsigned long long q, const double* __restrict__ sk_g,
-                     const double* __restrict__ gso_g, double s_g, uint64_t seed, uint64_t first_target) {
+                     const double* __restrict__ gso_g, double s_g, uint64_t seed, uint64_t first_target, int* flag) {
     extern __shared__ __align__(16) double sm[];
     double* sk = sm;             // k*k   sk[t*k+i] = (b_i)_t
     double* gs = sm + k * k;     // k*k   gs[t*k+i] = (b~_i)_t
@@ -58,7 +58,7 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
         for (int i = k - 1; i >= 0; --i) {
             double dot = 0;
             for (int t = 0; t < k; ++t) dot += c[t] * gs[t * k + i];
-            double z = sample_dgauss(dg[i], dot * inv_n2[i], rng);
+            double z = sample_dgauss(dg[i], dot * inv_n2[i], rng, flag);
             if (z != 0.0)
                 for (int t = 0; t < k; ++t) c[t] -= z * sk[t * k + i];
         }
@@ -68,11 +68,11 @@ gadget_sample_kernel(const int64_t* __restrict__ V, long ldv, double* __restrict
 }
 
 // rare path of np_diag (both pre-generated proposals rejected): continue the coordinate's Philox stream
-__device__ __noinline__ double np_sample_slow(DGaussParams dgp, double cp, uint64_t seed, uint64_t index) {
+__device__ __noinline__ double np_sample_slow(DGaussParams dgp, double cp, uint64_t seed, uint64_t index, int* flag) {
     Philox ph;
     ph.init(seed, index, QF_STREAM_NP);
     ph.c3 = 1;
-    return sample_dgauss(dgp, cp, ph);
+    return sample_dgauss(dgp, cp, ph, flag);
 }
 
 // First Philox block of every (target, coordinate) stream of the nearest-plane recursion turned into two
@@ -185,7 +185,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                     if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
                 }
                 if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
-                    z = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii));
+                    z = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), flag);
                 if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
                 const double* ucol = ust + ii * us_ld + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
                 if (qd == owner) c[NG - 1] = z;
@@ -215,7 +215,7 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
 
 cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long ldz, int B, int n, int k, int base,
                                     unsigned long long q, const double* sk, const double* gso, double s_g,
-                                    uint64_t seed, uint64_t first_target, cudaStream_t stream) {
+                                    uint64_t seed, uint64_t first_target, int* flag, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     if (k > KMAX) return cudaErrorInvalidValue;
     size_t smem = (size_t)(2 * k * k + k) * sizeof(double) + (size_t)k * sizeof(DGaussParams);
@@ -229,7 +229,7 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
     long long g = (total + GADGET_TPB - 1) / GADGET_TPB;
     if (g > 148 * 16) g = 148 * 16;
     gadget_sample_kernel<<<(int)g, GADGET_TPB, smem, stream>>>(V, ldv, Z, ldz, B, n, k, base, q, sk, gso, s_g, seed,
-                                                               first_target);
+                                                               first_target, flag);
     return cudaGetLastError();
 }
 

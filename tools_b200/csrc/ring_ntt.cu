@@ -116,12 +116,14 @@ __global__ void ring_f_a_kernel(const int32_t* __restrict__ sigma, const uint64_
     uint64_t* work = sm + (size_t)y * n;           // PP x n
     uint64_t* acc = sm + (size_t)PP * n + (size_t)y * n;  // PP x n
     __shared__ unsigned long long nrm_s;
+    __shared__ unsigned int nrm_ovf;
     const uint64_t* psi_rev = tw;
     const uint64_t* psi_inv_rev = tw + n;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        if (t_id == 0 && y == 0) nrm_s = 0;
+        if (t_id == 0 && y == 0) { nrm_s = 0; nrm_ovf = 0; }
         for (int i = t_id; i < n; i += nh) acc[i] = 0;
-        unsigned long long nrm = 0;
+        NormAcc nrm;  // saturating squared norm (common.cuh)
+        nrm.clear();
         const int rounds = (npoly + PP - 1) / PP;
         for (int rd = 0; rd < rounds; ++rd) {
             const int j = rd * PP + y;
@@ -131,7 +133,7 @@ __global__ void ring_f_a_kernel(const int32_t* __restrict__ sigma, const uint64_
                 const int32_t* src = sigma + ((long)b * npoly + j) * n;
                 for (int i = t_id; i < n; i += nh) {
                     long long v = src[i];
-                    nrm += (unsigned long long)(v * v);
+                    nrm.add_sq(src[i]);
                     work[i] = gl_from_i64(v);
                 }
             }
@@ -153,9 +155,11 @@ __global__ void ring_f_a_kernel(const int32_t* __restrict__ sigma, const uint64_
             }
         }
         if (norm2) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-            if (((t_id + y * nh) & 31) == 0) atomicAdd(&nrm_s, nrm);
+            nrm.warp_reduce();
+            if (((t_id + y * nh) & 31) == 0) {
+                const unsigned long long old = atomicAdd(&nrm_s, nrm.lo);
+                if (nrm.hi || old + nrm.lo < old) atomicOr(&nrm_ovf, 1u);
+            }
         }
         __syncthreads();
         ntt_inverse(res, psi_inv_rev, n, t_id, y == 0);
@@ -172,7 +176,7 @@ __global__ void ring_f_a_kernel(const int32_t* __restrict__ sigma, const uint64_
                 }
                 out[(long)b * n + i] = (int64_t)m;
             }
-            if (t_id == 0 && norm2) norm2[b] = nrm_s;
+            if (t_id == 0 && norm2) norm2[b] = nrm_ovf ? ~0ull : nrm_s;
         }
         __syncthreads();
     }
@@ -187,7 +191,8 @@ __global__ void ring_schoolbook_kernel(const int32_t* __restrict__ sigma, const 
         long b = idx / n;
         int i = (int)(idx - b * n);
         __int128 acc = 0;
-        unsigned long long nrm = 0;
+        NormAcc nrm;
+        nrm.clear();
         for (int j = 0; j < npoly; ++j) {
             const int32_t* s = sigma + ((long)b * npoly + j) * n;
             const int64_t* aj = a + (long)j * n;
@@ -197,10 +202,10 @@ __global__ void ring_schoolbook_kernel(const int32_t* __restrict__ sigma, const 
                 acc += (__int128)aj[t] * sv;
             }
             if (i == 0 && norm2)
-                for (int t = 0; t < n; ++t) nrm += (unsigned long long)((long long)s[t] * (long long)s[t]);
+                for (int t = 0; t < n; ++t) nrm.add_sq(s[t]);
         }
         out[b * n + i] = (int64_t)mod_i128(acc, q);
-        if (i == 0 && norm2) norm2[b] = nrm;
+        if (i == 0 && norm2) norm2[b] = nrm.value();
     }
 }
 

@@ -109,7 +109,8 @@ ring_small_kernel(const int32_t* __restrict__ sigma, const uint32_t* __restrict_
         for (int c = 0; c < D; ++c)
 #pragma unroll
             for (int r = 0; r < EPL; ++r) acc[c][r] = 0;
-        unsigned long long nrm = 0;
+        NormAcc nrm;  // saturating squared norm (common.cuh)
+        nrm.clear();
         for (int j = 0; j < npoly; ++j) {
             const int32_t* src = sigma + ((long)b * npoly + j) * n;
             uint32_t v[D][EPL];
@@ -126,8 +127,7 @@ ring_small_kernel(const int32_t* __restrict__ sigma, const uint32_t* __restrict_
                 }
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    const long long xv = x[c];
-                    nrm += (unsigned long long)(xv * xv);
+                    nrm.add_sq(x[c]);
                     int32_t m = x[c] % (int32_t)R.q;
                     v[c][r] = (uint32_t)(m < 0 ? m + (int32_t)R.q : m);
                 }
@@ -168,9 +168,8 @@ ring_small_kernel(const int32_t* __restrict__ sigma, const uint32_t* __restrict_
             }
         }
         if (norm2) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-            if (lane == 0) norm2[b] = nrm;
+            nrm.warp_reduce();
+            if (lane == 0) norm2[b] = nrm.value();
         }
     }
 }

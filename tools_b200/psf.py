@@ -31,6 +31,27 @@ def _exact_bound(*factors) -> int:
     return int(v)  # floor for non-negative values
 
 
+def _domain_i32(values, domain_shape):
+    """Domain batch -> (int32 array, per-row "has an entry outside int32" mask).  A plain astype(int32) wraps silently
+    (2^32 -> 0), which would report an out-of-domain sigma as in-domain; such rows are zeroed here and reported through
+    the mask: their norm exceeds every admissible bound (s r sqrt(m) < 2^31), so they are outside D_n."""
+    v = np.asarray(values)
+    assert v.shape[1:] == domain_shape, "sigma has the wrong shape"
+    if v.dtype == np.int32:
+        return np.ascontiguousarray(v), np.zeros(v.shape[0], dtype=bool)
+    lim = 2**31 - 1
+    if v.dtype == object:
+        big = np.array([[abs(int(x)) > lim for x in row.reshape(-1)] for row in v], dtype=bool).reshape(v.shape)
+    elif np.issubdtype(v.dtype, np.integer):
+        big = (v > lim) | (v < -lim)
+    else:
+        big = ~(np.abs(v) <= lim) | (v != np.rint(v))  # non-integers (and NaN) are not lattice points
+    oob = big.reshape(v.shape[0], -1).any(axis=1) if v.shape[0] else np.zeros(0, dtype=bool)
+    if oob.any():
+        v = np.where(big, 0, v)
+    return np.ascontiguousarray(v, dtype=np.int32), oob
+
+
 class _PSFBase:
     """Common plumbing: one qf_ctx, cached key/trapdoor uploads."""
 
@@ -54,11 +75,10 @@ class _PSFBase:
 
     # -- PSF::check_domain ------------------------------------------------------------------
     def check_domain_batch(self, sigmas: np.ndarray) -> np.ndarray:
-        s = np.ascontiguousarray(sigmas, dtype=np.int32)
-        assert s.shape[1:] == self._domain_shape
+        s, oob = _domain_i32(sigmas, self._domain_shape)
         flags = np.empty(s.shape[0], dtype=np.uint8)
         self.ctx.call("qf_check_domain", _ffi.ptr(s), s.shape[0], _ffi.ptr(flags))
-        return flags.astype(bool)
+        return flags.astype(bool) & ~oob
 
     def _shape_ok(self, sigma) -> bool:
         raise NotImplementedError
@@ -67,8 +87,6 @@ class _PSFBase:
         sigma = np.asarray(sigma)
         if not self._shape_ok(sigma):
             return False
-        if sigma.size and np.abs(sigma.astype(object)).max() > 2**31 - 1:
-            return False  # norm certainly above the bound (s * r * sqrt(m) < 2^31 is required)
         return bool(self.check_domain_batch(sigma.reshape((1,) + self._domain_shape))[0])
 
     # -- PSF::f_a ---------------------------------------------------------------------------
@@ -76,25 +94,22 @@ class _PSFBase:
         """u[b] = A sigma[b]; returns (u, in_domain).  strict=True raises NotInDomain like the
         reference's assert! when some sigma is outside D_n."""
         self._install_a(a)
-        s = np.ascontiguousarray(sigmas, dtype=np.int32)
-        assert s.shape[1:] == self._domain_shape, "sigma has the wrong shape"
+        s, oob = _domain_i32(sigmas, self._domain_shape)
         b = s.shape[0]
         u = np.empty((b, self.n), dtype=np.int64)
         flags = np.empty(b, dtype=np.uint8)
         st = self.ctx.status("qf_f_a", _ffi.ptr(s), b, _ffi.ptr(u), _ffi.ptr(flags))
-        if st == _ffi.QF_ERR_NOT_IN_DOMAIN:
-            if strict:
-                raise NotInDomain(st, "sigma is not in the domain D_n")
-        elif st != _ffi.QF_OK:
+        if st not in (_ffi.QF_OK, _ffi.QF_ERR_NOT_IN_DOMAIN):
             raise QfError(st, self.ctx._lib.qf_last_error(self.ctx._h).decode())
-        return u, flags.astype(bool)
+        ok = flags.astype(bool) & ~oob
+        if strict and not ok.all():
+            raise NotInDomain(_ffi.QF_ERR_NOT_IN_DOMAIN, "sigma is not in the domain D_n")
+        return u, ok
 
     def f_a(self, a, sigma) -> np.ndarray:
         sigma = np.asarray(sigma)
         if not self._shape_ok(sigma):
             raise NotInDomain(_ffi.QF_ERR_NOT_IN_DOMAIN, "sigma is not a column vector of the right length")
-        if sigma.size and np.abs(sigma.astype(object)).max() > 2**31 - 1:
-            raise NotInDomain(_ffi.QF_ERR_NOT_IN_DOMAIN, "sigma is not in the domain D_n")
         u, _ = self.f_a_batch(a, sigma.reshape((1,) + self._domain_shape))
         return u[0]
 
@@ -223,6 +238,20 @@ class PSFPerturbation(_PSFBase):
         out = np.empty((self.m, self.m), dtype=np.float64)
         self.ctx.call("qf_compute_sqrt_sigma_2", _ffi.ptr(r8), _ffi.ptr(sig), _ffi.ptr(out))
         return out
+
+    def randomized_nearest_plane_gadget_batch(self, a, td, vs, seed=None, first_index: int = 0) -> np.ndarray:
+        """mp_perturbation.rs:173-191 for a batch of syndromes v (B x n): z = x0 + SampleD(S, S~, -x0, r sqrt(b^2+1)),
+        x0 the base-b digits of v (find_solution_gadget_mat); G z = v mod q.  Returns B x (n k) int32."""
+        self._install_a(a)
+        self._install_td(a, td)
+        v = np.ascontiguousarray(vs, dtype=np.int64)
+        assert v.ndim == 2 and v.shape[1] == self.n
+        z = np.empty((v.shape[0], self.gp.n * self.gp.k), dtype=np.int32)
+        self.ctx.call("qf_randomized_nearest_plane_gadget", _ffi.ptr(v), v.shape[0], _seed(seed), first_index, _ffi.ptr(z))
+        return z
+
+    def randomized_nearest_plane_gadget(self, a, td, v, seed=None) -> np.ndarray:
+        return self.randomized_nearest_plane_gadget_batch(a, td, np.asarray(v, dtype=np.int64).reshape(1, self.n), seed)[0]
 
     def trap_gen(self, seed=None, full_gadget_basis: bool = None, dense_sqrt_sigma_2: bool = None):
         """mp_perturbation.rs:221-244.  dense_sqrt_sigma_2=False leaves the second trapdoor component None: the
