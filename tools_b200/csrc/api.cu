@@ -150,7 +150,12 @@ struct qf_ctx {
     // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
     bool use_ozaki = false;
     int u_limbs = 7;
+    int np_dlo = 2;        // digit sums below 256^np_dlo are dropped from the fixed-point updates (error budget: np_block)
     Dev dUl, dUscale, dNz, dMma;
+    // highest non-zero digit plane of z per 1024-block [0, n1024), per 4096-block [n1024, n1024 + n4096) and over the
+    // gadget-free block z2 [n1024 + n4096]: written by the digit split, read by the conditional contraction launches
+    Dev dGate;
+    int gate_n1024 = 0, gate_n4096 = 0;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -634,6 +639,32 @@ static long np_last_block_start(long D, long S) {
     return top;
 }
 
+// One contraction with the z digit planes as x operand, launched once per digit count LXv in [3, z_limbs]: every launch is
+// conditional on the device-side gate (highest non-zero digit plane of the z block it consumes), so exactly one of them
+// runs -- the one compiled for the digits that are really there (fewer accumulators in TMEM = wider tiles, less operand
+// traffic per MAC).  Without a gate a single launch with all z_limbs digits.
+qf_status gemm_i8_gated(qf_ctx* ctx, I8GemmArgs g, const int* gate) {
+    const int Lmax = g.LX;
+    if (!gate || Lmax <= 3) {
+        LAUNCH(ctx_gemm_i8(ctx, g));
+        return QF_OK;
+    }
+    for (int lx = 3; lx <= Lmax; ++lx) {
+        I8GemmArgs v = g;
+        v.LX = lx;
+        v.gate = gate;
+        v.gate_lo = lx == 3 ? 0 : lx - 1;
+        v.gate_hi = lx == Lmax ? 1 << 20 : lx - 1;
+        LAUNCH(ctx_gemm_i8(ctx, v));
+    }
+    return QF_OK;
+}
+
+// column -> index of its block at step S (the ragged top joins the last full block, np_last_block_start)
+static inline int np_block_index(long col, long D, long S) {
+    return (int)(std::min(col, np_last_block_start(D, S)) / S);
+}
+
 // Process coordinates [lo, hi) in descending order.  Precondition: T[:, lo:hi] already carries the
 // updates of every coordinate >= hi.  level 0 = one sequential diagonal block.  prop0 = first coordinate of the
 // enclosing 1024-level block (origin of the pre-generated proposals).
@@ -666,10 +697,14 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
             int8_t* zp = ctx->w[8].as<int8_t>();
+            int* gates = ctx->dGate.as<int>();
+            int* gate1 = gates + np_block_index(sub_lo, D, NP_SIZES[2]);
+            int* gate4 = gates + ctx->gate_n1024 + np_block_index(sub_lo, D, NP_SIZES[3]);
             if (level == 3)  // digits of the finished 1024-block of z (kept: the level above and the final S z reuse them)
                 LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
                                                  ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
-                                                 ctx->stream));
+                                                 ctx->stream, gate1, gate4,
+                                                 (ctx->gpv_struct && sub_hi > ctx->nk) ? gates + ctx->gate_n1024 + ctx->gate_n4096 : nullptr));
             // the update of the rows above it (within the enclosing block) on the tensor cores:
             //   T[:, lo:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
             if (sub_lo > lo && sub_hi - sub_lo < NP_THIN) {
@@ -687,7 +722,12 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                 g.scale = ctx->dUscale.as<double>() + (sub_lo / NP_SCALE_BLOCK) * D + lo;
                 g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb;
                 g.nz_kb_off = (int)(sub_lo / 128); g.nz_m_off = 0;
-                LAUNCH(ctx_gemm_i8(ctx, g));
+                // Dropped digit sums d < np_dlo: per launch |error| <= K 2^14 256^(d_lo - 1) d_lo scale_row (scale_row =
+                // row maximum of |U| / (127 256^6)), i.e. < 2^-27 |U|max K^(1/2) typically at d_lo = 2 -- four orders
+                // below the 2^-12 the centres need (the widths s / ||b~_i|| are >= 2.3), and below the fp64 rounding of T
+                // at |T| ~ 2^24.
+                g.d_lo = ctx->np_dlo;
+                QF_TRY(gemm_i8_gated(ctx, g, level == 3 ? gate1 : gate4));
             }
         } else if (sub_lo > lo) {
             LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
@@ -737,6 +777,11 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(ctx->w[8].ensure((size_t)ctx->z_limbs * C * ldk));
         CK(ctx->dNz.ensure(nzb));
         CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
+        ctx->gate_n1024 = np_block_index(D - 1, D, NP_SIZES[2]) + 1;
+        ctx->gate_n4096 = np_block_index(D - 1, D, NP_SIZES[3]) + 1;
+        const size_t gb = (size_t)(ctx->gate_n1024 + ctx->gate_n4096 + 1) * sizeof(int);
+        CK(ctx->dGate.ensure(gb));
+        CK(cudaMemsetAsync(ctx->dGate.p, 0, gb, ctx->stream));
     }
     QF_TRY(np_block(ctx, T, Z, Bc, 0, D, NP_TOP, 0, seed, first));
     // e = sol + S z   (exact integers)
@@ -767,7 +812,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
             g.out_kind = 2; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = I2; g.ldout = ldnk;
             g.flag = ctx->dFlag.as<int>();
             if (g.x_nz) g.nz_kb_off = (int)(nk / 128);
-            LAUNCH(ctx_gemm_i8(ctx, g));
+            QF_TRY(gemm_i8_gated(ctx, g, ctx->use_ozaki ? ctx->dGate.as<int>() + ctx->gate_n1024 + ctx->gate_n4096 : nullptr));
             LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev,
                                           ctx->stream));
             const long plane2 = C * ldk_nk;
@@ -1243,6 +1288,8 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
         ctx->use_i8 = !(env && env[0] == '1');
         const char* envf = getenv("QF_DISABLE_FUSED_FA");
         ctx->fused_fa = !(envf && envf[0] == '1');
+        const char* envd = getenv("QF_NP_DLO");  // test switch: 0 = every digit pair of the fixed-point updates
+        if (envd) ctx->np_dlo = std::max(0, std::min(3, atoi(envd)));
     }
     // default chunk: keep ~8 fp64-sized work matrices within ~16 GB; whole waves of 148 SMs x 128-target tiles
     long per_target = ctx->ld_dim * 8 * 8;

@@ -352,9 +352,11 @@ __device__ __forceinline__ void split_digits(long long v, int L, int8_t* planes,
 // One warp per target row, 128 columns (= one zero-tile) per warp iteration, 4 consecutive columns per lane:
 // one vector load, one char4 store per digit plane, and one warp vote per digit for the zero-tile map
 // (no global reads on the flag path).  col0 and ldk are multiples of 128 / 4 for every caller.
-__device__ __forceinline__ void split4(const long long v[4], int L, int8_t* planes, long plane_stride, long off, int* flag,
-                                       uint8_t* nz, long nz_plane, long nz_idx, int valid, int lane) {
+// returns (warp-uniform, when nz is given) the index of the highest digit plane this warp found non-zero, -1 if none
+__device__ __forceinline__ int split4(const long long v[4], int L, int8_t* planes, long plane_stride, long off, int* flag,
+                                      uint8_t* nz, long nz_plane, long nz_idx, int valid, int lane) {
     long long w[4] = {v[0], v[1], v[2], v[3]};
+    int top = -1;
     for (int l = 0; l < L; ++l) {
         int8_t dd[4];
         bool any = false;
@@ -379,13 +381,17 @@ __device__ __forceinline__ void split4(const long long v[4], int L, int8_t* plan
         if (nz) {
             const bool warp_any = __any_sync(0xffffffffu, any);
             if (warp_any && lane == 0) nz[l * nz_plane + nz_idx] = 1;
+            if (warp_any) top = l;
         }
     }
+    return top;
 }
 
+// gate0..2 (optional device ints): raised (atomicMax) to the index of the highest non-zero digit plane written by this
+// launch -- the contractions that consume these planes pick, on the device, the variant compiled for that many digits
 __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin, int8_t* __restrict__ planes,
                                        long plane_stride, long ldk, int B, int M, int L, int* flag, uint8_t* nz,
-                                       int nz_m_tiles, int nz_kb_total, int col0) {
+                                       int nz_m_tiles, int nz_kb_total, int col0, int* gate0, int* gate1, int* gate2) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int iters = (M + 127) >> 7;
@@ -412,8 +418,13 @@ __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin,
                 v[t] = __double2ll_rn(xx);
             }
         }
-        split4(v, L, planes, plane_stride, b * ldk + j, flag, nz, (long)nz_m_tiles * nz_kb_total,
-               (b >> 7) * nz_kb_total + ((col0 + j) >> 7), valid, lane);
+        const int top = split4(v, L, planes, plane_stride, b * ldk + j, flag, nz, (long)nz_m_tiles * nz_kb_total,
+                               (b >> 7) * nz_kb_total + ((col0 + j) >> 7), valid, lane);
+        if (lane == 0 && top > 0) {  // plain read first: almost every warp finds the gate already high enough
+            if (gate0 && *(volatile int*)gate0 < top) atomicMax(gate0, top);
+            if (gate1 && *(volatile int*)gate1 < top) atomicMax(gate1, top);
+            if (gate2 && *(volatile int*)gate2 < top) atomicMax(gate2, top);
+        }
     }
 }
 
@@ -617,13 +628,13 @@ cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, i
 }
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
-                                      cudaStream_t stream) {
+                                      cudaStream_t stream, int* gate0, int* gate1, int* gate2) {
     if (B <= 0) return cudaSuccess;
     // char4 stores need 4-byte aligned plane addresses: planes pointer, ldk and col0 multiples of 4 (true for all callers)
     if ((((uintptr_t)planes) & 3) || (ldk & 3) || (col0 & 3)) return cudaErrorMisalignedAddress;
     if (nz && (col0 & 127)) return cudaErrorInvalidValue;
     split_f64_limbs_kernel<<<grid_for((long long)B * ((M + 127) / 128), TPB / 32), TPB, 0, stream>>>(
-        in, ldin, planes, plane_stride, ldk, B, M, L, flag, nz, nz_m_tiles, nz_kb_total, col0);
+        in, ldin, planes, plane_stride, ldk, B, M, L, flag, nz, nz_m_tiles, nz_kb_total, col0, gate0, gate1, gate2);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,

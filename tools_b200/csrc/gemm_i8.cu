@@ -53,6 +53,14 @@ struct I8Params {
     // optional zero-tile map of the x digit planes: nz[(j * m_tiles_total + m_tile) * kb_total + kb_off + kb]
     const uint8_t* x_nz; int nz_m_tiles, nz_kb_total, nz_kb_off, nz_m_off;
     unsigned long long* mma_units;  // optional device counter of executed int8 operations (tensor pipe work)
+    // digit-sum window: only D_d with d >= d_lo are computed (accumulator t holds D_{d_lo + t}); the dropped low-order
+    // pairs lie below the error budget of the fixed-point update (out_kind 3 only, scale_mul = 256^d_lo)
+    int d_lo;
+    double scale_mul;
+    int acc_bufs;   // 2: the accumulators are double-buffered in TMEM (tile i+1's MMAs overlap tile i's epilogue)
+    // conditional launch: the grid exits at once unless gate_lo <= *gate <= gate_hi (device-side choice between
+    // variants of the same contraction compiled for different digit counts, no host round trip)
+    const int* gate; int gate_lo, gate_hi;
     // optional diagnostics (QF_TRACE): cycles the MMA warp waited for [0] drained accumulators, [1] operand tiles, and the
     // epilogue spent [2] waiting for the accumulators, [3] draining them (summed over CTAs)
     unsigned long long* tim;
@@ -66,15 +74,16 @@ __device__ __forceinline__ double s32_to_f64(int32_t x) {
 // Epilogue of one 128 x 16 half of a 32-column tile of the scaled fp64 update out[b][n] = old - V * scale[n],
 // V = sum_d 256^d D_d: NDT accumulators of 32 columns each (NDT compile time: straight-line Horner, no predication),
 // 4 columns per TMEM trip, the old values `pre` already in registers.  cb = first column of this warp's half.
-template <int NDT>
-__device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const double2 (&pre)[8], double* orow,
-                                             const double* __restrict__ scale, int nd_rt = NDT) {
+template <int NDT, int NC = 16>
+__device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const double2 (&pre)[16], double* orow,
+                                             const double* __restrict__ scale, int nd_rt = NDT, int nt = 32,
+                                             double mul = 1.0) {
 #pragma unroll
-    for (int c0 = 0; c0 < 16; c0 += 4) {
+    for (int c0 = 0; c0 < NC; c0 += 4) {
         int32_t t[NDT][4];
 #pragma unroll
         for (int d = 0; d < NDT; ++d)
-            if (d < nd_rt) tmem_ld4(lane_addr + (uint32_t)(d * 32 + cb + c0), t[d]);
+            if (d < nd_rt) tmem_ld4(lane_addr + (uint32_t)(d * nt + cb + c0), t[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         double r[4];
 #pragma unroll
@@ -85,7 +94,7 @@ __device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const d
             for (int d = NDT - 1; d >= 0; --d)
                 if (d < nd_rt) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
             const double old = (c & 1) ? pre[(c0 + c) >> 1].y : pre[(c0 + c) >> 1].x;
-            r[c] = fma(-dv, scale[cb + c0 + c], old);
+            r[c] = fma(-dv, scale[cb + c0 + c] * mul, old);
         }
         *reinterpret_cast<double2*>(orow + cb + c0) = make_double2(r[0], r[1]);
         *reinterpret_cast<double2*>(orow + cb + c0 + 2) = make_double2(r[2], r[3]);
@@ -96,7 +105,7 @@ __device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const d
 // old values fetched before the accumulators are read.
 template <int NDT, int COLS>
 __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow, const double* __restrict__ scale, int n0,
-                                               int nt, int N, bool rv, int nd, int cbeg, int cend) {
+                                               int nt, int N, bool rv, int nd, int cbeg, int cend, double mul) {
     for (int c0 = cbeg; c0 < cend; c0 += COLS) {
         double told[COLS];
 #pragma unroll
@@ -116,7 +125,7 @@ __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow,
             for (int d = NDT - 1; d >= 0; --d)
                 if (d < nd) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
             const int n = n0 + c0 + c;
-            if (rv && n < N) orow[n] = told[c] - dv * scale[n];
+            if (rv && n < N) orow[n] = told[c] - dv * (scale[n] * mul);
         }
     }
 }
@@ -126,6 +135,10 @@ __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow,
 template <int OK3>  // OK3 = 1: the scaled fp64 update epilogue (out_kind 3) only; 0: the integer epilogues
 __global__ void __launch_bounds__(I8_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
+    if (p.gate != nullptr) {  // uniform over the grid: either every thread leaves here or none does
+        const int gv = *p.gate;
+        if (gv < p.gate_lo || gv > p.gate_hi) return;
+    }
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand ring
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -135,13 +148,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
-    uint64_t* tmem_full = bars + 2 * p.stages;
-    uint64_t* tmem_empty = bars + 2 * p.stages + 1;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 2);
+    uint64_t* tmem_full = bars + 2 * p.stages;       // [2], one per accumulator buffer
+    uint64_t* tmem_empty = bars + 2 * p.stages + 2;  // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int ND = p.LX + p.LW - 1;
+    const int ND = p.LX + p.LW - 1 - p.d_lo;   // accumulators per buffer: digit sums d_lo .. LX + LW - 2
+    const int NB = p.acc_bufs;                 // accumulator buffers in TMEM (NB * ND * nt <= 512 columns)
+    const uint32_t buf_cols = (uint32_t)(ND * p.nt);
     const int total_tiles = p.m_tiles * p.n_tiles;
     // tile rasterisation: consecutive tiles walk group_m target tiles for one n tile, then the next n tile
     auto tile_coords = [&](int t, int& tile_m, int& tile_n) {
@@ -165,8 +180,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, EPI_WARPS);  // one arrival per epilogue warp
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], EPI_WARPS);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // allocate all 512 TMEM columns (one CTA per SM)
@@ -182,7 +199,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // accumulators zeroed by the epilogue of the previous tile.
     if (warp >= 2) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int c = ((warp - 2) >> 2) * 16; c < ND * p.nt; c += 16 * (EPI_WARPS / 4)) tmem_st16_zero(lane_addr + (uint32_t)c);
+        for (int c = ((warp - 2) >> 2) * 16; c < NB * ND * p.nt; c += 16 * (EPI_WARPS / 4)) tmem_st16_zero(lane_addr + (uint32_t)c);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -230,9 +247,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int tile_m, tile_n;
             tile_coords(tile, tile_m, tile_n);
-            if (it > 0) {  // the epilogue must have drained (and re-zeroed) the accumulators of the previous tile
+            const int buf = NB == 2 ? (it & 1) : 0, use = NB == 2 ? (it >> 1) : it;
+            const uint32_t acc_base = tmem_base + (uint32_t)buf * buf_cols;
+            if (use > 0) {  // the epilogue must have drained (and re-zeroed) this buffer's previous tile
                 const long long t0_ = p.tim ? clock64() : 0;
-                mbar_wait(tmem_empty, (uint32_t)((it - 1) & 1));
+                mbar_wait(&tmem_empty[buf], (uint32_t)((use - 1) & 1));
                 if (p.tim) tw_empty += clock64() - t0_;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
@@ -250,11 +269,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     for (int j = 0; j < p.LX; ++j) {
                         if (!((mk >> j) & 1u)) continue;
                         const uint64_t da = desc0 + (uint64_t)(sx_off + ((uint32_t)(j * x_tile) >> 4));
-                        for (int i0 = 0; i0 < p.LW; i0 += G) {
+                        for (int i0 = max(0, p.d_lo - j); i0 < p.LW; i0 += G) {  // pairs with i + j < d_lo are dropped
                             const int g = min(G, p.LW - i0);
                             const uint32_t idesc = idesc0 | ((uint32_t)((g * p.nt) >> 3) << 17);
                             const uint64_t db = desc0 + (uint64_t)(sw_off + ((uint32_t)(i0 * w_tile) >> 4));
-                            const uint32_t dcol = tmem_base + (uint32_t)((i0 + j) * p.nt);
+                            const uint32_t dcol = acc_base + (uint32_t)((i0 + j - p.d_lo) * p.nt);
 #pragma unroll
                             for (int kk = 0; kk < BK / 32; ++kk)  // +32 bytes along K = +2 in 16-byte units
                                 mma_i8(dcol, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
@@ -262,7 +281,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         }
                     }
                     mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
-                    if (kb == num_kb - 1) mma_commit(tmem_full);
+                    if (kb == num_kb - 1) mma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -277,7 +296,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // column range of this warp for tiles of any width: whole 16-column groups, the first half rounded up
         const int cmid = ((p.nt / 16 + 1) / 2) * 16;
         const int cbeg = half ? cmid : 0, cend = half ? p.nt : cmid;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const uint32_t lane_addr0 = tmem_base + ((uint32_t)(lg * 32) << 16);
         long long te_wait = 0, te_body = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -285,34 +304,48 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             tile_coords(tile, tile_m, tile_n);
             const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
             const int row = m0 + lg * 32 + lane;
+            const int buf = NB == 2 ? (it & 1) : 0, use = NB == 2 ? (it >> 1) : it;
+            const uint32_t lane_addr = lane_addr0 + (uint32_t)buf * buf_cols;
             // out_kind 3, 32-column tiles: this thread's 32 old values (one 256-byte row segment) are fetched NOW, while
             // the tile's MMAs are still running, so the DRAM latency of the read-modify-write is off the serial
             // MMA -> epilogue -> MMA chain (TMEM holds one tile: the next tile's MMAs wait for this epilogue)
             // (warp-uniform: tcgen05.ld is .aligned, every lane of the warp must take the same path)
-            const bool pre_ok = OK3 && p.nt == 32 && m0 + lg * 32 + 31 < p.B && n0 + 32 <= p.N && (p.ldout & 1) == 0 &&
-                                ((((uintptr_t)p.out) & 15) == 0);
-            double2 pre[8];
+            const bool pre_ok = OK3 && (p.nt == 32 || p.nt == 64) && m0 + lg * 32 + 31 < p.B && n0 + p.nt <= p.N &&
+                                (p.ldout & 1) == 0 && ((((uintptr_t)p.out) & 15) == 0);
+            // per warp: 16 columns of a 32-column tile, 32 columns of a 64-column tile
+            double2 pre[16];
             if (OK3 && pre_ok) {
-                const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0 + half * 16);
+                const int ncw = p.nt >> 1;
+                const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0 + half * ncw);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) pre[i] = src[i];
+                if (p.nt == 64) {
+#pragma unroll
+                    for (int i = 8; i < 16; ++i) pre[i] = src[i];
+                }
             }
             const long long te0_ = p.tim ? clock64() : 0;
-            mbar_wait(tmem_full, (uint32_t)(it & 1));
+            mbar_wait(&tmem_full[buf], (uint32_t)(use & 1));
             const long long te1_ = p.tim ? clock64() : 0;
             te_wait += te1_ - te0_;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (OK3 && pre_ok) {
+            if (OK3 && pre_ok && p.nt == 64) {
                 double* orow = (double*)p.out + (long)row * p.ldout + n0;
-                if (ND == 11) epi_update16<11>(lane_addr, half * 16, pre, orow, p.scale + n0);
-                else if (ND == 6) epi_update16<6>(lane_addr, half * 16, pre, orow, p.scale + n0);
-                else epi_update16<16>(lane_addr, half * 16, pre, orow, p.scale + n0, ND);
+                if (ND == 7) epi_update16<7, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, 7, 64, p.scale_mul);
+                else if (ND == 8) epi_update16<8, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, 8, 64, p.scale_mul);
+                else epi_update16<8, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, ND, 64, p.scale_mul);  // ND <= 8 at nt = 64
+            } else if (OK3 && pre_ok) {
+                double* orow = (double*)p.out + (long)row * p.ldout + n0;
+                if (ND == 11) epi_update16<11>(lane_addr, half * 16, pre, orow, p.scale + n0, 11, 32, p.scale_mul);
+                else if (ND == 6) epi_update16<6>(lane_addr, half * 16, pre, orow, p.scale + n0, 6, 32, p.scale_mul);
+                else if (ND <= 8) epi_update16<8>(lane_addr, half * 16, pre, orow, p.scale + n0, ND, 32, p.scale_mul);
+                else epi_update16<16>(lane_addr, half * 16, pre, orow, p.scale + n0, ND, 32, p.scale_mul);
             } else if (OK3) {
                 // ragged / wider tiles
                 double* orow = (double*)p.out + (long)row * p.ldout;
-                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
-                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
-                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend);
+                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
+                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
+                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
             } else if (!OK3) {
                 for (int c0 = cbeg; c0 < cend; c0 += 16) {
                     if (ND <= 4) {
@@ -394,7 +427,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
             if (p.tim) te_body += clock64() - te1_;
             // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
-            if (tile + (int)gridDim.x < total_tiles) {
+            if (tile + NB * (int)gridDim.x < total_tiles) {  // this buffer is used again
                 // (each warp zeroes exactly the columns it has just read: the other warp of the lane group may still be
                 // reading its own)
                 for (int d = 0; d < ND; ++d)
@@ -402,7 +435,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty);
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
         }
         if (warp == 2 && lane == 0 && p.tim) { atomicAdd(p.tim + 2, (unsigned long long)te_wait); atomicAdd(p.tim + 3, (unsigned long long)te_body); }
@@ -417,8 +450,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
 }  // namespace
 
-int qf_i8_tile_n(int LX, int LW, int N) {
-    const int ND = LX + LW - 1;
+int qf_i8_tile_n(int LX, int LW, int N, int d_lo) {
+    const int ND = LX + LW - 1 - d_lo;
     int nt = (512 / ND) / 16 * 16;
     if (nt > 256) nt = 256;
     int need = (N + 15) / 16 * 16;
@@ -429,12 +462,23 @@ int qf_i8_tile_n(int LX, int LW, int N) {
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (a.B <= 0 || a.N <= 0) return cudaSuccess;
     if (a.LX < 1 || a.LW < 1 || a.LX + a.LW - 1 > 16 || a.K < 1) return cudaErrorInvalidValue;
+    if (a.d_lo < 0 || (a.d_lo > 0 && a.out_kind != 3) || a.d_lo > a.LX + a.LW - 2) return cudaErrorInvalidValue;
     if ((a.ldx & 15) || (a.ldw & 15) || (a.x_plane & 15) || (a.w_plane & 15) || (((uintptr_t)a.x) & 15) ||
         (((uintptr_t)a.w) & 15))
         return cudaErrorMisalignedAddress;
-    const int nt = qf_i8_tile_n(a.LX, a.LW, a.N);
+    int nt = qf_i8_tile_n(a.LX, a.LW, a.N, a.d_lo);
     if (nt < 16) return cudaErrorInvalidValue;
+    const int ND = a.LX + a.LW - 1 - a.d_lo;
+    // the fast read-modify-write epilogue of the fixed-point update exists for 32- and 64-column tiles
+    // (wider tiles, ND <= 4, keep their width and take the generic epilogue)
+    if (a.out_kind == 3 && nt > 64 && nt < 128) nt = 64;
+    if (a.out_kind == 3 && nt > 32 && nt < 64) nt = 32;
     I8Params p{};
+    p.d_lo = a.d_lo;
+    p.scale_mul = 1.0;
+    for (int i = 0; i < a.d_lo; ++i) p.scale_mul *= 256.0;
+    p.acc_bufs = (2 * ND * nt <= 512) ? 2 : 1;
+    p.gate = a.gate; p.gate_lo = a.gate_lo; p.gate_hi = a.gate_hi;
     p.B = a.B; p.N = a.N; p.K = a.K; p.LX = a.LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
     p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.qmagic = qf_barrett_magic(a.q); p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
     p.ldout = a.ldout; p.flag = a.flag; p.scale = a.scale;

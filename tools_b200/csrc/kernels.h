@@ -166,8 +166,13 @@ struct I8GemmArgs {
     // optional device counter: += int8 operations the tensor pipe actually executed (zero digit tiles are skipped)
     unsigned long long* mma_units;
     unsigned long long* tim;  // optional: 4 phase cycle counters (diagnostics)
+    // out_kind 3 only: digit sums D_d with d < d_lo are not computed (their pairs lie below the error budget)
+    int d_lo;
+    // optional conditional launch: the grid runs only if gate_lo <= *gate <= gate_hi (device int)
+    const int* gate;
+    int gate_lo, gate_hi;
 };
-int qf_i8_tile_n(int LX, int LW, int N);
+int qf_i8_tile_n(int LX, int LW, int N, int d_lo = 0);
 // gemm_i8_fused.cu: out = X W^t mod q with X read as int32 (digit split fused into the contraction) and the
 // squared row norms of X accumulated on the way (norm2 optional)
 struct FaFusedArgs {
@@ -190,9 +195,10 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
 // balanced s8 digits; *flag |= 8 when a value does not fit L digits
 // nz (optional, pre-zeroed): zero-tile map [L][nz_m_tiles][nz_kb_total] over 128-target x 128-column tiles;
 // col0 = global column of in[.][0] (the planes pointer is already offset by col0)
+// gate0..2 (optional, need nz): device ints raised to the index of the highest non-zero digit plane written
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
-                                      cudaStream_t stream);
+                                      cudaStream_t stream, int* gate0 = nullptr, int* gate1 = nullptr, int* gate2 = nullptr);
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, unsigned long long* norm2, uint8_t* nz, int nz_m_tiles,
                                       int nz_kb_total, cudaStream_t stream);
