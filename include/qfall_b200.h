@@ -158,6 +158,17 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
                     int32_t* e_out);
 qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first_index,
                         int32_t* e_out);
+/* Narrow Domain form: the same preimages as int16 -- |e_i| <= 6 s r is far below 2^15 for the parameter sets of the
+ * reference (C2: 6 s = 8568; C3: 3135), so the device->host copy, which bounds the host-buffer path, is halved.  An entry
+ * that does not fit is reported as QF_ERR_NUMERIC (then use qf_samp_p).  Targets outside [0,q) are detected on the device
+ * (both variants) and reported as QF_ERR_INVALID when the call returns. */
+qf_status qf_samp_p_i16(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first_index,
+                        int16_t* e_out);
+/* f_a / check_domain on int16 Domain values (host pointers; otherwise as qf_f_a). */
+qf_status qf_f_a_i16(qf_ctx* ctx, const int16_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain);
+/* int32 -> int16 on the device (e.g. before the final gather of results over NVLink); *overflow (device int, zeroed by
+ * the caller) gets bit 64 set when a value does not fit.  in / out 16-byte aligned. */
+qf_status qf_narrow_i32_i16_dev(const int32_t* in, int16_t* out, size_t count, int* overflow, void* cuda_stream);
 
 /* ---- PSFPerturbation::randomized_nearest_plane_gadget (mp_perturbation.rs:173-191), the public helper samp_p calls:
  * z[b] = x0 + SampleD(S, S~, -x0, r sqrt(base^2 + 1)) with x0 = find_solution_gadget_mat(v[b]) -- a preimage of v[b]
@@ -203,6 +214,13 @@ qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t se
  * |w| < 2^(8 LW - 1) (w_signed = 1).  Host pointers. */
 qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int LX, int LW, int64_t B, int64_t N,
                            int64_t K, uint64_t q, int64_t* out);
+
+/* ---- measured ceiling of the int8 tensor pipe (roofline denominator of the limb contractions; SURVEY 8d: "measure a plain
+ * int8 tcgen05 GEMM probe once and use it"): a one-digit-pair B x N x K contraction on random bytes (128 x 256 tiles, K a
+ * multiple of 128, <= 65536), `iters` launches timed one by one -> best_tops (burst), then back to back for sustain_ms ->
+ * sustained_tops.  TOP/s = 2 B N K / time.  Allocates its own buffers on `device`. */
+qf_status qf_probe_i8_peak(int device, int64_t B, int64_t N, int64_t K, int iters, double sustain_ms, double* best_tops,
+                           double* sustained_tops);
 
 /* ---- synthetic inputs for benchmarks (Philox, on device) -------------------------------- */
 qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* cuda_stream);

@@ -66,6 +66,9 @@ extern "C" {
     pub fn qf_samp_p(ctx: *mut qf_ctx, u: *const i64, batch: i64, seed: u64, first_index: u64, e_out: *mut i32) -> i32;
     pub fn qf_samp_p_dev(ctx: *mut qf_ctx, u: *const i64, batch: i64, seed: u64, first_index: u64, e_out: *mut i32) -> i32;
 
+    pub fn qf_samp_p_i16(ctx: *mut qf_ctx, u: *const i64, batch: i64, seed: u64, first_index: u64, e_out: *mut i16) -> i32;
+    pub fn qf_f_a_i16(ctx: *mut qf_ctx, sigma: *const i16, batch: i64, u_out: *mut i64, in_domain: *mut u8) -> i32;
+    pub fn qf_narrow_i32_i16_dev(input: *const i32, out: *mut i16, count: usize, overflow: *mut i32, cuda_stream: *mut c_void) -> i32;
     pub fn qf_randomized_nearest_plane_gadget(ctx: *mut qf_ctx, v: *const i64, batch: i64, seed: u64, first_index: u64, z_out: *mut i32) -> i32;
 
     pub fn qf_compress_u16(input: *const u16, out: *mut u16, count: usize, q: u32, d: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
@@ -77,6 +80,7 @@ extern "C" {
 
     pub fn qf_sample_z(centers: *const f64, count: usize, s: f64, seed: u64, out: *mut i64) -> i32;
     pub fn qf_debug_gemm_i8(x: *const i64, w: *const i64, w_signed: i32, lx: i32, lw: i32, b: i64, n: i64, k: i64, q: u64, out: *mut i64) -> i32;
+    pub fn qf_probe_i8_peak(device: i32, b: i64, n: i64, k: i64, iters: i32, sustain_ms: f64, best_tops: *mut f64, sustained_tops: *mut f64) -> i32;
     pub fn qf_fill_uniform_modq_dev(out: *mut i64, count: usize, q: u64, seed: u64, cuda_stream: *mut c_void) -> i32;
     pub fn qf_version() -> *const c_char;
 }

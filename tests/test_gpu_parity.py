@@ -359,6 +359,54 @@ def test_key_change_invalidates_trapdoor(T):
     assert st == _ffi.QF_ERR_NO_KEY
 
 
+def test_int16_domain_form_and_device_range_check(T):
+    """Narrow boundary types: qf_samp_p_i16 returns the same preimages as qf_samp_p (same seed) in 16 bits, qf_f_a_i16
+    accepts them; a target outside [0, q) is caught by the device-side range check (QF_ERR_INVALID); an entry that does
+    not fit int16 is reported, not truncated."""
+    from tools_b200 import _ffi
+
+    n, q = 8, 64
+    gp = T.GadgetParameters.init_default(n, q)
+    rng = np.random.default_rng(3)
+    u = rng.integers(0, q, (777, n), dtype=np.int64)
+    for psf in (T.PSFGPV(gp, 90.0), T.PSFPerturbation(gp, 3.0, 25.0)):
+        a, td = psf.trap_gen(seed=4)
+        psf.ctx.call("qf_set_chunk", 256)  # several chunks: the overlapped copy path with its two int16 buffers
+        e32 = psf.samp_p_batch(a, td, u, seed=5)
+        e16 = psf.samp_p_batch(a, td, u, seed=5, dtype=np.int16)
+        assert e16.dtype == np.int16 and np.array_equal(e16.astype(np.int32), e32)
+        u16, fl = psf.f_a_batch(a, e16)
+        assert np.array_equal(u16, u) and fl.all()
+        bad = u.copy()
+        bad[500, 3] = q
+        with pytest.raises(T.QfError) as ei:
+            psf.samp_p_batch(a, td, bad, seed=5)
+        assert ei.value.status == _ffi.QF_ERR_INVALID
+        bad[500, 3] = -1
+        with pytest.raises(T.QfError) as ei:
+            psf.samp_p_batch(a, td, bad, seed=5, dtype=np.int16)
+        assert ei.value.status == _ffi.QF_ERR_INVALID
+        assert np.array_equal(psf.samp_p_batch(a, td, u, seed=5), e32)  # the context is usable again
+    # s r so large that entries exceed int16
+    wide = T.PSFPerturbation(gp, 300.0, 60.0)
+    a, td = wide.trap_gen(seed=1)
+    with pytest.raises(T.QfError) as ei:
+        wide.samp_p_batch(a, td, u, seed=2, dtype=np.int16)
+    assert ei.value.status == _ffi.QF_ERR_NUMERIC
+    e = wide.samp_p_batch(a, td, u, seed=2)
+    assert np.abs(e).max() > 32767 and np.array_equal(O.f_a_classical_batch(a, e, q), u)
+    # ring
+    gr = T.GadgetParametersRing.init_default(8, 1024)
+    pr = T.PSFGPVRing(gr, 300.0, 1.005)
+    ar, tdr = pr.trap_gen(seed=1)
+    ur = rng.integers(0, 1024, (50, 8), dtype=np.int64)
+    er = pr.samp_p_batch(ar, tdr, ur, seed=3)
+    er16 = pr.samp_p_batch(ar, tdr, ur, seed=3, dtype=np.int16)
+    assert np.array_equal(er16.astype(np.int32), er)
+    uu, fl = pr.f_a_batch(ar, er16)
+    assert np.array_equal(uu, ur) and fl.all()
+
+
 # ----------------------------------------------------------------------------------
 # samplers: exact law
 # ----------------------------------------------------------------------------------

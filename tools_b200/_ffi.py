@@ -62,6 +62,9 @@ SIGNATURES = {
     "qf_samp_d_dev": (_i32, [_vp, _i64, _u64, _u64, _vp]),
     "qf_samp_p": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
     "qf_samp_p_dev": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
+    "qf_samp_p_i16": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
+    "qf_f_a_i16": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "qf_narrow_i32_i16_dev": (_i32, [_vp, _vp, _sz, _vp, _vp]),
     "qf_randomized_nearest_plane_gadget": (_i32, [_vp, _vp, _i64, _u64, _u64, _vp]),
     "qf_compress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _vp]),
     "qf_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _vp]),
@@ -71,6 +74,7 @@ SIGNATURES = {
     "qf_decode_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _i32, _vp]),
     "qf_sample_z": (_i32, [_vp, _sz, C.c_double, _u64, _vp]),
     "qf_debug_gemm_i8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _u64, _vp]),
+    "qf_probe_i8_peak": (_i32, [_i32, _i64, _i64, _i64, _i32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qf_fill_uniform_modq_dev": (_i32, [_vp, _sz, _u64, _u64, _vp]),
 }
 

@@ -127,7 +127,7 @@ struct qf_ctx {
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];
-    Dev dNorm, dFlag, dRetry, io_a, io_b, io_c, io_a2;
+    Dev dNorm, dFlag, dRetry, io_a, io_b, io_c, io_a2, io_h[2];
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // tcgen05 int8 path for the exact integer contractions
@@ -237,6 +237,8 @@ qf_status check_flag(qf_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (h) {
         CK(cudaMemsetAsync(ctx->dFlag.p, 0, sizeof(int), ctx->stream));
+        if (h & 32) return ctx->fail(QF_ERR_INVALID, "target entry outside [0,q)");
+        if (h & 64) return ctx->fail(QF_ERR_NUMERIC, "a Domain entry does not fit int16: use the int32 entry point");
         char buf[128];
         snprintf(buf, sizeof buf, "internal range check tripped (flag=%d): a value left its exact-integer range", h);
         return ctx->fail(QF_ERR_NUMERIC, buf);
@@ -2071,21 +2073,23 @@ qf_status qf_samp_p_dev(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t s
     });
 }
 
-qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
+// host-buffer samp_p; i16: results leave as int16 (half the device->host bytes)
+static qf_status samp_p_host(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, void* e_out, bool i16) {
     if (!ctx || batch < 0 || (batch > 0 && (!u || !e_out))) return QF_ERR_INVALID;
     if (batch == 0) return QF_OK;
     CK(cudaSetDevice(ctx->device));
     QF_TRY(samp_p_ready(ctx));
-    for (int64_t i = 0; i < batch * ctx->n; ++i)
-        if (u[i] < 0 || (uint64_t)u[i] >= ctx->prm.q) return ctx->fail(QF_ERR_INVALID, "target entry outside [0,q)");
     const long C = ctx->chunk;
+    const size_t esz = i16 ? 2 : 4;
     CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    if (i16) CK(ctx->io_h[0].ensure((size_t)C * ctx->dim * 2));
     // results leave through a second stream: the device->host copy of chunk i overlaps the computation of
     // chunk i+1 (two result buffers, events in both directions)
     const bool overlap = batch > C;
     if (overlap) {
-        CK(ctx->io_a2.ensure((size_t)C * ctx->dim * 4));
+        if (i16) CK(ctx->io_h[1].ensure((size_t)C * ctx->dim * 2));
+        else CK(ctx->io_a2.ensure((size_t)C * ctx->dim * 4));
         if (!ctx->copy_stream) {
             CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) {
@@ -2097,19 +2101,31 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
     int64_t idx = 0;
     QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
         const int slot = (int)(idx & 1);
-        int32_t* dres = (overlap && slot) ? ctx->io_a2.as<int32_t>() : ctx->io_a.as<int32_t>();
+        // int32 results of the chunk: with int16 output they are narrowed into the slot's int16 buffer, so one int32
+        // buffer serves both slots
+        int32_t* dres = (!i16 && overlap && slot) ? ctx->io_a2.as<int32_t>() : ctx->io_a.as<int32_t>();
         if (overlap && idx >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));  // buffer free again?
         CK(cudaMemcpyAsync(ctx->io_b.p, u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // the targets must be residues in [0, q): checked on the device (a host loop over batch x n values would sit in
+        // front of every call), reported by check_flag as QF_ERR_INVALID
+        LAUNCH(qf_launch_range_check_i64(ctx->io_b.as<int64_t>(), (size_t)Bc * ctx->n, ctx->prm.q, ctx->dFlag.as<int>(), ctx->stream));
         QF_TRY(ctx->prm.kind == QF_PSF_PERTURBATION
                    ? samp_p_pert_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres)
                    : samp_p_np_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres));
+        const void* src = dres;
+        if (i16) {
+            int16_t* d16 = ctx->io_h[overlap ? slot : 0].as<int16_t>();
+            LAUNCH(qf_launch_narrow_i32_i16(dres, d16, (size_t)Bc * ctx->dim, ctx->dFlag.as<int>(), ctx->stream));
+            src = d16;
+        }
+        char* dst = (char*)e_out + (size_t)b0 * ctx->dim * esz;
         if (overlap) {
             CK(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[slot], 0));
-            CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, dres, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaMemcpyAsync(dst, src, (size_t)Bc * ctx->dim * esz, cudaMemcpyDeviceToHost, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
         } else {
-            CK(cudaMemcpyAsync(e_out + b0 * ctx->dim, dres, (size_t)Bc * ctx->dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(dst, src, (size_t)Bc * ctx->dim * esz, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
         }
         ++idx;
@@ -2117,6 +2133,50 @@ qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed,
     }));
     if (overlap) CK(cudaStreamSynchronize(ctx->copy_stream));
     return check_flag(ctx);
+}
+
+qf_status qf_samp_p(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int32_t* e_out) {
+    return samp_p_host(ctx, u, batch, seed, first, e_out, false);
+}
+qf_status qf_samp_p_i16(qf_ctx* ctx, const int64_t* u, int64_t batch, uint64_t seed, uint64_t first, int16_t* e_out) {
+    return samp_p_host(ctx, u, batch, seed, first, e_out, true);
+}
+
+// int16 Domain input: widened on the device (the H2D copy, which dominates the host path, is halved)
+qf_status qf_f_a_i16(qf_ctx* ctx, const int16_t* sigma, int64_t batch, int64_t* u_out, uint8_t* in_domain) {
+    if (!ctx || batch < 0 || (batch > 0 && (!sigma || !u_out))) return QF_ERR_INVALID;
+    if (batch == 0) return QF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
+    if (ring ? !ctx->has_ring : !ctx->has_a) return ctx->fail(QF_ERR_NO_KEY, "no key installed");
+    const long C = ctx->chunk;
+    CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
+    CK(ctx->io_h[0].ensure((size_t)C * ctx->dim * 2));
+    CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
+    CK(ctx->io_c.ensure((size_t)C));
+    std::vector<uint8_t> flags((size_t)batch);
+    QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
+        CK(cudaMemcpyAsync(ctx->io_h[0].p, sigma + b0 * ctx->dim, (size_t)Bc * ctx->dim * 2, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(qf_launch_widen_i16_i32(ctx->io_h[0].as<int16_t>(), ctx->io_a.as<int32_t>(), (size_t)Bc * ctx->dim, ctx->stream));
+        QF_TRY(ring ? ring_f_a_chunk(ctx, ctx->io_a.as<int32_t>(), Bc, ctx->io_b.as<int64_t>(), ctx->io_c.as<uint8_t>())
+                    : f_a_chunk(ctx, ctx->io_a.as<int32_t>(), Bc, ctx->io_b.as<int64_t>(), ctx->io_c.as<uint8_t>()));
+        CK(cudaMemcpyAsync(u_out + b0 * ctx->n, ctx->io_b.p, (size_t)Bc * ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(flags.data() + b0, ctx->io_c.p, (size_t)Bc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return QF_OK;
+    }));
+    bool all = true;
+    for (int64_t b = 0; b < batch; ++b) all = all && flags[b];
+    if (in_domain) memcpy(in_domain, flags.data(), (size_t)batch);
+    if (!all) return ctx->fail(QF_ERR_NOT_IN_DOMAIN, "f_a: sigma not in the domain D_n (check_domain failed)");
+    return QF_OK;
+}
+
+// device utility for the final gather of int32 Domain results in 16 bits: *overflow (device int, caller-zeroed) |= 64
+qf_status qf_narrow_i32_i16_dev(const int32_t* in, int16_t* out, size_t count, int* overflow, void* cuda_stream) {
+    if ((!in || !out) && count) return QF_ERR_INVALID;
+    cudaError_t e = qf_launch_narrow_i32_i16(in, out, count, overflow, (cudaStream_t)cuda_stream);
+    return e == cudaSuccess ? QF_OK : (e == cudaErrorMisalignedAddress ? QF_ERR_INVALID : QF_ERR_CUDA);
 }
 
 // ---- PSFPerturbation::randomized_nearest_plane_gadget (mp_perturbation.rs:173-191) ----------------------------
@@ -2313,6 +2373,61 @@ qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int
         if (e != cudaSuccess) { fprintf(stderr, "qf_debug_gemm_i8: %s\n", cudaGetErrorString(e)); rc = QF_ERR_CUDA; }
     }
     if (rc == QF_OK && cudaMemcpy(out, dout, (size_t)B * N * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = QF_ERR_CUDA;
+    cudaFree(dx); cudaFree(dw); cudaFree(dout);
+    return rc;
+}
+
+// Peak of the int8 tensor pipe as this library can drive it: a plain one-digit-pair contraction (LX = LW = 1: 128 x 256
+// tiles, two accumulator buffers in TMEM, int32 store epilogue) on random bytes, long K.  `iters` launches timed one by one
+// (best = burst figure), then launches back to back for >= sustain_ms (sustained figure, clocks settled under load).
+qf_status qf_probe_i8_peak(int device, int64_t B, int64_t N, int64_t K, int iters, double sustain_ms, double* best_tops,
+                           double* sustained_tops) {
+    if (B < 1 || N < 1 || K < 128 || K > 65536 || (K & 127) || iters < 1) return QF_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return QF_ERR_CUDA;
+    int8_t* dx = nullptr; uint8_t* dw = nullptr; int32_t* dout = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st = nullptr;
+    qf_status rc = QF_OK;
+    const size_t xb = (size_t)B * K, wb = (size_t)N * K;
+    if (cudaMalloc(&dx, xb) != cudaSuccess || cudaMalloc(&dw, wb) != cudaSuccess || cudaMalloc(&dout, (size_t)B * N * 4) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
+        rc = QF_ERR_CUDA;
+    if (rc == QF_OK && (qf_launch_uniform_modq((int64_t*)dx, (long)(xb / 8), 1ull << 62, 11, 0, st) != cudaSuccess ||
+                        qf_launch_uniform_modq((int64_t*)dw, (long)(wb / 8), 1ull << 62, 12, 0, st) != cudaSuccess))
+        rc = QF_ERR_CUDA;
+    I8GemmArgs a{};
+    a.x = dx; a.ldx = K; a.x_plane = (long)xb;
+    a.w = dw; a.ldw = K; a.w_plane = (long)wb;
+    a.LX = 1; a.LW = 1; a.w_signed = 0; a.B = (int)B; a.N = (int)N; a.K = (int)K;
+    a.out_kind = 1; a.sign = 1; a.q = 0; a.out = dout; a.ldout = N; a.flag = nullptr;
+    const double ops = 2.0 * (double)B * (double)N * (double)K;
+    double best = 0, sustained = 0;
+    for (int i = 0; i < iters + 2 && rc == QF_OK; ++i) {  // two warm-ups
+        cudaEventRecord(e0, st);
+        if (qf_launch_gemm_i8(a, st) != cudaSuccess) { rc = QF_ERR_CUDA; break; }
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = QF_ERR_CUDA; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2 && ms > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    if (rc == QF_OK && sustain_ms > 0 && best > 0) {
+        const int reps = std::max(4, (int)(sustain_ms / (ops / (best * 1e12) * 1e3)) + 1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < reps; ++i)
+            if (qf_launch_gemm_i8(a, st) != cudaSuccess) { rc = QF_ERR_CUDA; break; }
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = QF_ERR_CUDA;
+        float ms = 0;
+        if (rc == QF_OK) cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0) sustained = ops * reps / (ms * 1e-3) / 1e12;
+    }
+    if (best_tops) *best_tops = best;
+    if (sustained_tops) *sustained_tops = sustained;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
     cudaFree(dx); cudaFree(dw); cudaFree(dout);
     return rc;
 }

@@ -651,3 +651,77 @@ cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long
     add_cols_i32_kernel<<<grid_for((long long)B * ncols, TPB), TPB, 0, stream>>>(e, lde, sol, ldsol, cols, ncols, B);
     return cudaGetLastError();
 }
+
+// ---- narrow boundary types: int16 Domain values (|entry| <= 6 s r < 2^15 at C2 / C3) and the device-side range check of
+// the targets ------------------------------------------------------------------------------------------------------------
+namespace {
+// 8 values per thread: two 128-bit loads, one 128-bit store; *flag |= 64 when a value does not fit int16
+__global__ void __launch_bounds__(256) narrow_i32_i16_kernel(const int32_t* __restrict__ in, int16_t* __restrict__ out, size_t count,
+                                                             int* flag) {
+    const size_t groups = count >> 3;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const int4 a = __ldcs(reinterpret_cast<const int4*>(in) + 2 * g), b = __ldcs(reinterpret_cast<const int4*>(in) + 2 * g + 1);
+        const int v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            bad |= (v[2 * t] != (int)(short)v[2 * t]) | (v[2 * t + 1] != (int)(short)v[2 * t + 1]);
+            pk[t] = ((unsigned)v[2 * t] & 0xFFFFu) | ((unsigned)v[2 * t + 1] << 16);
+        }
+        __stcs(reinterpret_cast<uint4*>(out) + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (count & 7)) {
+        const size_t i = (groups << 3) + threadIdx.x;
+        const int v = in[i];
+        bad |= v != (int)(short)v;
+        out[i] = (int16_t)v;
+    }
+    if (bad && flag) atomicOr(flag, 64);
+}
+__global__ void __launch_bounds__(256) widen_i16_i32_kernel(const int16_t* __restrict__ in, int32_t* __restrict__ out, size_t count) {
+    const size_t groups = count >> 3;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(in) + g);
+        const unsigned w[4] = {a.x, a.y, a.z, a.w};
+        int v[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            v[2 * t] = (int)(short)(w[t] & 0xFFFFu);
+            v[2 * t + 1] = (int)(short)(w[t] >> 16);
+        }
+        __stcs(reinterpret_cast<int4*>(out) + 2 * g, make_int4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<int4*>(out) + 2 * g + 1, make_int4(v[4], v[5], v[6], v[7]));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (count & 7)) {
+        const size_t i = (groups << 3) + threadIdx.x;
+        out[i] = (int32_t)in[i];
+    }
+}
+// *flag |= 32 when some residue lies outside [0, q)
+__global__ void __launch_bounds__(256) range_check_i64_kernel(const int64_t* __restrict__ v, size_t count, unsigned long long q, int* flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        bad |= (unsigned long long)v[i] >= q;  // negative values are huge as unsigned
+    if (bad) atomicOr(flag, 32);
+}
+}  // namespace
+cudaError_t qf_launch_narrow_i32_i16(const int32_t* in, int16_t* out, size_t count, int* flag, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if ((((uintptr_t)in) & 15) || (((uintptr_t)out) & 15)) return cudaErrorMisalignedAddress;
+    narrow_i32_i16_kernel<<<grid_for((long long)((count >> 3) + 1), 256, 148 * 8), 256, 0, stream>>>(in, out, count, flag);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_widen_i16_i32(const int16_t* in, int32_t* out, size_t count, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    if ((((uintptr_t)in) & 15) || (((uintptr_t)out) & 15)) return cudaErrorMisalignedAddress;
+    widen_i16_i32_kernel<<<grid_for((long long)((count >> 3) + 1), 256, 148 * 8), 256, 0, stream>>>(in, out, count);
+    return cudaGetLastError();
+}
+cudaError_t qf_launch_range_check_i64(const int64_t* v, size_t count, unsigned long long q, int* flag, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    range_check_i64_kernel<<<grid_for((long long)count, 256, 148 * 4), 256, 0, stream>>>(v, count, q, flag);
+    return cudaGetLastError();
+}

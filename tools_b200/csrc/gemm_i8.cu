@@ -473,6 +473,11 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     // (wider tiles, ND <= 4, keep their width and take the generic epilogue)
     if (a.out_kind == 3 && nt > 64 && nt < 128) nt = 64;
     if (a.out_kind == 3 && nt > 32 && nt < 64) nt = 32;
+    {   // two pipeline stages of LX x-planes + LW w-planes must fit in shared memory
+        const int bk0 = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
+        const int budget0 = 227 * 1024 - 1024 - 256;
+        while (nt > 16 && 2 * (a.LX * TILE_M * bk0 + a.LW * nt * bk0) > budget0) nt = (a.out_kind == 3 && nt == 64) ? 32 : nt - 16;
+    }
     I8Params p{};
     p.d_lo = a.d_lo;
     p.scale_mul = 1.0;

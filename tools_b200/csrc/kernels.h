@@ -209,6 +209,12 @@ cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long
 cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int fs_last, int ss_last, int L,
                                     double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
 
+// narrow boundary types (elementwise.cu): int16 Domain values, device-side range check of residues
+// narrow: *flag |= 64 when a value does not fit int16; range check: *flag |= 32 when a residue is outside [0, q)
+cudaError_t qf_launch_narrow_i32_i16(const int32_t* in, int16_t* out, size_t count, int* flag, cudaStream_t stream);
+cudaError_t qf_launch_widen_i16_i32(const int16_t* in, int32_t* out, size_t count, cudaStream_t stream);
+cudaError_t qf_launch_range_check_i64(const int64_t* v, size_t count, unsigned long long q, int* flag, cudaStream_t stream);
+
 // polynomial arithmetic of the ring short basis (setup.cu): P[2][2][n], Q[k][2][n]
 cudaError_t qf_launch_ring_basis_polys(const int32_t* e, const int32_t* r, const int32_t* w, const int64_t* sk, int n, int k,
                                        int64_t* P, int64_t* Q, cudaStream_t stream);

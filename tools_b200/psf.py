@@ -94,11 +94,15 @@ class _PSFBase:
         """u[b] = A sigma[b]; returns (u, in_domain).  strict=True raises NotInDomain like the
         reference's assert! when some sigma is outside D_n."""
         self._install_a(a)
-        s, oob = _domain_i32(sigmas, self._domain_shape)
+        if isinstance(sigmas, np.ndarray) and sigmas.dtype == np.int16:  # narrow Domain form: half the host->device bytes
+            assert sigmas.shape[1:] == self._domain_shape, "sigma has the wrong shape"
+            s, oob, fn = np.ascontiguousarray(sigmas), np.zeros(sigmas.shape[0], dtype=bool), "qf_f_a_i16"
+        else:
+            (s, oob), fn = _domain_i32(sigmas, self._domain_shape), "qf_f_a"
         b = s.shape[0]
         u = np.empty((b, self.n), dtype=np.int64)
         flags = np.empty(b, dtype=np.uint8)
-        st = self.ctx.status("qf_f_a", _ffi.ptr(s), b, _ffi.ptr(u), _ffi.ptr(flags))
+        st = self.ctx.status(fn, _ffi.ptr(s), b, _ffi.ptr(u), _ffi.ptr(flags))
         if st not in (_ffi.QF_OK, _ffi.QF_ERR_NOT_IN_DOMAIN):
             raise QfError(st, self.ctx._lib.qf_last_error(self.ctx._h).decode())
         ok = flags.astype(bool) & ~oob
@@ -114,13 +118,18 @@ class _PSFBase:
         return u[0]
 
     # -- PSF::samp_p ------------------------------------------------------------------------
-    def samp_p_batch(self, a, td, us: np.ndarray, seed=None, first_index: int = 0) -> np.ndarray:
+    def samp_p_batch(self, a, td, us: np.ndarray, seed=None, first_index: int = 0, dtype=np.int32) -> np.ndarray:
+        """dtype=np.int16 returns the same preimages in 16 bits (qf_samp_p_i16: half the device->host bytes; raises
+        QfError if an entry does not fit, which needs 6 s r >= 2^15)."""
         self._install_a(a)
         self._install_td(a, td)
         u = np.ascontiguousarray(us, dtype=np.int64)
         assert u.ndim == 2 and u.shape[1] == self.n
-        e = np.empty((u.shape[0],) + self._domain_shape, dtype=np.int32)
-        self.ctx.call("qf_samp_p", _ffi.ptr(u), u.shape[0], _seed(seed), first_index, _ffi.ptr(e))
+        dtype = np.dtype(dtype)
+        assert dtype in (np.dtype(np.int32), np.dtype(np.int16))
+        e = np.empty((u.shape[0],) + self._domain_shape, dtype=dtype)
+        self.ctx.call("qf_samp_p" if dtype == np.int32 else "qf_samp_p_i16", _ffi.ptr(u), u.shape[0], _seed(seed), first_index,
+                      _ffi.ptr(e))
         return e
 
     def samp_p(self, a, td, u, seed=None) -> np.ndarray:
