@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""bench.py -- samp_p preimages/s (+ f_a evals/s) of the B200 backend on BASELINE.json configs[1]:
-PSFGPV, n = 256, q = 2^24, classical gadget, synthetic targets (the 1M-target workload is
-consumed in steps of --batch targets per GPU).
+"""bench.py -- samp_p preimages/s (+ f_a evals/s) of the B200 backend on the configurations BASELINE.json names.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--batch B] [--impl ours|reference]
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
-"""
+Default workload = BASELINE.json configs[1] (C2: PSFGPV n = 256, q = 2^24, 1M-target workload consumed in steps of
+--batch targets per GPU); the default single-GPU run also carries `extra.rows`: C1, C3 (ring f_a / samp_p), C4 (one
+PSFPerturbation shard, TrapGen's A_bar R timed separately) and C5 (compression, d in {1,4,10,11}), each with its own
+roofline entry.  One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means."""
 import argparse
 import json
 import math
@@ -20,21 +20,43 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
+
+def gpv_s_for(n, m_bar):
+    # SURVEY 8d: s = ceil((sqrt(m_bar)+1) * sqrt(5) * log2 n)   (bound from short_basis_classical.rs:233-235)
+    return float(math.ceil((math.sqrt(m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))
+
+
+def gpv_s(gp):
+    return gpv_s_for(gp.n, gp.m_bar)
+
+
+def pert_s_for(m_bar, nk):
+    # s above sqrt(5 (s1(R)^2 + 1) + 1) with s1(R) ~ (sqrt(m_bar) + sqrt(nk)) / sqrt(2); 15 % margin
+    s1 = (math.sqrt(m_bar) + math.sqrt(nk)) / math.sqrt(2)
+    return float(math.ceil(1.15 * math.sqrt(5 * (s1 * s1 + 1) + 1)))
+
+
+# name: kind, n, q, (r), default targets per step per GPU, description
 WORKLOADS = {
-    # name: (n, q, description)
-    "c2": (256, 2**24, "C2 PSFGPV n=256 q=2^24 classical gadget (m=12352), uniform synthetic targets"),
-    "c2small": (64, 2**24, "reduced PSFGPV n=64 q=2^24 (m=3108) -- smoke-size variant, not the headline"),
+    "c1": dict(kind="pert", n=8, q=64, r=3.0, s=25.0, batch=262144,
+               desc="C1 README PSFPerturbation init_default(8, 64), r=3, s=25 (m=105), uniform synthetic targets"),
+    "c2": dict(kind="gpv", n=256, q=2**24, batch=75776,  # four internal chunks of 148 SMs x 128 targets
+               desc="C2 PSFGPV n=256 q=2^24 classical gadget (m=12352), uniform synthetic targets"),
+    "c2small": dict(kind="gpv", n=64, q=2**24, batch=65536,
+                    desc="reduced PSFGPV n=64 q=2^24 (m=3108) -- smoke-size variant, not the headline"),
+    "c3": dict(kind="ring", n=256, q=3329, batch=131072,
+               desc="C3 PSFGPVRing over X^256+1 mod 3329 (14 polynomials, D=3584), uniform synthetic targets"),
+    "c4": dict(kind="pert", n=512, q=2**32 - 5, r=9.0, s=None, batch=60416,  # eight internal chunks of 7552 targets
+               desc="C4 PSFPerturbation n=512 q=2^32-5 k=32 r=9 (m=32849), targets sharded over the GPUs"),
+    "c5": dict(kind="compress", n=256, q=3329, batch=16 * 1024 * 1024,
+               desc="C5 LossyCompressionFIPS203 compress/decompress on 16 Mi polynomials of degree 256 mod 3329"),
 }
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
-
-
-def gpv_s(gp):
-    # SURVEY 8d: s = ceil((sqrt(m_bar)+1) * sqrt(5) * log2 n)   (bound from short_basis_classical.rs:233-235)
-    return float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(gp.n)))
 
 
 class ClockSampler:
@@ -84,6 +106,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ======================================================================================================================
+# reference arm: the CPU restatement of the reference's own algorithm (oracle/) on the box's host threads
+# ======================================================================================================================
 def exact_abar_r(a_bar, r, q):
     """(A_bar R) mod q in float64 BLAS, exact: A_bar split into 12-bit limbs."""
     rf = r.astype(np.float64)
@@ -99,14 +124,50 @@ def exact_abar_r(a_bar, r, q):
     return acc.astype(np.int64)
 
 
+def oracle_classical_key(n, q, seed):
+    """(A, R, gp) from the oracle's restatement of gen_trapdoor (gadget_classical.rs:56-68), numpy-vectorised product."""
+    from oracle import qfall_oracle as O
+
+    gp = O.GadgetParameters.init_default(n, q)
+    rng = np.random.default_rng(seed)
+    nk = n * gp.k
+    a_bar = rng.integers(0, q, (n, gp.m_bar), dtype=np.int64)
+    r = (rng.integers(0, 2, (gp.m_bar, nk)) - rng.integers(0, 2, (gp.m_bar, nk))).astype(np.int8)
+    ar = exact_abar_r(a_bar, r, q)
+    g = np.zeros((n, nk), dtype=np.int64)
+    gvec = [pow(gp.base, t, q) for t in range(gp.k)]
+    for j in range(n):
+        g[j, j * gp.k:(j + 1) * gp.k] = gvec
+    a = np.concatenate([a_bar, (g - ar) % q], axis=1)
+    return gp, a, r
+
+
+def oracle_short_basis(gp, a, r):
+    """gen_short_basis_for_trapdoor (short_basis_classical.rs:54-110, tag = I) restated with numpy blocks:
+    S = [[R S', I + R W],[S', W]], S' = I (x) S_k (columns reversed iff base^k = q), W = digits of -A[:, :m_bar]."""
+    from oracle import qfall_oracle as O
+
+    n, k, mb, q, base = gp.n, gp.k, gp.m_bar, gp.q, gp.base
+    nk = n * k
+    sk = np.array(O.short_basis_gadget_block(k, base, q), dtype=np.int64)
+    sp = np.kron(np.eye(n, dtype=np.int64), sk)
+    if base**k == q:
+        sp = sp[:, ::-1]
+    neg = (-a[:, :mb]) % q
+    w = np.zeros((nk, mb), dtype=np.int64)
+    for t in range(k):
+        w[t::k, :] = (neg // base**t) % base
+    rf = r.astype(np.float64)
+    top_l = np.rint(rf @ sp.astype(np.float64)).astype(np.int64)
+    top_r = np.eye(mb, dtype=np.int64) + np.rint(rf @ w.astype(np.float64)).astype(np.int64)
+    return np.block([[top_l, top_r], [sp, w]])
+
+
 def run_reference(args):
-    """The reference arm: the CPU restatement of the reference's own algorithm (oracle/oracle_c.c,
-    the reference crate cannot be built in this image) on all host threads, on a bounded sample
-    of the same workload."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import oracle_c as OC
-    from tools_b200 import gadget  # host-side numpy key setup only (untimed)
+    from oracle import qfall_oracle as O
 
     # torchrun exports OMP_NUM_THREADS=1; the (untimed) numpy key setup below would then run its BLAS calls on one
     # thread.  The timed part uses the C port's own pthreads (OC.threads()) and is not affected.
@@ -116,63 +177,199 @@ def run_reference(args):
         threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:
         pass
-
-    n, q, desc = WORKLOADS[args.workload]
-    gp = gadget.GadgetParameters.init_default(n, q)
-    s = gpv_s(gp)
-    rng = np.random.default_rng(2)
-    t0 = time.time()
-    a_bar = rng.integers(0, q, (n, gp.m_bar), dtype=np.int64)
-    r = (rng.integers(0, 2, (gp.m_bar, n * gp.k)) - rng.integers(0, 2, (gp.m_bar, n * gp.k))).astype(np.int8)
-    ar = exact_abar_r(a_bar, r, q)
-    g = np.zeros((n, n * gp.k), dtype=np.int64)
-    for j in range(n):
-        g[j, j * gp.k:(j + 1) * gp.k] = [(2**t) % q for t in range(gp.k)]
-    a = np.concatenate([a_bar, (g - ar) % q], axis=1)
-    basis = gadget.gen_short_basis_for_trapdoor(gp, a, r)
-    gso = np.linalg.qr(basis.astype(np.float64))
-    gso = gso[0] * np.diag(gso[1])[None, :]
-    piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
-    log(f"[reference] key setup {time.time() - t0:.1f}s (untimed)")
-    threads = OC.threads()
-    per_step = max(threads, args.ref_targets or threads)
-    bt = np.ascontiguousarray(basis.astype(np.float64).T)
-    gt = np.ascontiguousarray(gso.T)
     import ctypes as C
 
+    wl = WORKLOADS[args.workload]
+    kind, n, q, desc = wl["kind"], wl["n"], wl["q"], wl["desc"]
+    threads = OC.threads()
+    rng = np.random.default_rng(2)
     lib = OC.lib()
+    t0 = time.time()
+    unit, metric = "preimages/s", "samp_p_preimages_per_s"
+    if kind == "gpv":
+        gp, a, r = oracle_classical_key(n, q, 2)
+        s = gpv_s_for(n, gp.m_bar)
+        basis = oracle_short_basis(gp, a, r)
+        assert not ((a.astype(object) @ basis[:, :3].astype(object)) % q).any()  # basis columns lie in Lambda^perp(A)
+        qr = np.linalg.qr(basis.astype(np.float64))
+        gso = qr[0] * np.diag(qr[1])[None, :]
+        piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
+        per_step = max(threads, args.ref_targets or threads)
+        bt = np.ascontiguousarray(basis.astype(np.float64).T)
+        gt = np.ascontiguousarray(gso.T)
+        m = gp.m
+        cfg = {"workload": desc, "targets_per_step": per_step, "s": s}
+        sample = ("%d targets/step, one independent instance per thread; reference loop structure in fp64 (gpv.rs:152-161) "
+                  "with the per-call Gaussian elimination hoisted out" % per_step)
 
-    def step(seed):
-        u = rng.integers(0, q, (per_step, n), dtype=np.int64)
-        e = np.empty((per_step, gp.m), dtype=np.int32)
-        lib.orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
-                           C.c_void_p(ainv.ctypes.data), C.c_long(len(piv)), C.c_void_p(u.ctypes.data),
-                           C.c_void_p(e.ctypes.data), C.c_long(per_step), C.c_long(n), C.c_long(gp.m), C.c_uint64(q),
-                           C.c_double(s), C.c_uint64(seed), C.c_int(threads))
-        return u, e
+        def step(seed):
+            u = rng.integers(0, q, (per_step, n), dtype=np.int64)
+            e = np.empty((per_step, m), dtype=np.int32)
+            lib.orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
+                               C.c_void_p(ainv.ctypes.data), C.c_long(len(piv)), C.c_void_p(u.ctypes.data),
+                               C.c_void_p(e.ctypes.data), C.c_long(per_step), C.c_long(n), C.c_long(m), C.c_uint64(q),
+                               C.c_double(s), C.c_uint64(seed), C.c_int(threads))
+            return u, e, per_step
 
+        def verify(u, e):
+            assert np.array_equal(O.f_a_classical_batch(a, e[:2], q), u[:2])
+    elif kind == "pert":
+        gp, a, r = oracle_classical_key(n, q, 2)
+        rr = wl["r"]
+        s = wl["s"] or pert_s_for(gp.m_bar, n * gp.k)
+        lmat = O.compute_sqrt_sigma_2(r, s, rr, 2)
+        sb = np.array(O.short_basis_gadget(gp), dtype=np.float64)
+        sg = O.gso_f64(sb)
+        per_step = max(threads, args.ref_targets or (threads * (64 if gp.m < 1000 else 1)))
+        cfg = {"workload": desc, "targets_per_step": per_step, "s": s, "r": rr}
+        sample = ("%d targets/step, one independent instance per thread; reference loop structure in fp64 "
+                  "(mp_perturbation.rs:304-336: dense sqrt(Sigma_2) product, dense nk x nk gadget nearest plane)" % per_step)
+
+        def step(seed):
+            u = rng.integers(0, q, (per_step, n), dtype=np.int64)
+            e = OC.samp_p_pert(lmat, a, r, sb, sg, u, n, gp.k, gp.m_bar, 2, q, rr, seed, threads)
+            return u, e, per_step
+
+        def verify(u, e):
+            assert np.array_equal(O.f_a_classical_batch(a, e[:2], q), u[:2])
+    elif kind == "ring":
+        gp = O.GadgetParametersRing.init_default(n, q)
+        s = ((2 * 2 * 1.005 * math.sqrt(n) + 1) * 2) * 4
+        a_bar = [int(x) for x in rng.integers(0, q, n)]
+        rt = [[int(x) for x in np.rint(rng.normal(0, 1.005 / math.sqrt(2 * math.pi), n))] for _ in range(gp.k)]
+        et = [[int(x) for x in np.rint(rng.normal(0, 1.005 / math.sqrt(2 * math.pi), n))] for _ in range(gp.k)]
+        a = O.gen_trapdoor_ring_lwe(gp, a_bar, rt, et)
+        emb = np.array(O.coeff_embed(O.gen_short_basis_for_trapdoor_ring(gp, a, rt, et), n), dtype=np.float64)
+        gso = O.gso_f64(emb)
+        piv = np.arange(n, dtype=np.int32)
+        ainv = np.eye(n, dtype=np.int64)
+        per_step = max(threads, args.ref_targets or threads * 8)
+        bt, gt = np.ascontiguousarray(emb.T), np.ascontiguousarray(gso.T)
+        d = emb.shape[0]
+        cfg = {"workload": desc, "targets_per_step": per_step, "s": s}
+        sample = ("%d targets/step; GPV08 SampleD on the embedded basis in fp64 with the basis and its GSO built ONCE "
+                  "(the reference rebuilds both per call, gpv_ring.rs:169,205-211 -- favours the CPU arm)" % per_step)
+
+        def step(seed):
+            u = rng.integers(0, q, (per_step, n), dtype=np.int64)
+            e = np.empty((per_step, d), dtype=np.int32)
+            lib.orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
+                               C.c_void_p(ainv.ctypes.data), C.c_long(n), C.c_void_p(u.ctypes.data), C.c_void_p(e.ctypes.data),
+                               C.c_long(per_step), C.c_long(n), C.c_long(d), C.c_uint64(q), C.c_double(s), C.c_uint64(seed),
+                               C.c_int(threads))
+            return u, e, per_step
+
+        def verify(u, e):
+            assert O.f_a_ring(a, e[0].reshape(gp.k + 2, n).tolist(), n, q) == u[0].tolist()
+    else:  # compress
+        unit, metric = "GB/s", "lossy_compress_GBps"
+        count = (args.ref_targets or 2 * 1024 * 1024) * 256
+        x = rng.integers(0, q, count).astype(np.uint16)
+        cfg = {"workload": desc, "polys_per_step": count // 256, "d": 10}
+        sample = "%d polynomials/step, d = 10, all host threads (lossy_compression_fips203.rs:101-111 per coefficient)" % (count // 256)
+
+        def step(seed):
+            y = OC.compress_u16(x, q, 10, False, threads)
+            return x, y, count * 4 / 1e9
+
+        def verify(u, e):
+            assert np.array_equal(e[:1000].astype(np.uint64), O.lossy_compress_np(u[:1000], 10, q))
+    log(f"[reference] key setup {time.time() - t0:.1f}s (untimed)")
     for w in range(args.warmup):
         step(w)
     t0 = time.perf_counter()
+    units = 0
     for k in range(args.steps):
-        u, e = step(100 + k)
+        u, e, cnt = step(100 + k)
+        units += cnt
     dt = time.perf_counter() - t0
-    # the timed output is a valid preimage set
-    from oracle import qfall_oracle as O
-
-    assert np.array_equal(O.f_a_classical_batch(a, e[:2], q), u[:2])
-    val = args.steps * per_step / dt
+    verify(u, e)
+    val = units / dt
     line = {
-        "impl": "reference", "metric": "samp_p_preimages_per_s", "value": val, "unit": "preimages/s",
+        "impl": "reference", "metric": metric, "value": val, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "targets_per_step": per_step, "s": s},
-        "cpu_baseline": {"value": val, "unit": "preimages/s", "cores": threads, "kind": "port",
-                         "sample": f"{per_step} targets/step x {args.steps} steps, one independent instance per thread; "
-                                   "reference loop structure in fp64 (gpv.rs:152-161) with the per-call Gaussian "
-                                   "elimination hoisted out"},
-        "e2e": {"value": val, "unit": "preimages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if kind != "compress" else "u16",
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================================
+# our arm
+# ======================================================================================================================
+def measure_i8_peak(local):
+    """Measured int8 tensor-pipe ceiling (qf_probe_i8_peak): burst and sustained TOP/s of a plain one-digit-pair
+    tcgen05 kind::i8 contraction with long K."""
+    from tools_b200 import _ffi
+
+    best, sus = _ffi.C.c_double(), _ffi.C.c_double()
+    st = _ffi.lib().qf_probe_i8_peak(local, 37888, 8192, 16384, 8, 1500.0, _ffi.C.byref(best), _ffi.C.byref(sus))
+    if st != 0 or best.value <= 0:
+        return None
+    return {"burst_tops": best.value, "sustained_tops": sus.value,
+            "how": "qf_probe_i8_peak: 37888 x 8192 x 16384 u8 x s8 contraction (LX = LW = 1, 128 x 256 tiles, double-buffered "
+                   "TMEM, int32 store), random bytes; best of 8 launches (burst), back to back for 1.5 s (sustained)"}
+
+
+def compress_headline(args, torch, dev, rank, world, local, barrier):
+    """--workload c5: compress + decompress GB/s at d = 10 over all ranks (shard by polynomial index, no collective)."""
+    import bench_rows as BR
+    from tools_b200.compression import compress_dev
+
+    npoly = args.batch or WORKLOADS["c5"]["batch"]
+    count = npoly * 256
+    x = torch.randint(0, 3329, (count,), dtype=torch.int32, device=dev).to(torch.int16)
+    y = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(args.warmup):
+        compress_dev(x.data_ptr(), y.data_ptr(), count, 3329, 10, st)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        compress_dev(x.data_ptr(), y.data_ptr(), count, 3329, 10, st)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * count * 4 / (ms * 1e-3) / 1e9
+    # end to end: pinned host buffers through qf_compress_u16 (H2D + D2H inside)
+    from tools_b200 import _ffi
+
+    e2e_count = 1 << 28
+    hx = torch.empty(e2e_count, dtype=torch.int16).pin_memory()
+    hy = torch.empty(e2e_count, dtype=torch.int16).pin_memory()
+    hx.copy_(x[:e2e_count].cpu())
+    lib = _ffi.lib()
+    lib.qf_compress_u16(_ffi.ptr(hx.numpy()), _ffi.ptr(hy.numpy()), e2e_count, 3329, 10, 0, None)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        assert lib.qf_compress_u16(_ffi.ptr(hx.numpy()), _ffi.ptr(hy.numpy()), e2e_count, 3329, 10, 0, None) == 0
+    e2e_dt = (time.perf_counter() - t0) / 3
+    if rank != 0:
+        return
+    rows = BR.row_compress(dev, npoly) if world == 1 else []
+    line = {"metric": "lossy_compress_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c5"]["desc"], "polys_per_step_per_gpu": npoly, "d": 10,
+                       "l2": "17 GB per pass, far beyond L2"},
+            "e2e": {"value": world * e2e_count * 4 / e2e_dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e2e_count * 2,
+                    "d2h_bytes_per_step": e2e_count * 2},
+            "gpu_launches": args.steps,
+            "roofline": BR.hbm_roofline("compress_u16_kernel", count * 4, ms / args.steps, "compress_u16_kernel"),
+            "cpu_baseline": None, "clocks": clock_info, "extra": {"rows": rows}}
     print(json.dumps(line), flush=True)
 
 
@@ -186,6 +383,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-targets", type=int, default=0, help="reference arm: targets per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.rows block of the default run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -214,17 +412,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n, q, desc = WORKLOADS[args.workload]
-    gp = T.GadgetParameters.init_default(n, q)
-    s = gpv_s(gp)
-    batch = args.batch or (75776 if args.workload == "c2" else 65536)  # c2: four internal chunks of 148 x 128 targets
+    wl = WORKLOADS[args.workload]
+    kind, n, q, desc = wl["kind"], wl["n"], wl["q"], wl["desc"]
+    if kind == "compress":
+        compress_headline(args, torch, dev, rank, world, local, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    batch = args.batch or wl["batch"]
     t0 = time.time()
-    psf = T.PSFGPV(gp, s, device=local)
+    r_par = 1.0
+    if kind == "gpv":
+        gp = T.GadgetParameters.init_default(n, q)
+        s = gpv_s(gp)
+        psf = T.PSFGPV(gp, s, device=local)
+        dim, dom_shape = gp.m, (gp.m,)
+    elif kind == "pert":
+        gp = T.GadgetParameters.init_default(n, q)
+        r_par = wl["r"]
+        s = wl["s"] or pert_s_for(gp.m_bar, n * gp.k)
+        psf = T.PSFPerturbation(gp, r_par, s, device=local)
+        dim, dom_shape = gp.m, (gp.m,)
+    else:
+        gp = T.GadgetParametersRing.init_default(n, q)
+        s = ((2 * 2 * 1.005 * math.sqrt(n) + 1) * 2) * 4  # gpv_ring.rs:296-298
+        psf = T.PSFGPVRing(gp, s, 1.005, device=local)
+        dim, dom_shape = n * (gp.k + 2), (gp.k + 2, n)
+    ctx = psf.ctx
+    ctx.call("qf_profile", 1)
     a, td = psf.trap_gen(seed=2)  # same seed on every rank: the key is replicated, not communicated
+    t_trapgen = time.time() - t0
+    tg = [_ffi.C.c_double() for _ in range(6)]
+    tgl = [_ffi.C.c_uint64() for _ in range(2)]
+    ctx.call("qf_profile_read", _ffi.C.byref(tg[0]), _ffi.C.byref(tg[1]), _ffi.C.byref(tgl[0]), _ffi.C.byref(tg[2]),
+             _ffi.C.byref(tg[3]), _ffi.C.byref(tg[4]), _ffi.C.byref(tgl[1]))
+    ctx.call("qf_profile", 0)
+    trapgen_info = {"trap_gen_s": t_trapgen,
+                    "abar_r_tcgen05": {"ms": tg[2].value, "useful_ops": tg[3].value,
+                                       "TOPs": tg[3].value / tg[2].value / 1e9 if tg[2].value else None,
+                                       "launches": int(tgl[1].value)} if kind != "ring" else None}
     psf._install_a(a)
     psf._install_td(a, td)
-    ctx = psf.ctx
-    log(f"[rank {rank}] key setup {time.time() - t0:.1f}s  m={gp.m} s={s} batch/step/gpu={batch}")
+    log(f"[rank {rank}] key setup {time.time() - t0:.1f}s  dim={dim} s={s} batch/step/gpu={batch}")
     # a dedicated (non-default) stream shared by torch's events and the library's launches
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
@@ -235,7 +464,7 @@ def main():
 
     total_steps = args.warmup + args.steps
     u = torch.empty((batch, n), dtype=torch.int64, device=dev)
-    e = torch.empty((batch, gp.m), dtype=torch.int32, device=dev)
+    e = torch.empty((batch,) + dom_shape, dtype=torch.int32, device=dev)
 
     def fill_targets(step_idx):
         # Philox-seeded uniform targets, distinct per (rank, step)
@@ -287,8 +516,9 @@ def main():
     ctx.call("qf_synchronize")
     assert torch.equal(uo, u), "A e != u in the timed output"
     assert bool(fl.all()), "a timed preimage fails check_domain"
-    # spherical law: E||e||^2 = m s^2 / (2 pi) for D_{Lambda_u^perp(A), s}
-    norm_ratio = float((e[:4096].double() ** 2).sum(1).mean().item() / (gp.m * s * s / (2 * math.pi)))
+    # spherical law: E||e||^2 = dim (s r)^2 / (2 pi) for D_{Lambda_u^perp(A), s r}
+    norm_ratio = float((e[:4096].double() ** 2).reshape(min(batch, 4096), -1).sum(1).mean().item()
+                       / (dim * (s * r_par) ** 2 / (2 * math.pi)))
 
     # ---- f_a evals/s (device resident; sigma = the preimages, in domain) ---------------------------------
     for _ in range(3):
@@ -308,15 +538,40 @@ def main():
         fa_ms = float(t.item())
     fa_value = world * fa_steps * batch / (fa_ms * 1e-3)
 
+    # ---- final gather over NVLink: the last step's shards, narrowed to int16 on the device, are
+    # gathered to rank 0 with one NCCL gather when they fit there; verified on rank 0 against the gathered targets --------
+    gather_info = None
+    if world > 1:
+        from tools_b200.sharding import gather_domain_i16
+
+        gather_info = gather_domain_i16(torch, dist, lib, _ffi, e, u, rank, world, dev, tstream, max_bytes=64 << 30)
+        if rank == 0 and gather_info and gather_info.get("gathered") is not None:
+            ge, gu = gather_info.pop("gathered")
+            # rank 0 checks the LAST rank's shard with its own (replicated) key: A e = u
+            lo = (world - 1) * batch
+            chk_e = ge[lo:lo + min(batch, 8192)].to(torch.int32).contiguous()
+            chk_u = torch.empty((chk_e.shape[0], n), dtype=torch.int64, device=dev)
+            chk_f = torch.empty(chk_e.shape[0], dtype=torch.uint8, device=dev)
+            ctx.call("qf_f_a_dev", _ffi.ptr(chk_e.data_ptr()), chk_e.shape[0], _ffi.ptr(chk_u.data_ptr()), _ffi.ptr(chk_f.data_ptr()))
+            ctx.call("qf_synchronize")
+            assert torch.equal(chk_u, gu[lo:lo + chk_e.shape[0]]) and bool(chk_f.all()), "gathered shard: A e != u"
+            gather_info["verified"] = "A e = u on the last rank's gathered shard (rank 0, replicated key)"
+            del ge, gu, chk_e, chk_u, chk_f
+        elif gather_info:
+            gather_info.pop("gathered", None)
+
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ----------------
-    e2e_batch = batch
+    # int16 Domain form when every entry fits (|e_i| <= 6 s r < 2^15: C2, C3; not C1/C4 sized s r), else int32
+    e2e_i16 = 6.5 * s * r_par < 32767
+    e2e_batch = batch if dim * batch * 4 <= (6 << 30) else max(1024, ((6 << 30) // (dim * 4)) // 1024 * 1024)
     hu = torch.empty((e2e_batch, n), dtype=torch.int64).pin_memory()
-    he = torch.empty((e2e_batch, gp.m), dtype=torch.int32).pin_memory()
-    hu.copy_(u.cpu())
+    he = torch.empty((e2e_batch,) + dom_shape, dtype=torch.int16 if e2e_i16 else torch.int32).pin_memory()
+    hu.copy_(u[:e2e_batch].cpu())
     hu_np, he_np = hu.numpy(), he.numpy()
+    e2e_fn = "qf_samp_p_i16" if e2e_i16 else "qf_samp_p"
 
     def e2e_step(i):
-        ctx.call("qf_samp_p", _ffi.ptr(hu_np), e2e_batch, 2, (rank * 1000 + i) * e2e_batch, _ffi.ptr(he_np))
+        ctx.call(e2e_fn, _ffi.ptr(hu_np), e2e_batch, 2, (rank * 1000 + i) * e2e_batch, _ffi.ptr(he_np))
 
     e2e_step(0)
     barrier()
@@ -331,19 +586,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = world * e2e_steps * e2e_batch / e2e_dt
-    assert np.array_equal(he_np[:4].astype(np.int64) @ a.T % q, hu_np[:4])
+    if kind != "ring":
+        assert np.array_equal(he_np[:4].astype(np.int64) @ a.T % q, hu_np[:4])
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (gemm_f64: fp64 tensor-pipe DMMA) -------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    # MEASURED_PEAKS.json has no fp64 entry: measure the cuBLAS DGEMM burst the same way the driver
-    # measured bf16 (torch.matmul 8192^3, best of 5) and use it as the denominator.
+    # ---- roofline of the dominant kernels -----------------------------------------------------------------------
+    import bench_rows as BR
+
+    peaks = BR.PEAKS
+    # fp64: MEASURED_PEAKS.json has no fp64 entry: measure the cuBLAS DGEMM burst the same way the driver measured
+    # bf16 (torch.matmul 8192^3, best of 6) and use it as the denominator.
     x = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
     y = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
     best = 1e9
@@ -356,10 +612,15 @@ def main():
         best = min(best, p0.elapsed_time(p1))
     dgemm_tf = 2 * 8192**3 / (best * 1e-3) / 1e12
     del x, y
+    i8 = measure_i8_peak(local)
     bf16 = peaks.get("bf16_tflops")
-    i8_peak = 2.0 * (bf16 or 1590.0)
-    i8_src = ("2 x the measured bf16 burst of MEASURED_PEAKS.json (%.1f TF/s); int8 is not in the file, nominal dense int8 "
-              "is 4.5 POP/s" % bf16) if bf16 else "2 x the fallback bf16 figure 1.59 PF/s of B200_PROFILING.md"
+    if i8:
+        # the contraction kernels run inside a long step: the sustained figure is the denominator
+        i8_peak = i8["sustained_tops"] or i8["burst_tops"]
+        i8_src = "measured in this run, sustained: " + i8["how"]
+    else:
+        i8_peak = 2.0 * (bf16 or 1590.0)
+        i8_src = "2 x the bf16 burst (probe failed)"
     f64_achieved = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else None
     f64_roof = {
         "kernel": "gemm_f64_kernel (mma.sync.m8n8k4.f64 DMMA): nearest-plane updates inside 1024-blocks, centre -> GSO map",
@@ -371,22 +632,21 @@ def main():
     if ims.value > 0:
         issued = iiss.value / (ims.value * 1e-3) / 1e12
         algo = iops.value / (ims.value * 1e-3) / 1e12
+        tr = BR.profile_traffic("gemm_i8_kernel") or {}
         # dominant kernel of the step.  `achieved` counts the ALGORITHMIC contraction 2*B*N*K of every launch
         # (the exact integer / fixed-point product the reference computes in big-number arithmetic); the tensor pipe
-        # executes that once per digit pair (`issued`), which is what is compared with the int8 peak in `frac`.
+        # executes that once per digit pair (`issued`).
         roofline = {
-            "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z (K = 1024 / 4096) and exact e = sol + S*z",
+            "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): fixed-point nearest-plane updates U*z and exact "
+                      "integer products (S*z, A*p, R*z)" if kind != "pert" else
+                      "gemm_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM): x2 = sqrt(Sigma_2) g (fixed point), v = u - A p, e = p + [R;I] z",
             "bound": "tensor", "achieved": algo, "peak": i8_peak, "unit": "TOP/s", "frac": algo / i8_peak,
             "achieved_issued": issued, "frac_issued": issued / i8_peak,
             "algorithmic_ops": "2*B*N*K per launch (B targets x N coordinates x K contraction length), summed over the "
                                "launches of the timed region; `issued` multiplies by the digit pairs the tensor pipe "
                                "actually executed (zero digit planes skipped), counted by the kernel",
-            "traffic": 8.62e9, "traffic_note": "dram read+write of the largest launch (fixed-point update N = 8192 rows, "
-                                              "K = 4096, 12.7 ms) from the ncu --set full capture "
-                                              "profiles/prof_i8_update4096_r1.ncu-rep; algorithmic 2.95 GB for that launch "
-                                              "(T read+write 2.48 + z digits 0.23 + U digits 0.23): the U digit planes are "
-                                              "re-read per target tile (L2 hit rate 88 %)",
-            "peak_source": i8_src, "digit_pairs_per_mac": issued / algo if algo else None,
+            "traffic": tr.get("dram_bytes"), "traffic_note": tr.get("note"),
+            "peak_source": i8_src, "i8_peak_probe": i8, "digit_pairs_per_mac": issued / algo if algo else None,
             "kernel_ms_per_step": ims.value / args.steps, "kernel_share_of_step": ims.value / ms, "launches": int(iln.value),
         }
     else:
@@ -396,32 +656,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            from oracle import oracle_c as OC
-
-            threads = OC.threads()
-            sample = threads  # one target per thread: ~ one pass over the 2.4 GB of basis + GSO each
-            sb, sg = td
-            if sg is None:  # the backend kept the GSO on the device: fetch a host copy for the CPU arm (untimed)
-                sg = psf.gso(sb)
-            t1 = time.perf_counter()
-            piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
-            us = np.ascontiguousarray(hu_np[:sample])
-            import ctypes as C
-
-            bt = np.ascontiguousarray(np.asarray(sb, dtype=np.float64).T)  # rows = basis vectors (untimed layout change)
-            gt = np.ascontiguousarray(np.asarray(sg, dtype=np.float64).T)
-            ec = np.empty((sample, gp.m), dtype=np.int32)
-            tc = time.perf_counter()
-            OC.lib().orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
-                                    C.c_void_p(ainv.ctypes.data), C.c_long(len(piv)), C.c_void_p(us.ctypes.data),
-                                    C.c_void_p(ec.ctypes.data), C.c_long(sample), C.c_long(n), C.c_long(gp.m), C.c_uint64(q),
-                                    C.c_double(s), C.c_uint64(1), C.c_int(threads))
-            dtc = time.perf_counter() - tc
-            assert np.array_equal(ec[:2].astype(np.int64) @ a.T % q, us[:2])
-            cpu = {"value": sample / dtc, "unit": "preimages/s", "cores": threads, "kind": "port",
-                   "sample": f"{sample} targets of the same workload, one per host thread ({dtc:.1f}s); reference "
-                             "loop structure in fp64 with the per-call Gaussian elimination hoisted out "
-                             f"(setup {tc - t1:.1f}s untimed)"}
+            cpu = cpu_baseline(kind, psf, gp, a, td, hu_np, n, q, s, r_par)
         except Exception as ex:  # the baseline is reported, never required
             cpu = {"value": None, "error": repr(ex)}
 
@@ -430,22 +665,100 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "targets_per_step_per_gpu": batch, "total_targets_timed": world * args.steps * batch,
-                   "s": s, "l2": "per-step working set (T, Z: batch x m fp64 = %.1f GB each) exceeds L2" % (batch * gp.m * 8 / 1e9),
+                   "note": "the configuration's target count is consumed in steps of targets_per_step_per_gpu (HBM workspace); "
+                           "throughput does not depend on the number of steps",
+                   "s": s, "r": r_par if kind == "pert" else None,
+                   "l2": "per-step working set (T, Z: batch x dim fp64 = %.1f GB each) exceeds L2" % (batch * dim * 8 / 1e9),
                    "sharding": "targets split across ranks, key replicated, no collective on the data path"},
         "e2e": {"value": e2e_value, "unit": "preimages/s", "h2d_bytes_per_step": e2e_batch * n * 8,
-                "d2h_bytes_per_step": e2e_batch * gp.m * 4, "steps": e2e_steps},
+                "d2h_bytes_per_step": e2e_batch * dim * (2 if e2e_i16 else 4), "steps": e2e_steps,
+                "targets_per_step_per_gpu": e2e_batch, "domain_dtype": "int16" if e2e_i16 else "int32", "entry": e2e_fn},
         "f_a": {"value": fa_value, "unit": "evals/s", "ms_per_step": fa_ms / fa_steps},
         "gpu_launches": int(launches),
         "checks": {"A_e_equals_u_all_targets_last_step": True, "check_domain_all": True,
-                   "mean_norm2_over_m_s2_2pi": norm_ratio},
+                   "mean_norm2_over_dim_s2_2pi": norm_ratio},
         "roofline": roofline,
         "roofline_f64": f64_roof,
+        "key_setup": trapgen_info,
+        "gather": gather_info,
         "cpu_baseline": cpu,
         "clocks": clock_info,
     }
+    # ---- the other configurations of BASELINE.json, device resident, each with its own roofline ----------------
+    if world == 1 and args.workload == "c2" and not args.no_extra:
+        del u, e, uo, fl, hu, he
+        psf.ctx.close()
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        torch.cuda.empty_cache()
+        rows = []
+        plan = [("compress", lambda: BR.row_compress(dev)), ("encode", lambda: BR.row_encode(dev, ds=(10,))),
+                ("ring", lambda: BR.row_ring(dev)),
+                ("pert_c4", lambda: [BR.row_pert(dev, *BR.c4_params(), 15104,
+                                                 "C4 PSFPerturbation n=512 q=2^32-5 k=32 r=9 (one GPU shard)", i8_peak=i8_peak)]),
+                ("pert_c1", lambda: [BR.row_pert(dev, 8, 64, 3.0, 25.0, 262144, "C1 README PSFPerturbation n=8 q=64 r=3 s=25",
+                                                 i8_peak=i8_peak)])]
+        for name, fn in plan:
+            try:
+                rows.extend(fn())
+            except Exception as ex:
+                rows.append({"row": name, "error": repr(ex)})
+            torch.cuda.empty_cache()
+        line["extra"] = {"rows": rows}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline(kind, psf, gp, a, td, hu_np, n, q, s, r_par):
+    """The oracle's C restatement of the reference loop on a bounded sample of the same workload (rank 0, N = 1)."""
+    import ctypes as C
+
+    from oracle import oracle_c as OC
+
+    threads = OC.threads()
+    if kind == "gpv":
+        sample = threads  # one target per thread: ~ one pass over the 2.4 GB of basis + GSO each
+        sb, sg = td
+        if sg is None:  # the backend kept the GSO on the device: fetch a host copy for the CPU arm (untimed)
+            sg = psf.gso(sb)
+        t1 = time.perf_counter()
+        piv, ainv = OC.unit_pivots(a[:, : 4 * n + 64], q)
+        us = np.ascontiguousarray(hu_np[:sample])
+        bt = np.ascontiguousarray(np.asarray(sb, dtype=np.float64).T)  # rows = basis vectors (untimed layout change)
+        gt = np.ascontiguousarray(np.asarray(sg, dtype=np.float64).T)
+        ec = np.empty((sample, gp.m), dtype=np.int32)
+        tc = time.perf_counter()
+        OC.lib().orc_samp_p_gpv(C.c_void_p(bt.ctypes.data), C.c_void_p(gt.ctypes.data), C.c_void_p(piv.ctypes.data),
+                                C.c_void_p(ainv.ctypes.data), C.c_long(len(piv)), C.c_void_p(us.ctypes.data),
+                                C.c_void_p(ec.ctypes.data), C.c_long(sample), C.c_long(n), C.c_long(gp.m), C.c_uint64(q),
+                                C.c_double(s), C.c_uint64(1), C.c_int(threads))
+        dtc = time.perf_counter() - tc
+        assert np.array_equal(ec[:2].astype(np.int64) @ a.T % q, us[:2])
+        return {"value": sample / dtc, "unit": "preimages/s", "cores": threads, "kind": "port",
+                "sample": f"{sample} targets of the same workload, one per host thread ({dtc:.1f}s); reference "
+                          "loop structure in fp64 with the per-call Gaussian elimination hoisted out "
+                          f"(setup {tc - t1:.1f}s untimed)"}
+    if kind == "pert":
+        rmat, l, (sb, sg) = td
+        if gp.m > 4096:
+            return {"value": None, "unit": "preimages/s", "cores": threads, "kind": "port",
+                    "sample": "not run in the default bench: the dense m x m sqrt(Sigma_2) and nk x nk gadget GSO the reference "
+                              "loop needs are 8.6 + 4.3 GB of host doubles at C4 (`bench.py --impl reference --workload c4` runs it)"}
+        if l is None:
+            l = psf.compute_sqrt_sigma_2(rmat)
+        from oracle import qfall_oracle as O
+
+        sbf = np.array(O.short_basis_gadget(O.GadgetParameters.init_default(n, q)), dtype=np.float64)
+        sample = threads * 256
+        us = np.ascontiguousarray(hu_np[:sample])
+        tc = time.perf_counter()
+        ec = OC.samp_p_pert(l, a, rmat, sbf, O.gso_f64(sbf), us, n, gp.k, gp.m_bar, 2, q, r_par, 1, threads)
+        dtc = time.perf_counter() - tc
+        assert np.array_equal(ec[:2].astype(np.int64) @ a.T % q, us[:2])
+        return {"value": sample / dtc, "unit": "preimages/s", "cores": threads, "kind": "port",
+                "sample": f"{sample} targets, reference loop structure in fp64 (mp_perturbation.rs:304-336), {dtc:.2f}s"}
+    return {"value": None, "unit": "preimages/s", "cores": threads, "kind": "port",
+            "sample": "ring: `bench.py --impl reference --workload c3`"}
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ from bench import WORKLOADS, gpv_s  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 15616
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-n, q, _ = WORKLOADS[wl]
+n, q = WORKLOADS[wl]["n"], WORKLOADS[wl]["q"]
 gp = T.GadgetParameters.init_default(n, q)
 psf = T.PSFGPV(gp, gpv_s(gp))
 a, td = psf.trap_gen(seed=2)

@@ -305,7 +305,7 @@ qf_status upload_limbs(qf_ctx* ctx, const int64_t* h, long rows, long cols, long
 }
 
 // tcgen05 int8 contraction with optional event timing
-cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
+cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a, bool count_ops = true) {
     qf_ctx::ProfRec rec{};
     if (ctx->prof) {
         for (cudaEvent_t* e : {&rec.a, &rec.b}) {
@@ -313,7 +313,8 @@ cudaError_t ctx_gemm_i8(qf_ctx* ctx, const I8GemmArgs& a) {
             else if (cudaEventCreate(e) != cudaSuccess) return cudaErrorUnknown;
         }
         rec.kind = 1;
-        rec.flops = 2.0 * a.B * (double)a.N * a.K;
+        // of the conditional launches of one contraction (gemm_i8_gated) exactly one runs: its work is counted once
+        rec.flops = count_ops ? 2.0 * a.B * (double)a.N * a.K : 0.0;
         rec.issued = rec.flops * a.LX * a.LW;
         cudaEventRecord(rec.a, ctx->stream);
     }
@@ -657,7 +658,7 @@ qf_status gemm_i8_gated(qf_ctx* ctx, I8GemmArgs g, const int* gate) {
         v.gate = gate;
         v.gate_lo = lx == 3 ? 0 : lx - 1;
         v.gate_hi = lx == Lmax ? 1 << 20 : lx - 1;
-        LAUNCH(ctx_gemm_i8(ctx, v));
+        LAUNCH(ctx_gemm_i8(ctx, v, lx == Lmax));
     }
     return QF_OK;
 }
@@ -676,7 +677,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
     const double* U = ctx->dU.as<double>();
     if (level == 0) {
         LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
-                                 ctx->w[9].as<float4>() + (lo - prop0), NP_PROP_LD, Bc, (int)lo, (int)(hi - lo), (int)D,
+                                 ctx->w[9].as<float4>() + (lo - prop0) * ctx->chunk, ctx->chunk, Bc, (int)lo, (int)(hi - lo), (int)D,
                                  seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
         return QF_OK;
     }
@@ -690,7 +691,8 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
         if (level == 3) {
             // the rejection-sampling proposals of this 1024-block for all targets, at full occupancy
             CK(ctx->w[9].ensure((size_t)ctx->chunk * NP_PROP_LD * sizeof(float4)));
-            LAUNCH(qf_launch_np_propose(ctx->w[9].as<float4>(), NP_PROP_LD, Bc, (int)sub_lo, (int)(sub_hi - sub_lo), (int)D,
+            // (coordinate-major: row i holds the proposals of all targets of the chunk for coordinate sub_lo + i)
+            LAUNCH(qf_launch_np_propose(ctx->w[9].as<float4>(), ctx->chunk, Bc, (int)sub_lo, (int)(sub_hi - sub_lo), (int)D,
                                         seed, first, ctx->stream));
             prop0 = sub_lo;
         }

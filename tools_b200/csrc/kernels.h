@@ -87,11 +87,11 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
 // for i = j0+nb-1 .. j0:  c' = T[b][i] - sum_{j>i in block} U[i][j] z_j ;  z_i <- D_{Z, s/||b~_i||, c'}
 // writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).
 // *flag is set when |z| >= zlimit (exact-integer range check).
-// prop: this block's pre-generated proposals (np_propose), prop[b * ldprop + (i - j0)]
+// prop: this block's pre-generated proposals (np_propose), coordinate-major: prop[(i - j0) * ldprop + b]
 cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
                               uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream);
-// two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[b * ldo + (i - j_lo)]
+// two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[(i - j_lo) * ldo + b]
 cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
                                  uint64_t first_target, cudaStream_t stream);
 

@@ -78,39 +78,43 @@ __device__ __noinline__ double np_sample_slow(DGaussParams dgp, double cp, uint6
 // First Philox block of every (target, coordinate) stream of the nearest-plane recursion turned into two
 // proposals (two normals, logs of two uniforms).  The transcendental work does not depend on the centres, so it
 // runs here at full occupancy instead of inside the sequential per-target chain of np_diag.
+// Layout: coordinate-major, out[(i - j_lo) * ldo + b] (ldo = target stride): np_diag reads, per step, the proposals of
+// consecutive targets for ONE coordinate -- contiguous.
 __global__ void __launch_bounds__(256)
 np_propose_kernel(float4* __restrict__ out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
                   uint64_t first_target) {
     const long total = (long)B * width;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long b = idx / width;
-        const int i = (int)(idx - b * width);
+        const int i = (int)(idx / B);
+        const long b = idx - (long)i * B;
         Philox ph;
         ph.init(seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j_lo + i), QF_STREAM_NP);
         float n0, n1;
         ph.normal2(n0, n1);
         const float u0 = ph.uniform24(), u1 = ph.uniform24();
-        out[b * ldo + i] = make_float4(n0, n1, __logf(u0), __logf(u1));
+        out[(long)i * ldo + b] = make_float4(n0, n1, __logf(u0), __logf(u1));
     }
 }
 
-constexpr int NP_TARGETS = 32;   // targets per CTA
-constexpr int NP_TPB = 128;      // 4 lanes per target
+constexpr int NP_TPL = 4;                 // targets per lane
+constexpr int NP_TARGETS = 32 * NP_TPL;   // targets per CTA: 4 warps x 8 quads x 4 targets
+constexpr int NP_TPB = 128;               // 4 lanes (a quad) per group of NP_TPL targets
 constexpr int NP_NB_MAX = 64;
-constexpr int NP_TS = NP_NB_MAX + 1;   // centre tile is target-major: ts[t * NP_TS + i]
+constexpr int NP_TS = NP_NB_MAX + 1;      // centre tile is target-major: ts[t * NP_TS + i]
 
-// One nb-wide diagonal block.  Three phases per CTA of 32 targets:
-//  0. stage the mu-block (transposed) and the 32 x nb tile of centres through shared memory (coalesced);
+// One nb-wide diagonal block.  Three phases per CTA of 128 targets (one CTA per SM: 148 CTAs = one chunk of 18944):
+//  0. stage the mu-block (transposed) and the 128 x nb tile of centres through shared memory (coalesced);
 //  1. the proposals of every (target, coordinate) -- the first Philox block of that coordinate's stream turned into
-//     two normals and the logs of two uniforms by np_propose_kernel at full occupancy -- are NOT staged through
-//     shared memory: each quad prefetches the four proposals of the next coordinate group into registers one
-//     group ahead, which keeps the CTA at ~50 KB of shared memory and four CTAs per SM;
-//  2. the recursion i = nb-1 .. 0 with 4 lanes per target: accept / reject on the pre-generated proposals
-//     (a handful of flops), then a right-looking update c'_j -= mu_ji z_i of the remaining centres, the
-//     j's strided over the 4 lanes (independent FMAs instead of one dependent dot product).
+//     two normals and the logs of two uniforms by np_propose_kernel at full occupancy -- are read from global memory
+//     one coordinate ahead (coordinate-major layout: the 4 targets of a lane are one 64-byte segment);
+//  2. the recursion i = nb-1 .. 0.  A quad of lanes owns NP_TPL = 4 targets; lane qd of the quad keeps the centres of
+//     coordinates 4k+qd of all four targets in registers.  Per step: one quad shuffle per target, the accept / reject
+//     arithmetic (a handful of flops per target), then the right-looking update c'_j -= mu_ji z_i of the remaining
+//     centres: every mu value read from shared memory is used for the four targets of the lane (the kernel is bound
+//     by exactly those shared-memory reads: one target per lane needs 4x the bandwidth for the same flops).
 // Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
 // one-thread-per-target formulation.
-__global__ void __launch_bounds__(NP_TPB, 4)
+__global__ void __launch_bounds__(NP_TPB, 1)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
                int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
@@ -133,74 +137,93 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
             for (int c = lane; c < nbe; c += 32) ts[r * NP_TS + c] = T[b * ldt + j0 + c];
     }
     __syncthreads();
-    // phase 2 (first 4 warps; the others wait at the barrier below).  Lane qd of a target's quad keeps the
-    // centres of coordinates 4k+qd in registers; the recursion is fully unrolled so that every register index
-    // is static: per step one quad shuffle, the accept/reject arithmetic, and 16 predicated register FMAs.
-    const int t = (tid >> 2) & (NP_TARGETS - 1), qd = tid & 3;
-    const long b = b0 + t;
-    const bool live = b < B;
-    if (tid < 4 * NP_TARGETS) {
+    // phase 2: the recursion, fully register resident; the loop over coordinate groups stays rolled (the register file
+    // is rotated by one group after each group, so all register indices are static)
+    {
+        const int tl = (tid >> 2) * NP_TPL, qd = tid & 3;   // first local target of this lane's quad, lane within the quad
+        const long bq = b0 + tl;
         constexpr int NG = NP_NB_MAX / 4;  // 16 coordinate groups; group j = coordinates 4j .. 4j+3
-        double c[NG];
+        double c[NP_TPL][NG];
 #pragma unroll
-        for (int k = 0; k < NG; ++k) c[k] = (4 * k + qd < nbe) ? ts[t * NP_TS + 4 * k + qd] : 0.0;
-        // the group being sampled always sits in c[NG-1]; after each group the register file is rotated by one,
-        // so all register indices are static while the loop over groups stays rolled (small code footprint)
-        // proposals of this target (pre-generated by np_propose_kernel; prop points at column j0), one group ahead
-        const float4* prow = prop + (live ? b : 0) * ldprop;
-        float4 pcur[4], pnxt[4];
+        for (int k = 0; k < NP_TPL; ++k)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int ii = 4 * (NG - 1) + o;
-            pcur[o] = (ii < nbe) ? prow[ii] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < NG; ++j) c[k][j] = (4 * j + qd < nbe) ? ts[(tl + k) * NP_TS + 4 * j + qd] : 0.0;
+        // proposals (prop points at coordinate j0): row ii holds the proposals of all targets for coordinate j0 + ii
+        const float4* pq = prop + bq;
+        float4 pcur[NP_TPL], pnxt[NP_TPL];
+        {
+            const int ii = 4 * NG - 1;
+#pragma unroll
+            for (int k = 0; k < NP_TPL; ++k) pcur[k] = (ii < nbe) ? pq[(long)ii * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int kidx = 0; kidx < NG; ++kidx) {
             const int g = NG - 1 - kidx;
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int ii = 4 * (g - 1) + o;
-                pnxt[o] = (g > 0 && ii < nbe) ? prow[ii] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
             for (int owner = 3; owner >= 0; --owner) {
                 const int ii = 4 * g + owner;
-                if (ii >= nbe) continue;  // uniform
-                const double cp = __shfl_sync(0xffffffffu, c[NG - 1], (lane & ~3) | owner);
-                const DGaussParams dgp = dgs[ii];
-                const float4 pr = pcur[owner];
-                const double c_int = rint(cp);
-                const float c_frac = (float)(cp - c_int);
-                double z = 0.0;
-                bool done = false;
-                {
-                    float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
-                    float d = x - c_frac;
-                    float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
-                    if (fabsf(d) <= dgp.tail && pr.z < e) { z = c_int + (double)x; done = true; }
-                }
-                if (!done) {
-                    float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
-                    float d = x - c_frac;
-                    float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
-                    if (fabsf(d) <= dgp.tail && pr.w < e) { z = c_int + (double)x; done = true; }
-                }
-                if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
-                    z = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)(j0 + ii), flag);
-                if (live && qd == 0 && !(fabs(z) < zlimit) && flag) atomicOr(flag, 2);
-                const double* ucol = ust + ii * us_ld + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
-                if (qd == owner) c[NG - 1] = z;
-                else if (qd < owner) c[NG - 1] = fma(-ucol[4 * g], z, c[NG - 1]);
+                {   // proposals of the next coordinate, in flight during this step
+                    const int in = ii - 1;
 #pragma unroll
-                for (int kk = 0; kk < NG - 1; ++kk) {
-                    const int grp = kk - kidx;  // group held by c[kk]
-                    if (grp >= 0) c[kk] = fma(-ucol[4 * grp], z, c[kk]);
+                    for (int k = 0; k < NP_TPL; ++k)
+                        pnxt[k] = (in >= 0 && in < nbe) ? pq[(long)in * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (ii < nbe) {  // uniform
+                    const DGaussParams dgp = dgs[ii];
+                    double z[NP_TPL];
+#pragma unroll
+                    for (int k = 0; k < NP_TPL; ++k) {
+                        const double cp = __shfl_sync(0xffffffffu, c[k][NG - 1], (lane & ~3) | owner);
+                        const float4 pr = pcur[k];
+                        const double c_int = rint(cp);
+                        const float c_frac = (float)(cp - c_int);
+                        double zz = 0.0;
+                        bool done = false;
+                        {
+                            float x = rintf(fmaf(dgp.sigma_p, pr.x, c_frac));
+                            float d = x - c_frac;
+                            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.x, pr.x, -dgp.emax));
+                            if (fabsf(d) <= dgp.tail && pr.z < e) { zz = c_int + (double)x; done = true; }
+                        }
+                        if (!done) {
+                            float x = rintf(fmaf(dgp.sigma_p, pr.y, c_frac));
+                            float d = x - c_frac;
+                            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * pr.y, pr.y, -dgp.emax));
+                            if (fabsf(d) <= dgp.tail && pr.w < e) { zz = c_int + (double)x; done = true; }
+                        }
+                        const bool live = bq + k < B;
+                        if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
+                            zz = np_sample_slow(dgp, cp, seed, (first_target + (uint64_t)(bq + k)) * (uint64_t)dim + (uint64_t)(j0 + ii), flag);
+                        if (live && qd == 0 && !(fabs(zz) < zlimit) && flag) atomicOr(flag, 2);
+                        z[k] = zz;
+                    }
+                    const double* ucol = ust + ii * us_ld + qd;  // ucol[4 j] = U[j0 + 4 j + qd][j0 + ii]
+                    {
+                        const double u = ucol[4 * g];
+#pragma unroll
+                        for (int k = 0; k < NP_TPL; ++k) {
+                            if (qd == owner) c[k][NG - 1] = z[k];
+                            else if (qd < owner) c[k][NG - 1] = fma(-u, z[k], c[k][NG - 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < NG - 1; ++kk) {
+                        const int grp = kk - kidx;  // group held by c[.][kk]
+                        if (grp >= 0) {
+                            const double u = ucol[4 * grp];
+#pragma unroll
+                            for (int k = 0; k < NP_TPL; ++k) c[k][kk] = fma(-u, z[k], c[k][kk]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NP_TPL; ++k) pcur[k] = pnxt[k];
             }
-            if (4 * g + qd < nbe) ts[t * NP_TS + 4 * g + qd] = c[NG - 1];
 #pragma unroll
-            for (int kk = NG - 1; kk > 0; --kk) c[kk] = c[kk - 1];
+            for (int k = 0; k < NP_TPL; ++k) {
+                if (4 * g + qd < nbe) ts[(tl + k) * NP_TS + 4 * g + qd] = c[k][NG - 1];
 #pragma unroll
-            for (int o = 0; o < 4; ++o) pcur[o] = pnxt[o];
+                for (int kk = NG - 1; kk > 0; --kk) c[k][kk] = c[k][kk - 1];
+            }
         }
     }
     __syncthreads();

@@ -59,6 +59,7 @@ class _PSFBase:
 
     def _make_ctx(self, n, k, m_bar, base, q, s, r, bound, device):
         self.ctx = _ffi.Context(self.kind, n, k, m_bar, base, q, s, r, bound, device)
+        self.device = device
         self.ctx_dim = n * (k + 2) if self.kind == _ffi.QF_PSF_GPV_RING else m_bar + n * k
         self._a_id = None
         self._td_id = None
@@ -369,7 +370,7 @@ class PSFGPVRing(_PSFBase):
         gp = self.gp
         seed = _seed(seed)
         # r, e: 2k polynomials of n Gaussian coefficients from the device sampler
-        tmp = _ffi.Context(_ffi.QF_PSF_GPV, 1, 1, 2 * gp.k * gp.n - 1, 2, 2, self.s_td, 1.0, 1, 0)
+        tmp = _ffi.Context(_ffi.QF_PSF_GPV, 1, 1, 2 * gp.k * gp.n - 1, 2, 2, self.s_td, 1.0, 1, self.device)
         try:
             re = np.empty((1, 2 * gp.k * gp.n), dtype=np.int32)
             tmp.call("qf_samp_d", 1, seed ^ 0x52494E47, 0, _ffi.ptr(re))

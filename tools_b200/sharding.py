@@ -11,3 +11,45 @@ def shard(total: int, rank: int, world: int):
     base, rem = divmod(total, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_domain_i16(torch, dist, lib, ffi, e, u, rank, world, dev, stream, max_bytes=64 << 30, dst=0):
+    """Final gather of the per-rank Domain results over NVLink: each rank narrows its int32 shard to int16
+    on the device (qf_narrow_i32_i16_dev -- |e_i| <= 6 s r fits for the reference's parameter sets; overflow is detected and
+    reported) and ONE NCCL gather brings the shards to `dst`; the targets travel the same way (as int64) so that `dst` can
+    verify the gathered preimages.  Device-timed (max over ranks is the caller's business: the gather is a collective, its
+    duration on `dst` is the duration).  Returns a dict {ms, bytes, GBps, dtype, ...}; on `dst` also "gathered": (e_all int16
+    [world * B, ...], u_all).  Skipped (returns {"skipped": why}) when the gathered tensor would not fit max_bytes on `dst`
+    -- C4's 4 Mi x 32849 preimages are 276 GB: those results stay sharded."""
+    b = e.shape[0]
+    count = e.numel()
+    total_bytes = world * count * 2
+    if total_bytes > max_bytes:
+        return {"skipped": f"gathered int16 results would be {total_bytes / 1e9:.1f} GB: kept sharded"}
+    with torch.cuda.stream(stream):
+        e16 = torch.empty(e.shape, dtype=torch.int16, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        out_e = torch.empty((world * b,) + tuple(e.shape[1:]), dtype=torch.int16, device=dev) if rank == dst else None
+        out_u = torch.empty((world * b,) + tuple(u.shape[1:]), dtype=u.dtype, device=dev) if rank == dst else None
+        stream.synchronize()
+        dist.barrier()
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ev0.record(stream)
+        st = lib.qf_narrow_i32_i16_dev(ffi.ptr(e.data_ptr()), ffi.ptr(e16.data_ptr()), count, ffi.ptr(ovf.data_ptr()),
+                                       ffi.ptr(stream.cuda_stream))
+        assert st == 0
+        ev1.record(stream)
+        dist.gather(e16, list(out_e.split(b)) if rank == dst else None, dst=dst)
+        ev2.record(stream)
+        dist.gather(u, list(out_u.split(b)) if rank == dst else None, dst=dst)
+        stream.synchronize()
+    assert int(ovf.item()) == 0, "a preimage entry does not fit int16: gather the int32 form instead"
+    ms_narrow, ms_gather = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
+    recv = (world - 1) * count * 2
+    info = {"collective": "NCCL gather to rank %d (NVLink / NVSwitch)" % dst, "dtype": "int16", "ranks": world,
+            "bytes_received_by_dst": recv, "narrow_ms": ms_narrow, "gather_ms": ms_gather,
+            "GBps_into_dst": recv / ms_gather / 1e6 if ms_gather > 0 else None,
+            "per_target_bytes": (count // b) * 2}
+    if rank == dst:
+        info["gathered"] = (out_e, out_u)
+    return info
