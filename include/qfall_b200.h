@@ -202,6 +202,23 @@ qf_status qf_compress_encode_u16(const uint16_t* in, uint8_t* out, size_t npoly,
 qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npoly, uint32_t q, uint32_t d, int decompress,
                                    int device_ptrs, void* cuda_stream);
 
+/* ---- message encodings (src/utils/common_encodings.rs), batched ------------------------------------
+ * encode_value_in_polynomialringzq (:49-92): digit d of the value w.r.t. `base` -> coefficient d * floor(q / base);
+ * decode_value_from_polynomialringzq (:125-153): coefficient c (any representative) -> digit
+ * floor((c * base + floor(q / (2 base))) / q) mod base.  A batch is a flat stream of `count` digits, one byte each
+ * (2 <= base <= 256); coefficients are coeff_bytes wide: 2 (u16, q < 2^16) or 8 (FLINT words, q < 2^62).  The big-integer
+ * <-> digit-string conversion of the reference's `value: Z` stays with the caller (one value = up to n digits, padded
+ * with zeros).  base < 2 is QF_ERR_INVALID (the reference returns MathError::InvalidIntegerInput).  device_ptrs != 0:
+ * device pointers, asynchronous on cuda_stream. */
+qf_status qf_encode_digits(const uint8_t* digits, void* coeffs, size_t count, uint64_t q, uint32_t base, int coeff_bytes,
+                           int device_ptrs, void* cuda_stream);
+qf_status qf_decode_digits(const void* coeffs, uint8_t* digits, size_t count, uint64_t q, uint32_t base, int coeff_bytes,
+                           int device_ptrs, void* cuda_stream);
+/* base 2 with bit-packed messages (bit j of byte i = coefficient 8 i + j; a 32-byte message <-> 256 u16 coefficients, the
+ * mu -> floor(q/2) mu map of the lib.rs example :28-36): nbytes message bytes <-> 8 nbytes coefficients, q < 2^16. */
+qf_status qf_encode_bits_u16(const uint8_t* msg, uint16_t* coeffs, size_t nbytes, uint32_t q, int device_ptrs, void* cuda_stream);
+qf_status qf_decode_bits_u16(const uint16_t* coeffs, uint8_t* msg, size_t nbytes, uint32_t q, int device_ptrs, void* cuda_stream);
+
 /* ---- Z::sample_discrete_gauss for a batch of (centre) values (qfall-math SampleZ as used at
  * gpv.rs:115 and inside sample_d_precomputed_gso): out[i] <- D_{Z, s, centers[i]}. Host pointers, any count.
  * Value i draws from its own Philox stream (seed, i) under a stream id that no PSF method uses, so equal seeds
@@ -218,9 +235,11 @@ qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int
 /* ---- measured ceiling of the int8 tensor pipe (roofline denominator of the limb contractions; SURVEY 8d: "measure a plain
  * int8 tcgen05 GEMM probe once and use it"): a one-digit-pair B x N x K contraction on random bytes (128 x 256 tiles, K a
  * multiple of 128, <= 65536), `iters` launches timed one by one -> best_tops (burst), then back to back for sustain_ms ->
- * sustained_tops.  TOP/s = 2 B N K / time.  Allocates its own buffers on `device`. */
+ * sustained_tops.  TOP/s = 2 B N K / time.  pipe_tops (optional): the tensor pipe on its own -- every SM repeats the MMAs of
+ * one shared-memory-resident 128 x 256 x 128 block (no operand traffic), i.e. the rate at 100 % pipe activity; the GEMM probe
+ * sits below it because a cta_group::1 tiling is bound by the L2 -> shared-memory operand feed.  Allocates its own buffers. */
 qf_status qf_probe_i8_peak(int device, int64_t B, int64_t N, int64_t K, int iters, double sustain_ms, double* best_tops,
-                           double* sustained_tops);
+                           double* sustained_tops, double* pipe_tops);
 
 /* ---- synthetic inputs for benchmarks (Philox, on device) -------------------------------- */
 qf_status qf_fill_uniform_modq_dev(int64_t* out, size_t count, uint64_t q, uint64_t seed, void* cuda_stream);

@@ -698,6 +698,46 @@ def compute_sqrt_sigma_2(r_mat, s: float, r: float, base: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# Message encodings (src/utils/common_encodings.rs)
+# --------------------------------------------------------------------------
+
+
+def encode_value_in_polynomialringzq(value: int, base: int, n: int, q: int):
+    """common_encodings.rs:49-92: digits of `value` w.r.t. `base` spread by floor(q / base) over the coefficients of a
+    polynomial in Z_q[X]/(X^n + 1).  ValueError where the reference returns MathError::InvalidIntegerInput
+    (negative value :58-62; more digits than coefficients :64-70; base < 2 through log_ceil :64).  Returns n coefficients."""
+    if value < 0:
+        raise ValueError("The given value needs to be non-negative.")
+    if base < 2:
+        raise ValueError("base < 2")
+    min_req_degree = ceil_log(value + 1, base)  # (&value + Z::ONE).log_ceil(&base)
+    if min_req_degree > n:
+        raise ValueError("not enough coefficients")
+    base_repr = []
+    while value > 0:  # :73-78
+        base_repr.append(value % base)
+        value //= base
+    q_div_base = q // base  # :87
+    coeffs = [0] * n
+    for i, digit in enumerate(base_repr):
+        coeffs[i] = (digit * q_div_base) % q
+    return coeffs
+
+
+def decode_value_from_polynomialringzq(coeffs, base: int, q: int) -> int:
+    """common_encodings.rs:125-153: mu_i = floor((c_i * base + floor(q / (2 base))) / q) mod base on the least
+    non-negative representatives, value = sum mu_i base^i (Horner from the top coefficient, :143-150)."""
+    if base <= 1:
+        raise ValueError("base < 2")
+    q_div_2base = q // (2 * base)
+    out = 0
+    for c in reversed([int(x) % q for x in coeffs]):
+        res = ((c * base + q_div_2base) // q) % base
+        out = out * base + res
+    return out
+
+
+# --------------------------------------------------------------------------
 # Discrete Gaussians (qfall-math behaviour restated; CONTRIBUTING.md:35-45)
 # --------------------------------------------------------------------------
 

@@ -78,9 +78,13 @@ extern "C" {
     pub fn qf_compress_encode_u16(input: *const u16, out: *mut u8, npoly: usize, q: u32, d: u32, compress: i32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
     pub fn qf_decode_decompress_u16(input: *const u8, out: *mut u16, npoly: usize, q: u32, d: u32, decompress: i32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
 
+    pub fn qf_encode_digits(digits: *const u8, coeffs: *mut c_void, count: usize, q: u64, base: u32, coeff_bytes: i32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
+    pub fn qf_decode_digits(coeffs: *const c_void, digits: *mut u8, count: usize, q: u64, base: u32, coeff_bytes: i32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
+    pub fn qf_encode_bits_u16(msg: *const u8, coeffs: *mut u16, nbytes: usize, q: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
+    pub fn qf_decode_bits_u16(coeffs: *const u16, msg: *mut u8, nbytes: usize, q: u32, device_ptrs: i32, cuda_stream: *mut c_void) -> i32;
     pub fn qf_sample_z(centers: *const f64, count: usize, s: f64, seed: u64, out: *mut i64) -> i32;
     pub fn qf_debug_gemm_i8(x: *const i64, w: *const i64, w_signed: i32, lx: i32, lw: i32, b: i64, n: i64, k: i64, q: u64, out: *mut i64) -> i32;
-    pub fn qf_probe_i8_peak(device: i32, b: i64, n: i64, k: i64, iters: i32, sustain_ms: f64, best_tops: *mut f64, sustained_tops: *mut f64) -> i32;
+    pub fn qf_probe_i8_peak(device: i32, b: i64, n: i64, k: i64, iters: i32, sustain_ms: f64, best_tops: *mut f64, sustained_tops: *mut f64, pipe_tops: *mut f64) -> i32;
     pub fn qf_fill_uniform_modq_dev(out: *mut i64, count: usize, q: u64, seed: u64, cuda_stream: *mut c_void) -> i32;
     pub fn qf_version() -> *const c_char;
 }

@@ -3,8 +3,11 @@
 //! * [`PSFGPVB200`] implements `qfall_tools::primitive::psf::PSF` (src/primitive/psf.rs:39-81) with the associated types
 //!   of `PSFGPV` (gpv.rs:59-63), one target per call exactly like the reference, plus [`PSFBatch`] -- the extension the
 //!   reference lacks because its methods reject multi-column inputs (gpv.rs:221, pinned by gpv.rs:287-298).
-//! * [`compress_words`] / [`decompress_words`] are what `LossyCompressionFIPS203::lossy_compress / lossy_decompress`
-//!   (lossy_compression_fips203.rs:89-114, 143-172) call per coefficient, for a whole coefficient vector at once.
+//! * [`PSFPerturbationB200`] (perturbation.rs) and [`PSFGPVRingB200`] (ring.rs) do the same for `PSFPerturbation`
+//!   (mp_perturbation.rs:193-197) and `PSFGPVRing` (gpv_ring.rs:69-73).
+//! * [`PolynomialRingZqB200`] / [`MatPolynomialRingZqB200`] (compression.rs) implement `LossyCompressionFIPS203`
+//!   (lossy_compression_fips203.rs:20-59) over [`compress_words`] / [`decompress_words`], which run `Compress_d` /
+//!   `Decompress_d` (:101-111, :159-169) for a whole coefficient vector at once.
 //!
 //! Values cross the boundary as fixed-width words: Range / key entries are residues in [0, q), q < 2^62 (`i64`), Domain
 //! entries are `i32`.  Every C entry point returns a status; a non-zero status is turned into the panic (or the
@@ -12,9 +15,13 @@
 //!
 //! This crate is shipped as SOURCE: the image the backend is built in has no Rust toolchain, so it has not been
 //! compiled there.  The `extern "C"` block (ffi.rs) is checked mechanically against include/qfall_b200.h.
+pub mod compression;
 pub mod ffi;
 pub mod perturbation;
+pub mod ring;
+pub use compression::{MatPolynomialRingZqB200, PolynomialRingZqB200};
 pub use perturbation::PSFPerturbationB200;
+pub use ring::PSFGPVRingB200;
 
 use ffi::*;
 use qfall_math::{
@@ -150,7 +157,9 @@ impl PSFGPVB200 {
             q: u64::try_from(&Z::from(&gp.q)).map_err(|_| "modulus must be below 2^62".to_string())?,
             s: f64::from(&inner.s),
             r: 1.0,
-            norm_bound: 0,
+            // gpv.rs:223: ||sigma||^2 <= s^2 * m, compared exactly (floor of the exact rational; 0 would make the
+            // backend derive it from the f64-rounded s)
+            norm_bound: ring::floor_u64(&(&inner.s * &inner.s * Q::from(i64::try_from(&(&gp.m_bar + &gp.n * &gp.k)).unwrap()))),
         };
         Ok(PSFGPVB200 { inner, ctx: Context::new(&params, device)?, installed: RefCell::new(None), seed: RefCell::new(seed) })
     }
@@ -194,6 +203,7 @@ impl PSF for PSFGPVB200 {
         let m_bar = i64::try_from(&self.inner.gp.m_bar).unwrap() as usize;
         let (mut a, mut r) = (vec![0i64; n * m], vec![0i8; m_bar * (m - m_bar)]);
         self.ctx.check(unsafe { qf_trap_gen(self.ctx.raw, self.next_seed(), a.as_mut_ptr(), r.as_mut_ptr()) }, "qf_trap_gen");
+        *self.installed.borrow_mut() = None; // qf_trap_gen installed a new key: whatever trapdoor was cached is gone
         let mut s = vec![0i64; m * m];
         self.ctx.check(unsafe { qf_gen_short_basis(self.ctx.raw, r.as_ptr(), s.as_mut_ptr()) }, "qf_gen_short_basis");
         let mut gso = vec![0f64; m * m];

@@ -16,7 +16,10 @@ pub struct PSFPerturbationB200 {
     pub inner: PSFPerturbation,
     ctx: Context,
     installed_a: RefCell<Option<Vec<i64>>>,
-    installed_r: RefCell<Option<Vec<i64>>>,
+    /// the trapdoor on the device: (R words, bit patterns of sqrt(Sigma_2), gadget block S_k, bit patterns of its GSO) --
+    /// every component takes part in the comparison: the same R with another covariance (compute_sqrt_sigma_2 with a
+    /// custom Sigma, mp_perturbation.rs:94-104) or another gadget basis is a different trapdoor
+    installed_r: RefCell<Option<(Vec<i64>, Vec<u64>, Vec<i64>, Vec<u64>)>>,
     seed: RefCell<u64>,
 }
 
@@ -32,7 +35,10 @@ impl PSFPerturbationB200 {
             q: u64::try_from(&Z::from(&gp.q)).map_err(|_| "modulus must be below 2^62".to_string())?,
             s: f64::from(&inner.s),
             r: f64::from(&inner.r),
-            norm_bound: 0,
+            // mp_perturbation.rs:401: ||sigma||^2 <= s^2 r^2 m, compared exactly: floor of the exact rational
+            norm_bound: crate::ring::floor_u64(
+                &(&inner.s * &inner.s * &inner.r * &inner.r * Q::from(i64::try_from(&(&gp.m_bar + &gp.n * &gp.k)).unwrap())),
+            ),
         };
         Ok(PSFPerturbationB200 {
             inner,
@@ -72,9 +78,6 @@ impl PSFPerturbationB200 {
     /// (what `short_basis_gadget` returns, gadget_classical.rs:273-286): only its first k x k block crosses the boundary.
     fn install_td(&self, td: &(MatZ, MatQ, (MatZ, MatQ))) {
         let rw = matz_to_words(&td.0);
-        if self.installed_r.borrow().as_ref() == Some(&rw) {
-            return;
-        }
         let r8: Vec<i8> = rw.iter().map(|v| i8::try_from(*v).expect("R entries are small")).collect();
         let (m, k) = (self.m(), self.k());
         let mut sqrt_sigma_2 = Vec::with_capacity(m * m);
@@ -93,11 +96,20 @@ impl PSFPerturbationB200 {
                 s_block_gso.push(f64::from(&x));
             }
         }
+        let key = (
+            rw,
+            sqrt_sigma_2.iter().map(|x| x.to_bits()).collect::<Vec<u64>>(),
+            s_block.clone(),
+            s_block_gso.iter().map(|x| x.to_bits()).collect::<Vec<u64>>(),
+        );
+        if self.installed_r.borrow().as_ref() == Some(&key) {
+            return;
+        }
         let st = unsafe {
             qf_set_trapdoor_perturbation(self.ctx.raw, r8.as_ptr(), sqrt_sigma_2.as_ptr(), s_block.as_ptr(), s_block_gso.as_ptr())
         };
         self.ctx.check(st, "qf_set_trapdoor_perturbation");
-        *self.installed_r.borrow_mut() = Some(rw);
+        *self.installed_r.borrow_mut() = Some(key);
     }
 }
 
@@ -115,6 +127,9 @@ impl PSF for PSFPerturbationB200 {
         let nk = m - m_bar;
         let (mut a, mut r) = (vec![0i64; n * m], vec![0i8; m_bar * nk]);
         self.ctx.check(unsafe { qf_trap_gen(self.ctx.raw, self.next_seed(), a.as_mut_ptr(), r.as_mut_ptr()) }, "qf_trap_gen");
+        // qf_trap_gen installed a new key (and thereby dropped the device's trapdoor): forget the cached one
+        *self.installed_a.borrow_mut() = None;
+        *self.installed_r.borrow_mut() = None;
         let mut l = vec![0f64; m * m];
         let st = unsafe { qf_compute_sqrt_sigma_2(self.ctx.raw, r.as_ptr(), std::ptr::null(), l.as_mut_ptr()) };
         self.ctx.check(st, "qf_compute_sqrt_sigma_2"); // QF_ERR_INVALID = Sigma_2 not positive definite (the reference panics)

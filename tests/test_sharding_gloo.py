@@ -48,6 +48,47 @@ def _worker(rank, world, port, total, out_path):
     del bufs
 
 
+def _gather_worker(rank, world, port, total, dim, out_path):
+    """The product's own collective (tools_b200.sharding.gather_shards: the call bench.py makes over NCCL) on gloo."""
+    from tools_b200.sharding import gather_shards
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard(total, rank, world)
+    idx = torch.arange(lo, hi, dtype=torch.int64)
+    # per-target int16 "preimages" and int64 targets as pure functions of the GLOBAL target index -- what keying the
+    # samplers by (seed, first_index + row) gives on the device
+    e16 = ((idx[:, None] * 7 + torch.arange(dim)[None, :] * 3) % 2001 - 1000).to(torch.int16)
+    u = idx[:, None] * 5 + torch.arange(4)[None, :]
+    ge = gather_shards(dist, e16, rank, world, dst=0)
+    gu = gather_shards(dist, u, rank, world, dst=0)
+    if rank == 0:
+        assert ge.dtype == torch.int16 and ge.shape == (total, dim)
+        np.save(out_path, ge.numpy())
+        np.save(out_path + ".u.npy", gu.numpy())
+    else:
+        assert ge is None and gu is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_helper(tmp_path):
+    """Shards produced per rank (keyed by the global target index) and gathered by the product's helper equal the
+    single-process result, in global target order."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    total, dim = 512, 24
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_gather_worker, args=(2, port, total, dim, out), nprocs=2, join=True)
+    idx = np.arange(total)
+    want = ((idx[:, None] * 7 + np.arange(dim)[None, :] * 3) % 2001 - 1000).astype(np.int16)
+    assert np.array_equal(np.load(out), want)
+    assert np.array_equal(np.load(out + ".u.npy"), idx[:, None] * 5 + np.arange(4)[None, :])
+
+
 def test_two_rank_gloo_gather(tmp_path):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

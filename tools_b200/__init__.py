@@ -5,6 +5,8 @@ Host-side mirror of the reference's interface for that path only:
   sample.g_trapdoor: GadgetParameters(Ring), gen_trapdoor, short bases (src/sample/g_trapdoor/)
   compression     : LossyCompressionFIPS203                          (src/compression/)
   utils           : rot_minus, rot_minus_matrix                      (src/utils/rotation_matrix.rs)
+                    encode / decode_value_*_polynomialringzq         (src/utils/common_encodings.rs)
+  serde_io        : serde-JSON / typetag / FLINT-string import of parameters and keys
 All arithmetic on the hot path runs in the CUDA library behind include/qfall_b200.h.
 """
 from . import _ffi  # noqa: F401
@@ -13,3 +15,4 @@ from .gadget import (GadgetParameters, GadgetParametersRing, find_solution_gadge
 from ._ffi import NotInDomain, QfError  # noqa: F401
 from .psf import PSFGPV, PSFGPVRing, PSFPerturbation  # noqa: F401
 from .compression import lossy_compress, lossy_decompress  # noqa: F401
+from .encodings import decode_value_from_polynomialringzq, encode_value_in_polynomialringzq  # noqa: F401

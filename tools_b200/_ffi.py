@@ -72,9 +72,14 @@ SIGNATURES = {
     "qf_decompress_i64": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _vp]),
     "qf_compress_encode_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _i32, _vp]),
     "qf_decode_decompress_u16": (_i32, [_vp, _vp, _sz, _u32, _u32, _i32, _i32, _vp]),
+    "qf_encode_digits": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _i32, _vp]),
+    "qf_decode_digits": (_i32, [_vp, _vp, _sz, _u64, _u32, _i32, _i32, _vp]),
+    "qf_encode_bits_u16": (_i32, [_vp, _vp, _sz, _u32, _i32, _vp]),
+    "qf_decode_bits_u16": (_i32, [_vp, _vp, _sz, _u32, _i32, _vp]),
     "qf_sample_z": (_i32, [_vp, _sz, C.c_double, _u64, _vp]),
     "qf_debug_gemm_i8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _u64, _vp]),
-    "qf_probe_i8_peak": (_i32, [_i32, _i64, _i64, _i64, _i32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qf_probe_i8_peak": (_i32, [_i32, _i64, _i64, _i64, _i32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double)]),
     "qf_fill_uniform_modq_dev": (_i32, [_vp, _sz, _u64, _u64, _vp]),
 }
 

@@ -2295,6 +2295,79 @@ qf_status qf_decode_decompress_u16(const uint8_t* in, uint16_t* out, size_t npol
     return byte_code_any(in, out, npoly, q, d, decompress, dev, st, 1);
 }
 
+// ---- common_encodings.rs:49-153, batched ----------------------------------------------------------------------------------
+// in_bytes / out_bytes per element are fixed by the direction: digits are bytes, coefficients coeff_bytes (2 or 8) wide
+static qf_status encode_any(const void* in, void* out, size_t count, size_t in_esz, size_t out_esz, int dev, cudaStream_t st,
+                            cudaError_t (*run)(const void*, void*, void*), void* closure) {
+    auto map_err = [](cudaError_t e) { return e == cudaSuccess ? QF_OK : (e == cudaErrorMisalignedAddress ? QF_ERR_INVALID : QF_ERR_CUDA); };
+    if (dev) return map_err(run(in, out, closure));
+    void *di = nullptr, *dout = nullptr;
+    if (cudaMalloc(&di, count * in_esz) != cudaSuccess) return QF_ERR_CUDA;
+    if (cudaMalloc(&dout, count * out_esz) != cudaSuccess) { cudaFree(di); return QF_ERR_CUDA; }
+    qf_status rc = QF_OK;
+    if (cudaMemcpyAsync(di, in, count * in_esz, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (rc == QF_OK) rc = map_err(run(di, dout, closure));
+    if (rc == QF_OK && cudaMemcpyAsync(out, dout, count * out_esz, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QF_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == QF_OK) rc = QF_ERR_CUDA;
+    cudaFree(di);
+    cudaFree(dout);
+    return rc;
+}
+struct EncClosure { size_t count; unsigned long long q; unsigned base; int coeff_bytes; cudaStream_t st; };
+
+static qf_status encode_args_ok(const void* in, const void* out, size_t count, uint64_t q, uint32_t base, int coeff_bytes) {
+    if ((!in || !out) && count) return QF_ERR_INVALID;
+    if (base < 2 || q < 2) return QF_ERR_INVALID;  // MathError::InvalidIntegerInput (common_encodings.rs:133-137)
+    if (base > 256 || q >= (1ull << 62)) return QF_ERR_UNSUPPORTED;
+    if (coeff_bytes != 2 && coeff_bytes != 8) return QF_ERR_INVALID;
+    if (coeff_bytes == 2 && q > 65535) return QF_ERR_INVALID;
+    return QF_OK;
+}
+
+qf_status qf_encode_digits(const uint8_t* digits, void* coeffs, size_t count, uint64_t q, uint32_t base, int coeff_bytes,
+                           int device_ptrs, void* cuda_stream) {
+    qf_status st = encode_args_ok(digits, coeffs, count, q, base, coeff_bytes);
+    if (st != QF_OK || count == 0) return st;
+    EncClosure c{count, q, base, coeff_bytes, (cudaStream_t)cuda_stream};
+    return encode_any(digits, coeffs, count, 1, (size_t)coeff_bytes, device_ptrs, c.st,
+                      [](const void* i, void* o, void* cl) {
+                          auto* c = (EncClosure*)cl;
+                          return qf_launch_encode_digits((const uint8_t*)i, o, c->count, c->q, c->base, c->coeff_bytes, c->st);
+                      }, &c);
+}
+qf_status qf_decode_digits(const void* coeffs, uint8_t* digits, size_t count, uint64_t q, uint32_t base, int coeff_bytes,
+                           int device_ptrs, void* cuda_stream) {
+    qf_status st = encode_args_ok(coeffs, digits, count, q, base, coeff_bytes);
+    if (st != QF_OK || count == 0) return st;
+    EncClosure c{count, q, base, coeff_bytes, (cudaStream_t)cuda_stream};
+    return encode_any(coeffs, digits, count, (size_t)coeff_bytes, 1, device_ptrs, c.st,
+                      [](const void* i, void* o, void* cl) {
+                          auto* c = (EncClosure*)cl;
+                          return qf_launch_decode_digits(i, (uint8_t*)o, c->count, c->q, c->base, c->coeff_bytes, c->st);
+                      }, &c);
+}
+qf_status qf_encode_bits_u16(const uint8_t* msg, uint16_t* coeffs, size_t nbytes, uint32_t q, int device_ptrs, void* cuda_stream) {
+    qf_status st = encode_args_ok(msg, coeffs, nbytes, q, 2, 2);
+    if (st != QF_OK || nbytes == 0) return st;
+    EncClosure c{nbytes, q, 2, 2, (cudaStream_t)cuda_stream};
+    // count = message bytes; 16 bytes of coefficients per message byte
+    return encode_any(msg, coeffs, nbytes, 1, 16, device_ptrs, c.st,
+                      [](const void* i, void* o, void* cl) {
+                          auto* c = (EncClosure*)cl;
+                          return qf_launch_encode_bits_u16((const uint8_t*)i, (uint16_t*)o, c->count, (uint32_t)c->q, c->st);
+                      }, &c);
+}
+qf_status qf_decode_bits_u16(const uint16_t* coeffs, uint8_t* msg, size_t nbytes, uint32_t q, int device_ptrs, void* cuda_stream) {
+    qf_status st = encode_args_ok(coeffs, msg, nbytes, q, 2, 2);
+    if (st != QF_OK || nbytes == 0) return st;
+    EncClosure c{nbytes, q, 2, 2, (cudaStream_t)cuda_stream};
+    return encode_any(coeffs, msg, nbytes, 16, 1, device_ptrs, c.st,
+                      [](const void* i, void* o, void* cl) {
+                          auto* c = (EncClosure*)cl;
+                          return qf_launch_decode_bits_u16((const uint16_t*)i, (uint8_t*)o, c->count, (uint32_t)c->q, c->st);
+                      }, &c);
+}
+
 qf_status qf_sample_z(const double* centers, size_t count, double s, uint64_t seed, int64_t* out) {
     if (!centers || !out || !(s > 0)) return QF_ERR_INVALID;
     if (!(s < 2.0e6)) return QF_ERR_UNSUPPORTED;  // proposals are rounded in fp32: 7.6 sigma' must stay below 2^24
@@ -2383,7 +2456,7 @@ qf_status qf_debug_gemm_i8(const int64_t* x, const int64_t* w, int w_signed, int
 // tiles, two accumulator buffers in TMEM, int32 store epilogue) on random bytes, long K.  `iters` launches timed one by one
 // (best = burst figure), then launches back to back for >= sustain_ms (sustained figure, clocks settled under load).
 qf_status qf_probe_i8_peak(int device, int64_t B, int64_t N, int64_t K, int iters, double sustain_ms, double* best_tops,
-                           double* sustained_tops) {
+                           double* sustained_tops, double* pipe_tops) {
     if (B < 1 || N < 1 || K < 128 || K > 65536 || (K & 127) || iters < 1) return QF_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return QF_ERR_CUDA;
     int8_t* dx = nullptr; uint8_t* dw = nullptr; int32_t* dout = nullptr;
@@ -2424,6 +2497,23 @@ qf_status qf_probe_i8_peak(int device, int64_t B, int64_t N, int64_t K, int iter
         float ms = 0;
         if (rc == QF_OK) cudaEventElapsedTime(&ms, e0, e1);
         if (ms > 0) sustained = ops * reps / (ms * 1e-3) / 1e12;
+    }
+    // the pipe itself: MMAs on resident operands, one CTA per SM (best of 3 launches of ~5 ms)
+    if (rc == QF_OK && pipe_tops && B >= 1024) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        double bestp = 0;
+        for (int i = 0; i < 4 && rc == QF_OK; ++i) {
+            double pops = 0;
+            cudaEventRecord(e0, st);
+            if (qf_launch_i8_pipe_probe(dx, dw, 20000, sms, &pops, st) != cudaSuccess) { rc = QF_ERR_CUDA; break; }
+            cudaEventRecord(e1, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = QF_ERR_CUDA; break; }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (i >= 1 && ms > 0) bestp = std::max(bestp, pops / (ms * 1e-3) / 1e12);
+        }
+        *pipe_tops = bestp;
     }
     if (best_tops) *best_tops = best;
     if (sustained_tops) *sustained_tops = sustained;

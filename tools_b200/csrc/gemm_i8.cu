@@ -448,6 +448,59 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
 }
 
+// Ceiling of the int8 tensor pipe itself: every CTA loads ONE 128 x 128-byte x tile and ONE 256 x 128-byte w tile and then
+// issues the MMAs of that k block `iters` times on the resident operands (no operand traffic at all: what is measured is
+// tcgen05.mma kind::i8 at M = 128, N = 256, i.e. 100 % "IMMA pipe active").  The accumulator wraps around; nothing is read back.
+__global__ void __launch_bounds__(128, 1)
+i8_pipe_probe_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int iters) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int x_tile = TILE_M * BLOCK_K, w_tile = 256 * BLOCK_K;
+    uint64_t* bars = (uint64_t*)(smem + x_tile + w_tile);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[0], (uint32_t)(x_tile + w_tile));
+            tma_load_3d(&map_x, smem, &bars[0], 0, (int)(blockIdx.x % 8) * TILE_M, 0);
+            tma_load_3d(&map_w, smem + x_tile, &bars[0], 0, 0, 0);
+        }
+        mbar_wait(&bars[0], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem + x_tile));
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / 32; ++kk) mma_i8(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, 1u);
+            }
+            mma_commit(&bars[1]);
+        }
+        __syncwarp();
+        mbar_wait(&bars[1], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 }  // namespace
 
 int qf_i8_tile_n(int LX, int LW, int N, int d_lo) {
@@ -538,5 +591,18 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     dim3 grid((unsigned)(total_tiles < sm_count ? total_tiles : sm_count));  // persistent: one CTA per SM
     if (a.out_kind == 3) gemm_i8_kernel<1><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
     else gemm_i8_kernel<0><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
+    return cudaGetLastError();
+}
+
+// x: >= 1024 rows x 128 bytes, w: 256 rows x 128 bytes of int8 (row stride 128).  Returns the int8 operations issued.
+cudaError_t qf_launch_i8_pipe_probe(const int8_t* x, const uint8_t* w, int iters, int grid, double* ops_out, cudaStream_t stream) {
+    CUtensorMap mx, mw;
+    if (!make_map(&mx, x, BLOCK_K, 8 * TILE_M, 1, BLOCK_K, (long)8 * TILE_M * BLOCK_K, TILE_M)) return cudaErrorInvalidValue;
+    if (!make_map(&mw, w, BLOCK_K, 256, 1, BLOCK_K, (long)256 * BLOCK_K, 256)) return cudaErrorInvalidValue;
+    const int smem = TILE_M * BLOCK_K + 256 * BLOCK_K + 1024 + 64;
+    cudaError_t e = cudaFuncSetAttribute(i8_pipe_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    i8_pipe_probe_kernel<<<grid, 128, smem, stream>>>(mx, mw, iters);
+    if (ops_out) *ops_out = 2.0 * grid * (double)iters * TILE_M * 256.0 * BLOCK_K;
     return cudaGetLastError();
 }

@@ -106,6 +106,14 @@ cudaError_t qf_launch_byte_decode(const uint8_t* in, uint16_t* out, size_t npoly
 cudaError_t qf_launch_compress_i64(const int64_t* in, int64_t* out, size_t count, unsigned long long q,
                                    uint32_t d, int decompress, cudaStream_t stream);
 
+// ---- encodings.cu : common_encodings.rs:49-153, batched (digits as bytes, base <= 256; bit-packed base 2) ----------
+cudaError_t qf_launch_encode_digits(const uint8_t* digits, void* coeffs, size_t count, unsigned long long q, unsigned base,
+                                    int coeff_bytes, cudaStream_t stream);
+cudaError_t qf_launch_decode_digits(const void* coeffs, uint8_t* digits, size_t count, unsigned long long q, unsigned base,
+                                    int coeff_bytes, cudaStream_t stream);
+cudaError_t qf_launch_encode_bits_u16(const uint8_t* msg, uint16_t* coeffs, size_t nbytes, uint32_t q, cudaStream_t stream);
+cudaError_t qf_launch_decode_bits_u16(const uint16_t* coeffs, uint8_t* msg, size_t nbytes, uint32_t q, cudaStream_t stream);
+
 // ---- ring_ntt.cu -----------------------------------------------------------
 // Negacyclic products over Z_q[X]/(X^n+1) through an exact NTT over the Goldilocks prime.
 // a_hat: npoly x n precomputed transforms of the key polynomials (centred lift of a mod q).
@@ -190,6 +198,8 @@ struct FaFusedArgs {
 };
 cudaError_t qf_launch_f_a_fused(const FaFusedArgs& a, cudaStream_t stream);
 cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream);
+// tensor-pipe ceiling probe: MMAs on shared-memory-resident operands (gemm_i8.cu)
+cudaError_t qf_launch_i8_pipe_probe(const int8_t* x, const uint8_t* w, int iters, int grid, double* ops_out, cudaStream_t stream);
 
 // ---- limb splitting (elementwise.cu) ---------------------------------------------------------
 // balanced s8 digits; *flag |= 8 when a value does not fit L digits

@@ -96,25 +96,25 @@ np_propose_kernel(float4* __restrict__ out, long ldo, int B, int j_lo, int width
     }
 }
 
-constexpr int NP_TPL = 4;                 // targets per lane
-constexpr int NP_TARGETS = 32 * NP_TPL;   // targets per CTA: 4 warps x 8 quads x 4 targets
+constexpr int NP_TPL = 2;                 // targets per lane
+constexpr int NP_TARGETS = 32 * NP_TPL;   // targets per CTA: 4 warps x 8 quads x NP_TPL targets
 constexpr int NP_TPB = 128;               // 4 lanes (a quad) per group of NP_TPL targets
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = NP_NB_MAX + 1;      // centre tile is target-major: ts[t * NP_TS + i]
 
-// One nb-wide diagonal block.  Three phases per CTA of 128 targets (one CTA per SM: 148 CTAs = one chunk of 18944):
+// One nb-wide diagonal block.  Three phases per CTA of 64 targets (two CTAs per SM: 296 CTAs = one chunk of 18944):
 //  0. stage the mu-block (transposed) and the 128 x nb tile of centres through shared memory (coalesced);
 //  1. the proposals of every (target, coordinate) -- the first Philox block of that coordinate's stream turned into
 //     two normals and the logs of two uniforms by np_propose_kernel at full occupancy -- are read from global memory
-//     one coordinate ahead (coordinate-major layout: the 4 targets of a lane are one 64-byte segment);
-//  2. the recursion i = nb-1 .. 0.  A quad of lanes owns NP_TPL = 4 targets; lane qd of the quad keeps the centres of
-//     coordinates 4k+qd of all four targets in registers.  Per step: one quad shuffle per target, the accept / reject
+//     one coordinate GROUP (four steps) ahead (coordinate-major layout: a warp reads contiguous segments);
+//  2. the recursion i = nb-1 .. 0.  A quad of lanes owns NP_TPL targets; lane qd of the quad keeps the centres of
+//     coordinates 4k+qd of all its targets in registers.  Per step: one quad shuffle per target, the accept / reject
 //     arithmetic (a handful of flops per target), then the right-looking update c'_j -= mu_ji z_i of the remaining
-//     centres: every mu value read from shared memory is used for the four targets of the lane (the kernel is bound
-//     by exactly those shared-memory reads: one target per lane needs 4x the bandwidth for the same flops).
+//     centres: every mu value read from shared memory is used for all targets of the lane (the kernel is bound
+//     by exactly those shared-memory reads: one target per lane needs NP_TPL x the bandwidth for the same flops).
 // Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
 // one-thread-per-target formulation.
-__global__ void __launch_bounds__(NP_TPB, 1)
+__global__ void __launch_bounds__(NP_TPB, 2)
 np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
                int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
@@ -126,15 +126,19 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbe = min(nb, dim - j0);
     const long b0 = (long)blockIdx.x * NP_TARGETS;
+#pragma unroll 8
     for (int i = tid; i < nb * nb; i += NP_TPB) {
         const int r = i / nb, c = i - r * nb;  // coalesced read along c
         ust[c * us_ld + r] = (r < nbe && c < nbe && c > r) ? U[(long)(j0 + r) * ldu + (j0 + c)] : 0.0;
     }
     for (int i = tid; i < nbe; i += NP_TPB) dgs[i] = dg_g[j0 + i];
+#pragma unroll 4
     for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
         const long b = b0 + r;
-        if (b < B)
-            for (int c = lane; c < nbe; c += 32) ts[r * NP_TS + c] = T[b * ldt + j0 + c];
+        const double v0 = (b < B && lane < nbe) ? T[b * ldt + j0 + lane] : 0.0;
+        const double v1 = (b < B && lane + 32 < nbe) ? T[b * ldt + j0 + lane + 32] : 0.0;
+        ts[r * NP_TS + lane] = v0;
+        ts[r * NP_TS + lane + 32] = v1;
     }
     __syncthreads();
     // phase 2: the recursion, fully register resident; the loop over coordinate groups stays rolled (the register file
@@ -150,30 +154,32 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
             for (int j = 0; j < NG; ++j) c[k][j] = (4 * j + qd < nbe) ? ts[(tl + k) * NP_TS + 4 * j + qd] : 0.0;
         // proposals (prop points at coordinate j0): row ii holds the proposals of all targets for coordinate j0 + ii
         const float4* pq = prop + bq;
-        float4 pcur[NP_TPL], pnxt[NP_TPL];
-        {
-            const int ii = 4 * NG - 1;
+        float4 pcur[4][NP_TPL], pnxt[4][NP_TPL];
 #pragma unroll
-            for (int k = 0; k < NP_TPL; ++k) pcur[k] = (ii < nbe) ? pq[(long)ii * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < 4; ++o) {
+            const int ii = 4 * (NG - 1) + o;
+#pragma unroll
+            for (int k = 0; k < NP_TPL; ++k) pcur[o][k] = (ii < nbe) ? pq[(long)ii * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int kidx = 0; kidx < NG; ++kidx) {
             const int g = NG - 1 - kidx;
 #pragma unroll
+            for (int o = 0; o < 4; ++o) {  // proposals of the next group, in flight during the four steps of this one
+                const int in = 4 * (g - 1) + o;
+#pragma unroll
+                for (int k = 0; k < NP_TPL; ++k)
+                    pnxt[o][k] = (g > 0 && in < nbe) ? pq[(long)in * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
             for (int owner = 3; owner >= 0; --owner) {
                 const int ii = 4 * g + owner;
-                {   // proposals of the next coordinate, in flight during this step
-                    const int in = ii - 1;
-#pragma unroll
-                    for (int k = 0; k < NP_TPL; ++k)
-                        pnxt[k] = (in >= 0 && in < nbe) ? pq[(long)in * ldprop + k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
                 if (ii < nbe) {  // uniform
                     const DGaussParams dgp = dgs[ii];
                     double z[NP_TPL];
 #pragma unroll
                     for (int k = 0; k < NP_TPL; ++k) {
                         const double cp = __shfl_sync(0xffffffffu, c[k][NG - 1], (lane & ~3) | owner);
-                        const float4 pr = pcur[k];
+                        const float4 pr = pcur[owner][k];
                         const double c_int = rint(cp);
                         const float c_frac = (float)(cp - c_int);
                         double zz = 0.0;
@@ -215,9 +221,11 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
                         }
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < NP_TPL; ++k) pcur[k] = pnxt[k];
             }
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int k = 0; k < NP_TPL; ++k) pcur[o][k] = pnxt[o][k];
 #pragma unroll
             for (int k = 0; k < NP_TPL; ++k) {
                 if (4 * g + qd < nbe) ts[(tl + k) * NP_TS + 4 * g + qd] = c[k][NG - 1];

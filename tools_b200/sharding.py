@@ -13,14 +13,32 @@ def shard(total: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def gather_shards(dist, local, rank, world, dst=0, group=None):
+    """ONE gather of equally shaped per-rank tensors to `dst` (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU
+    tests).  Returns the concatenation along dim 0 on `dst` (rank order = global target order, because shard() hands out
+    contiguous slices in rank order), None elsewhere."""
+    # a gather only moves bytes: int16 (which neither NCCL nor gloo has as a reduction type) travels as uint8
+    import torch
+
+    rows = local.shape[0]
+    wire = local.contiguous().view(torch.uint8).reshape(rows, -1) if local.dtype == torch.int16 else local.contiguous()
+    if rank == dst:
+        out = wire.new_empty((world * rows,) + tuple(wire.shape[1:]))
+        dist.gather(wire, list(out.split(rows)), dst=dst, group=group)
+        if wire is not local and local.dtype == torch.int16:
+            out = out.view(torch.int16).reshape((world * rows,) + tuple(local.shape[1:]))
+        return out
+    dist.gather(wire, None, dst=dst, group=group)
+    return None
+
+
 def gather_domain_i16(torch, dist, lib, ffi, e, u, rank, world, dev, stream, max_bytes=64 << 30, dst=0):
     """Final gather of the per-rank Domain results over NVLink: each rank narrows its int32 shard to int16
     on the device (qf_narrow_i32_i16_dev -- |e_i| <= 6 s r fits for the reference's parameter sets; overflow is detected and
     reported) and ONE NCCL gather brings the shards to `dst`; the targets travel the same way (as int64) so that `dst` can
-    verify the gathered preimages.  Device-timed (max over ranks is the caller's business: the gather is a collective, its
-    duration on `dst` is the duration).  Returns a dict {ms, bytes, GBps, dtype, ...}; on `dst` also "gathered": (e_all int16
-    [world * B, ...], u_all).  Skipped (returns {"skipped": why}) when the gathered tensor would not fit max_bytes on `dst`
-    -- C4's 4 Mi x 32849 preimages are 276 GB: those results stay sharded."""
+    verify the gathered preimages.  Device-timed on the library's stream.  Returns a dict {narrow_ms, gather_ms, bytes, GBps,
+    ...}; on `dst` also "gathered": (e_all int16 [world * B, ...], u_all).  Skipped (returns {"skipped": why}) when the gathered
+    tensor would not fit max_bytes on `dst` -- C4's 4 Mi x 32849 preimages are 276 GB: those results stay sharded."""
     b = e.shape[0]
     count = e.numel()
     total_bytes = world * count * 2
@@ -29,8 +47,6 @@ def gather_domain_i16(torch, dist, lib, ffi, e, u, rank, world, dev, stream, max
     with torch.cuda.stream(stream):
         e16 = torch.empty(e.shape, dtype=torch.int16, device=dev)
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-        out_e = torch.empty((world * b,) + tuple(e.shape[1:]), dtype=torch.int16, device=dev) if rank == dst else None
-        out_u = torch.empty((world * b,) + tuple(u.shape[1:]), dtype=u.dtype, device=dev) if rank == dst else None
         stream.synchronize()
         dist.barrier()
         ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -39,9 +55,9 @@ def gather_domain_i16(torch, dist, lib, ffi, e, u, rank, world, dev, stream, max
                                        ffi.ptr(stream.cuda_stream))
         assert st == 0
         ev1.record(stream)
-        dist.gather(e16, list(out_e.split(b)) if rank == dst else None, dst=dst)
+        out_e = gather_shards(dist, e16, rank, world, dst)
         ev2.record(stream)
-        dist.gather(u, list(out_u.split(b)) if rank == dst else None, dst=dst)
+        out_u = gather_shards(dist, u, rank, world, dst)
         stream.synchronize()
     assert int(ovf.item()) == 0, "a preimage entry does not fit int16: gather the int32 form instead"
     ms_narrow, ms_gather = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
