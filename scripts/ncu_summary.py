@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (one kernel) into a few lines of markdown:  python scripts/ncu_summary.py rep [rep...]"""
+"""Summarise an .ncu-rep (one kernel) into a few lines of markdown:  python scripts/ncu_summary.py rep [rep...]
+  python scripts/ncu_summary.py --json key=rep [key=rep ...] > profiles/traffic_r2.json
+writes, per key, the dram read + write bytes of the captured launch (what bench.py reports as roofline.traffic)."""
 import csv
 import subprocess
 import sys
@@ -22,7 +24,37 @@ WANT = [
 ]
 
 
+def raw_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    return [{h: (v, u) for h, v, u in zip(hdr, vals, units)} for vals in rows[2:]]
+
+
+def to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+
+def main_json(pairs):
+    import json
+
+    out = {}
+    for pair in pairs:
+        key, rep = pair.split("=", 1)
+        d = raw_rows(rep)[0]
+        rd, wr = to_bytes(*d["dram__bytes_read.sum"]), to_bytes(*d["dram__bytes_write.sum"])
+        out[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr,
+                    "duration_ms": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(d["gpu__time_duration.sum"][1], 1),
+                    "kernel": d["Kernel Name"][0][:120], "grid": d["Grid Size"][0],
+                    "tensor_pipe_active_pct": d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("", ""))[0],
+                    "note": f"ncu --set full capture {rep} (one launch)"}
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--json":
+        return main_json(sys.argv[2:])
     for rep in sys.argv[1:]:
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))

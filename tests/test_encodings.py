@@ -56,12 +56,14 @@ def test_device_encodings_match_oracle(q, base, n):
     assert E.decode_values_batch(enc, base, q) == vals
     # noisy coefficients, any representative (negative, above q): decode digit by digit against the oracle
     tol = max(0, q // (2 * base * base) - 1)  # see test_oracle_round_trip_reference_cases
-    noise = rng.integers(-tol, tol + 1, enc.shape)
-    noisy = (enc.astype(object) + noise.astype(object))
-    shifted = noisy + rng.integers(-2, 3, enc.shape).astype(object) * q
-    if q < 2**40:
-        got = E.decode_values_batch(np.asarray(shifted, dtype=np.int64), base, q)
-        assert got == [O.decode_value_from_polynomialringzq(r.tolist(), base, q) for r in shifted] == vals
+    for amp, recover in ((tol // 2, True), (2 * tol + 3, False)):  # inside the decoding radius / beyond it (parity only)
+        noise = rng.integers(-amp, amp + 1, enc.shape)
+        shifted = enc.astype(object) + noise.astype(object) + rng.integers(-2, 3, enc.shape).astype(object) * q
+        if q < 2**40:
+            got = E.decode_values_batch(np.asarray(shifted, dtype=np.int64), base, q)
+            assert got == [O.decode_value_from_polynomialringzq(r.tolist(), base, q) for r in shifted]
+            if recover:
+                assert got == vals
     # trait-shaped single calls and the reference's error cases
     one = E.encode_value_in_polynomialringzq(vals[5], base, n, q)
     assert E.decode_value_from_polynomialringzq(one, base, q) == vals[5]

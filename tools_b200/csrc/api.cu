@@ -150,6 +150,7 @@ struct qf_ctx {
     // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
     bool use_ozaki = false;
     int u_limbs = 7;
+    bool np_fuse64 = true; // the rank-64 updates inside a 256-block run in the tail of the diagonal-block kernel
     int np_dlo = 2;        // digit sums below 256^np_dlo are dropped from the fixed-point updates (error budget: np_block)
     Dev dUl, dUscale, dNz, dMma;
     // highest non-zero digit plane of z per 1024-block [0, n1024), per 4096-block [n1024, n1024 + n4096) and over the
@@ -672,13 +673,15 @@ static inline int np_block_index(long col, long D, long S) {
 // updates of every coordinate >= hi.  level 0 = one sequential diagonal block.  prop0 = first coordinate of the
 // enclosing 1024-level block (origin of the pre-generated proposals).
 qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, int level, long prop0, uint64_t seed,
-                   uint64_t first) {
+                   uint64_t first, long up_lo = -1) {
     const long D = ctx->dim, ldD = ctx->ld_dim;
     const double* U = ctx->dU.as<double>();
     if (level == 0) {
+        // up_lo >= 0: the diagonal-block kernel also applies this block's update to the columns [up_lo, lo) of the
+        // enclosing 256-block (fused: no K = 64 GEMM launch, no extra pass over Z)
         LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
                                  ctx->w[9].as<float4>() + (lo - prop0) * ctx->chunk, ctx->chunk, Bc, (int)lo, (int)(hi - lo), (int)D,
-                                 seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream));
+                                 seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream, (int)up_lo));
         return QF_OK;
     }
     const long step = NP_SIZES[level - 1];
@@ -696,7 +699,12 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                                         seed, first, ctx->stream));
             prop0 = sub_lo;
         }
-        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, prop0, seed, first));
+        const bool fused_update = level == 1 && ctx->np_fuse64 && (sub_lo - lo) % 16 == 0;
+        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, prop0, seed, first, fused_update ? lo : -1));
+        if (fused_update) {
+            sub_hi = sub_lo;
+            continue;
+        }
         if (i8_level) {
             const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
@@ -1292,6 +1300,8 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
         ctx->use_i8 = !(env && env[0] == '1');
         const char* envf = getenv("QF_DISABLE_FUSED_FA");
         ctx->fused_fa = !(envf && envf[0] == '1');
+        const char* envu = getenv("QF_DISABLE_NP_FUSE64");  // test switch: separate K = 64 GEMM launches as before
+        ctx->np_fuse64 = !(envu && envu[0] == '1');
         const char* envd = getenv("QF_NP_DLO");  // test switch: 0 = every digit pair of the fixed-point updates
         if (envd) ctx->np_dlo = std::max(0, std::min(3, atoi(envd)));
     }

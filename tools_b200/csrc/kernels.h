@@ -88,9 +88,11 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
 // writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).
 // *flag is set when |z| >= zlimit (exact-integer range check).
 // prop: this block's pre-generated proposals (np_propose), coordinate-major: prop[(i - j0) * ldprop + b]
-cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
+// up_lo (optional, -1 = none): the kernel also applies the block's update to the columns [up_lo, j0) of its own targets,
+//   T[b][j] -= sum_i Z[b][j0 + i] U[j][j0 + i]   (the rank-nb update inside the enclosing 256-block)
+cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
-                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream);
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo = -1);
 // two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[(i - j_lo) * ldo + b]
 cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
                                  uint64_t first_target, cudaStream_t stream);

@@ -101,6 +101,7 @@ constexpr int NP_TARGETS = 32 * NP_TPL;   // targets per CTA: 4 warps x 8 quads 
 constexpr int NP_TPB = 128;               // 4 lanes (a quad) per group of NP_TPL targets
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = NP_NB_MAX + 1;      // centre tile is target-major: ts[t * NP_TS + i]
+constexpr int NP_UST_DOUBLES = (NP_NB_MAX * (NP_NB_MAX + 1) + 1) & ~1;  // mu block, later the update panel (64 x 65)
 
 // One nb-wide diagonal block.  Three phases per CTA of 64 targets (two CTAs per SM: 296 CTAs = one chunk of 18944):
 //  0. stage the mu-block (transposed) and the 128 x nb tile of centres through shared memory (coalesced);
@@ -115,13 +116,13 @@ constexpr int NP_TS = NP_NB_MAX + 1;      // centre tile is target-major: ts[t *
 // Draw order and Philox counters are those of sample_dgauss(), so the output is identical to the
 // one-thread-per-target formulation.
 __global__ void __launch_bounds__(NP_TPB, 2)
-np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
+np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
-               int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag) {
+               int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag, int up_lo) {
     extern __shared__ __align__(16) double np_sm[];
     const int us_ld = nb + 1;                             // padded: the transposing store is (almost) conflict-free
     double* ust = np_sm;                                  // ust[c * us_ld + r] = U[j0+r][j0+c], c > r
-    double* ts = ust + ((nb * us_ld + 1) & ~1);           // ts[t * NP_TS + i]  (16-byte aligned)
+    double* ts = ust + NP_UST_DOUBLES;                    // ts[t * NP_TS + i]  (16-byte aligned)
     DGaussParams* dgs = reinterpret_cast<DGaussParams*>(ts + ((NP_TARGETS * NP_TS + 1) & ~1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbe = min(nb, dim - j0);
@@ -240,6 +241,52 @@ np_diag_kernel(const double* __restrict__ T, long ldt, double* __restrict__ Z, l
         if (bb < B)
             for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[r * NP_TS + c];
     }
+    // phase 3: the rank-nb update of the columns [up_lo, j0) that remain in the enclosing 256-block, for this CTA's own
+    // targets:  T[b][j] -= sum_i z_i U[j][j0 + i].  The z tile is still in shared memory; the panel of U goes through
+    // the (now free) mu buffer 64 columns at a time.  Lanes are targets (lane, lane + 32), warps are 16-column groups:
+    // the z reads are conflict-free (row stride 65), the U reads are warp-wide broadcasts, 32 accumulators per lane.
+    // (This used to be a separate K = 64 fp64 GEMM launch per diagonal block: launch- and latency-bound, ~10 ms per chunk.)
+    for (int c0 = up_lo; c0 < j0; c0 += 64) {
+        const int ncol = min(64, j0 - c0);
+        __syncthreads();
+        for (int idx = tid; idx < 64 * 64; idx += NP_TPB) {
+            const int j = idx >> 6, i = idx & 63;  // coalesced along i
+            ust[i * NP_TS + j] = (j < ncol && i < nbe) ? U[(long)(c0 + j) * ldu + j0 + i] : 0.0;
+        }
+        __syncthreads();
+        double acc0[16], acc1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = 0.0;
+        const double* z0 = ts + lane * NP_TS;
+        const double* z1 = ts + (lane + 32) * NP_TS;
+        const double* ub = ust + warp * 16;
+#pragma unroll 2
+        for (int i = 0; i < nbe; ++i) {
+            const double a = z0[i], bq2 = z1[i];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const double u = ub[i * NP_TS + c];
+                acc0[c] = fma(a, u, acc0[c]);
+                acc1[c] = fma(bq2, u, acc1[c]);
+            }
+        }
+        if (warp * 16 < ncol) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long bb = b0 + lane + 32 * k;
+                if (bb < B) {
+                    double2* tr = reinterpret_cast<double2*>(T + bb * ldt + c0 + warp * 16);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        double2 v = tr[c];
+                        v.x -= k ? acc1[2 * c] : acc0[2 * c];
+                        v.y -= k ? acc1[2 * c + 1] : acc0[2 * c + 1];
+                        tr[c] = v;
+                    }
+                }
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -274,14 +321,17 @@ cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int wid
     return cudaGetLastError();
 }
 
-cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
+cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
-                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream) {
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo) {
     if (B <= 0) return cudaSuccess;
     if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
-    size_t smem = (size_t)(((nb * (nb + 1) + 1) & ~1) + ((NP_TARGETS * NP_TS + 1) & ~1)) * sizeof(double) +
-                  (size_t)nb * sizeof(DGaussParams);
+    if (up_lo < 0 || up_lo > j0) up_lo = j0;  // no fused update
+    // the fused update needs 16-byte aligned rows and whole 16-column groups
+    if (up_lo < j0 && ((ldt & 1) || ((j0 - up_lo) & 15) || (up_lo & 1) || (((uintptr_t)T) & 15))) return cudaErrorInvalidValue;
+    size_t smem = (size_t)(NP_UST_DOUBLES + ((NP_TARGETS * NP_TS + 1) & ~1)) * sizeof(double) +
+                  (size_t)NP_NB_MAX * sizeof(DGaussParams);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -289,6 +339,6 @@ cudaError_t qf_launch_np_diag(const double* T, long ldt, double* Z, long ldz, co
         configured = smem;
     }
     np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0, nb, dim, seed,
-                                                   first_target, zlimit, flag);
+                                                   first_target, zlimit, flag, up_lo);
     return cudaGetLastError();
 }
