@@ -153,10 +153,11 @@ struct qf_ctx {
     bool np_fuse64 = true; // the rank-64 updates inside a 256-block run in the tail of the diagonal-block kernel
     int np_dlo = 2;        // digit sums below 256^np_dlo are dropped from the fixed-point updates (error budget: np_block)
     Dev dUl, dUscale, dNz, dMma;
-    // highest non-zero digit plane of z per 1024-block [0, n1024), per 4096-block [n1024, n1024 + n4096) and over the
-    // gadget-free block z2 [n1024 + n4096]: written by the digit split, read by the conditional contraction launches
+    // highest non-zero digit plane of z per 256-block [0, n256), per 1024-block [n256, n256 + n1024), per 4096-block
+    // [.., + n4096) and over the gadget-free block z2 [last]: written by the digit split, read by the conditional
+    // contraction launches
     Dev dGate;
-    int gate_n1024 = 0, gate_n4096 = 0;
+    int gate_n256 = 0, gate_n1024 = 0, gate_n4096 = 0;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -623,9 +624,10 @@ qf_status samp_p_pert_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t s
 // GPV / ring samp_p on one chunk: GPV08 SampleD in GSO coordinates (gpv.rs:152-161,
 // gpv_ring.rs:160-212)
 // ---------------------------------------------------------------------------
-// Block sizes of the recursion: 64-wide diagonal blocks are sequential per target (np_diag); the updates between 64- and
-// 256-blocks run on the fp64 tensor pipe (gemm_f64), the updates between 1024-blocks inside a 4096-block and between
-// 4096-blocks on tcgen05 (fixed-point digits).  The top level contracts K = 4096 coordinates per launch: its epilogue
+// Block sizes of the recursion: 64-wide diagonal blocks are sequential per target (np_diag, which also applies the rank-64
+// updates inside its 256-block); the updates between 256-blocks inside a 1024-block, between 1024-blocks inside a
+// 4096-block and between 4096-blocks run on tcgen05 (fixed-point digits); fp64 GEMMs (gemm_f64) remain for dimensions
+// below the tensor-core threshold.  The top level contracts K = 4096 coordinates per launch: its epilogue
 // (a read-modify-write of T, serialised with the MMAs because TMEM holds one tile) is paid once per 4096 instead of
 // once per 1024 coordinates.
 constexpr long NP_SIZES[4] = {64, 256, 1024, 4096};
@@ -685,7 +687,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
         return QF_OK;
     }
     const long step = NP_SIZES[level - 1];
-    const bool i8_level = level >= 3 && ctx->use_ozaki;
+    const bool i8_level = level >= 2 && ctx->use_ozaki;
     for (long sub_hi = hi; sub_hi > lo;) {
         long sub_lo = std::max(lo, (sub_hi - 1) / step * step);
         // tensor-core levels: the ragged top of the whole recursion joins the block below it (the digit planes of U are
@@ -710,16 +712,18 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
             int8_t* zp = ctx->w[8].as<int8_t>();
             int* gates = ctx->dGate.as<int>();
-            int* gate1 = gates + np_block_index(sub_lo, D, NP_SIZES[2]);
-            int* gate4 = gates + ctx->gate_n1024 + np_block_index(sub_lo, D, NP_SIZES[3]);
-            if (level == 3)  // digits of the finished 1024-block of z (kept: the level above and the final S z reuse them)
+            int* gate0 = gates + np_block_index(sub_lo, D, NP_SIZES[1]);
+            int* gate1 = gates + ctx->gate_n256 + np_block_index(sub_lo, D, NP_SIZES[2]);
+            int* gate4 = gates + ctx->gate_n256 + ctx->gate_n1024 + np_block_index(sub_lo, D, NP_SIZES[3]);
+            int* gate_z2 = gates + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096;
+            if (level == 2)  // digits of the finished 256-block of z (kept: the levels above and the final S z reuse them)
                 LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
                                                  ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
-                                                 ctx->stream, gate1, gate4,
-                                                 (ctx->gpv_struct && sub_hi > ctx->nk) ? gates + ctx->gate_n1024 + ctx->gate_n4096 : nullptr));
+                                                 ctx->stream, gate0, gate1, gate4,
+                                                 (ctx->gpv_struct && sub_hi > ctx->nk) ? gate_z2 : nullptr));
             // the update of the rows above it (within the enclosing block) on the tensor cores:
             //   T[:, lo:sub_lo] -= (z digits) x (fixed-point digits of U) * 2^-e
-            if (sub_lo > lo && sub_hi - sub_lo < NP_THIN) {
+            if (sub_lo > lo && sub_hi - sub_lo < NP_SIZES[1]) {
                 // a thin block: per-tile overheads dominate the tensor-core path, use fp64
                 LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
                                 (int)(sub_hi - sub_lo), -1.0, 1.0, 0));
@@ -739,7 +743,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                 // below the 2^-12 the centres need (the widths s / ||b~_i|| are >= 2.3), and below the fp64 rounding of T
                 // at |T| ~ 2^24.
                 g.d_lo = ctx->np_dlo;
-                QF_TRY(gemm_i8_gated(ctx, g, level == 3 ? gate1 : gate4));
+                QF_TRY(gemm_i8_gated(ctx, g, level == 2 ? gate0 : level == 3 ? gate1 : gate4));
             }
         } else if (sub_lo > lo) {
             LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
@@ -789,9 +793,10 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(ctx->w[8].ensure((size_t)ctx->z_limbs * C * ldk));
         CK(ctx->dNz.ensure(nzb));
         CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
+        ctx->gate_n256 = np_block_index(D - 1, D, NP_SIZES[1]) + 1;
         ctx->gate_n1024 = np_block_index(D - 1, D, NP_SIZES[2]) + 1;
         ctx->gate_n4096 = np_block_index(D - 1, D, NP_SIZES[3]) + 1;
-        const size_t gb = (size_t)(ctx->gate_n1024 + ctx->gate_n4096 + 1) * sizeof(int);
+        const size_t gb = (size_t)(ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096 + 1) * sizeof(int);
         CK(ctx->dGate.ensure(gb));
         CK(cudaMemsetAsync(ctx->dGate.p, 0, gb, ctx->stream));
     }
@@ -824,7 +829,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
             g.out_kind = 2; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = I2; g.ldout = ldnk;
             g.flag = ctx->dFlag.as<int>();
             if (g.x_nz) g.nz_kb_off = (int)(nk / 128);
-            QF_TRY(gemm_i8_gated(ctx, g, ctx->use_ozaki ? ctx->dGate.as<int>() + ctx->gate_n1024 + ctx->gate_n4096 : nullptr));
+            QF_TRY(gemm_i8_gated(ctx, g, ctx->use_ozaki ? ctx->dGate.as<int>() + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096 : nullptr));
             LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev,
                                           ctx->stream));
             const long plane2 = C * ldk_nk;
@@ -1730,8 +1735,10 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
             CK(ctx->dUscale.ensure((size_t)nblk * D * 8));
             CK(ctx->dUl.ensure((size_t)ctx->u_limbs * D * ctx->ldk_dim));
             CK(cudaMemsetAsync(ctx->dUl.p, 0, (size_t)ctx->u_limbs * D * ctx->ldk_dim, ctx->stream));
-            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[2], (int)NP_SCALE_BLOCK,
-                                           (int)np_last_block_start(D, NP_SIZES[2]), (int)np_last_block_start(D, NP_SCALE_BLOCK),
+            // digitised: every U[i][j] whose row lies in an earlier 256-block than its column (what the 256-, 1024- and
+            // 4096-level updates read)
+            LAUNCH(qf_launch_ozaki_prepare(ctx->dU.as<double>(), ld, (int)D, (int)NP_SIZES[1], (int)NP_SCALE_BLOCK,
+                                           (int)np_last_block_start(D, NP_SIZES[1]), (int)np_last_block_start(D, NP_SCALE_BLOCK),
                                            ctx->u_limbs,
                                            ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
                                            ctx->stream));

@@ -391,7 +391,7 @@ __device__ __forceinline__ int split4(const long long v[4], int L, int8_t* plane
 // launch -- the contractions that consume these planes pick, on the device, the variant compiled for that many digits
 __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin, int8_t* __restrict__ planes,
                                        long plane_stride, long ldk, int B, int M, int L, int* flag, uint8_t* nz,
-                                       int nz_m_tiles, int nz_kb_total, int col0, int* gate0, int* gate1, int* gate2) {
+                                       int nz_m_tiles, int nz_kb_total, int col0, int* gate0, int* gate1, int* gate2, int* gate3) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int iters = (M + 127) >> 7;
@@ -424,6 +424,7 @@ __global__ void split_f64_limbs_kernel(const double* __restrict__ in, long ldin,
             if (gate0 && *(volatile int*)gate0 < top) atomicMax(gate0, top);
             if (gate1 && *(volatile int*)gate1 < top) atomicMax(gate1, top);
             if (gate2 && *(volatile int*)gate2 < top) atomicMax(gate2, top);
+            if (gate3 && *(volatile int*)gate3 < top) atomicMax(gate3, top);
         }
     }
 }
@@ -628,13 +629,13 @@ cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, i
 }
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
-                                      cudaStream_t stream, int* gate0, int* gate1, int* gate2) {
+                                      cudaStream_t stream, int* gate0, int* gate1, int* gate2, int* gate3) {
     if (B <= 0) return cudaSuccess;
     // char4 stores need 4-byte aligned plane addresses: planes pointer, ldk and col0 multiples of 4 (true for all callers)
     if ((((uintptr_t)planes) & 3) || (ldk & 3) || (col0 & 3)) return cudaErrorMisalignedAddress;
     if (nz && (col0 & 127)) return cudaErrorInvalidValue;
     split_f64_limbs_kernel<<<grid_for((long long)B * ((M + 127) / 128), TPB / 32), TPB, 0, stream>>>(
-        in, ldin, planes, plane_stride, ldk, B, M, L, flag, nz, nz_m_tiles, nz_kb_total, col0, gate0, gate1, gate2);
+        in, ldin, planes, plane_stride, ldk, B, M, L, flag, nz, nz_m_tiles, nz_kb_total, col0, gate0, gate1, gate2, gate3);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,

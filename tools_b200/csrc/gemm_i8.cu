@@ -526,6 +526,10 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     // (wider tiles, ND <= 4, keep their width and take the generic epilogue)
     if (a.out_kind == 3 && nt > 64 && nt < 128) nt = 64;
     if (a.out_kind == 3 && nt > 32 && nt < 64) nt = 32;
+    {
+        static const int force_nt = getenv("QF_I8_UPDATE_NT") ? atoi(getenv("QF_I8_UPDATE_NT")) : 0;  // experiments only
+        if (a.out_kind == 3 && (force_nt == 32 || force_nt == 64) && nt >= force_nt) nt = force_nt;
+    }
     {   // two pipeline stages of LX x-planes + LW w-planes must fit in shared memory
         const int bk0 = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
         const int budget0 = 227 * 1024 - 1024 - 256;

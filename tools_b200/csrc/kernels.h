@@ -210,7 +210,8 @@ cudaError_t qf_launch_i8_pipe_probe(const int8_t* x, const uint8_t* w, int iters
 // gate0..2 (optional, need nz): device ints raised to the index of the highest non-zero digit plane written
 cudaError_t qf_launch_split_f64_limbs(const double* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, int* flag, uint8_t* nz, int nz_m_tiles, int nz_kb_total, int col0,
-                                      cudaStream_t stream, int* gate0 = nullptr, int* gate1 = nullptr, int* gate2 = nullptr);
+                                      cudaStream_t stream, int* gate0 = nullptr, int* gate1 = nullptr, int* gate2 = nullptr,
+                                      int* gate3 = nullptr);
 cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* planes, long plane_stride, long ldk, int B,
                                       int M, int L, unsigned long long* norm2, uint8_t* nz, int nz_m_tiles,
                                       int nz_kb_total, cudaStream_t stream);

@@ -101,7 +101,8 @@ constexpr int NP_TARGETS = 32 * NP_TPL;   // targets per CTA: 4 warps x 8 quads 
 constexpr int NP_TPB = 128;               // 4 lanes (a quad) per group of NP_TPL targets
 constexpr int NP_NB_MAX = 64;
 constexpr int NP_TS = NP_NB_MAX + 1;      // centre tile is target-major: ts[t * NP_TS + i]
-constexpr int NP_UST_DOUBLES = (NP_NB_MAX * (NP_NB_MAX + 1) + 1) & ~1;  // mu block, later the update panel (64 x 65)
+constexpr int NP_PANEL_LD = NP_NB_MAX + 2;  // row stride of the update panel: even, so that column pairs are 16-byte aligned
+constexpr int NP_UST_DOUBLES = NP_NB_MAX * NP_PANEL_LD;  // mu block (64 x 65), later the update panel (64 x 66)
 
 // One nb-wide diagonal block.  Three phases per CTA of 64 targets (two CTAs per SM: 296 CTAs = one chunk of 18944):
 //  0. stage the mu-block (transposed) and the 128 x nb tile of centres through shared memory (coalesced);
@@ -251,7 +252,7 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
         __syncthreads();
         for (int idx = tid; idx < 64 * 64; idx += NP_TPB) {
             const int j = idx >> 6, i = idx & 63;  // coalesced along i
-            ust[i * NP_TS + j] = (j < ncol && i < nbe) ? U[(long)(c0 + j) * ldu + j0 + i] : 0.0;
+            ust[i * NP_PANEL_LD + j] = (j < ncol && i < nbe) ? U[(long)(c0 + j) * ldu + j0 + i] : 0.0;
         }
         __syncthreads();
         double acc0[16], acc1[16];
@@ -259,15 +260,17 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
         for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = 0.0;
         const double* z0 = ts + lane * NP_TS;
         const double* z1 = ts + (lane + 32) * NP_TS;
-        const double* ub = ust + warp * 16;
+        const double2* ub = reinterpret_cast<const double2*>(ust + warp * 16);  // 16-byte aligned: even stride, even offset
 #pragma unroll 2
         for (int i = 0; i < nbe; ++i) {
             const double a = z0[i], bq2 = z1[i];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const double u = ub[i * NP_TS + c];
-                acc0[c] = fma(a, u, acc0[c]);
-                acc1[c] = fma(bq2, u, acc1[c]);
+            for (int c = 0; c < 8; ++c) {
+                const double2 u = ub[i * (NP_PANEL_LD / 2) + c];  // warp-wide broadcast, two columns per load
+                acc0[2 * c] = fma(a, u.x, acc0[2 * c]);
+                acc0[2 * c + 1] = fma(a, u.y, acc0[2 * c + 1]);
+                acc1[2 * c] = fma(bq2, u.x, acc1[2 * c]);
+                acc1[2 * c + 1] = fma(bq2, u.y, acc1[2 * c + 1]);
             }
         }
         if (warp * 16 < ncol) {
