@@ -126,7 +126,7 @@ struct qf_ctx {
     Dev dRotl;
     std::vector<int64_t> hAring;
     // workspace
-    Dev w[12];
+    Dev w[12];  // (w[10]: digit planes of the particular solution)
     Dev dNorm, dFlag, dRetry, io_a, io_b, io_c, io_a2, io_h[2];
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -150,6 +150,11 @@ struct qf_ctx {
     // tensor-core nearest-plane updates: fixed-point digit planes of U per 1024-column block
     bool use_ozaki = false;
     int u_limbs = 7;
+    // centre -> GSO coordinates T = -Mt_P sol_P on tcgen05: fixed-point digit planes of Mt_P (one scale per row)
+    bool mtp_i8 = false;
+    Dev dMtPl, dMtPscale;
+    long ldk_piv = 0;
+    int sol_limbs = 0;
     bool np_fuse64 = true; // the rank-64 updates inside a 256-block run in the tail of the diagonal-block kernel
     int np_dlo = 2;        // digit sums below 256^np_dlo are dropped from the fixed-point updates (error budget: np_block)
     Dev dUl, dUscale, dNz, dMma;
@@ -783,7 +788,27 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         LAUNCH(qf_launch_combine_f64(ca, Sol, ldp, Bc, np, ctx->stream));
     }
     // centre c = -sol in GSO coordinates: T = -(B~^t D^-1)[:,P] sol_P   (gpv.rs:158)
-    LAUNCH(ctx_gemm(ctx, Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0));
+    if (ctx->mtp_i8) {
+        // exact digits of sol (residues < q) times fixed-point digits of Mt_P on the tensor cores; the epilogue stores
+        // T = -V * scale (no read of T)
+        const long ldkp = ctx->ldk_piv, planep = C * ldkp;
+        CK(ctx->w[10].ensure((size_t)ctx->sol_limbs * planep));
+        if (np < ldkp) CK(cudaMemsetAsync(ctx->w[10].p, 0, (size_t)ctx->sol_limbs * planep, ctx->stream));
+        LAUNCH(qf_launch_split_f64_limbs(Sol, ldp, ctx->w[10].as<int8_t>(), planep, ldkp, Bc, np, ctx->sol_limbs,
+                                         ctx->dFlag.as<int>(), nullptr, 0, 0, 0, ctx->stream));
+        I8GemmArgs g{};
+        g.x = ctx->w[10].as<int8_t>(); g.ldx = ldkp; g.x_plane = planep;
+        g.w = ctx->dMtPl.p; g.ldw = ldkp; g.w_plane = D * ldkp;
+        g.LX = ctx->sol_limbs; g.LW = ctx->u_limbs; g.w_signed = 1;
+        g.B = Bc; g.N = (int)D; g.K = np;
+        g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
+        g.flag = ctx->dFlag.as<int>();
+        g.scale = ctx->dMtPscale.as<double>();
+        g.d_lo = ctx->np_dlo; g.overwrite = 1;
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    } else {
+        LAUNCH(ctx_gemm(ctx, Sol, ldp, ctx->dMtP.as<double>(), ldp, T, ldD, Bc, (int)D, np, -1.0, 0.0, 0));
+    }
     // randomized nearest plane, i = D-1 .. 0 (gpv.rs:160), blocked on three levels: 64-wide diagonal
     // blocks are sequential per target (np_diag); everything off the diagonal is a GEMM with K = 64, 256
     // or 1024, so that most of the work runs at K = 1024.
@@ -1743,6 +1768,21 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
                                            ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
                                            ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            // Mt_P as fixed-point digit planes (D rows x npiv columns, one scale per row): T = -Mt_P sol_P on tcgen05
+            ctx->sol_limbs = limbs_for((double)ctx->prm.q);
+            const char* envm = getenv("QF_DISABLE_MTP_I8");  // test switch: fp64 DMMA as before
+            ctx->mtp_i8 = !(envm && envm[0] == '1') && ctx->sol_limbs + ctx->u_limbs - 1 - ctx->np_dlo <= 9;
+            if (ctx->mtp_i8) {
+                ctx->ldk_piv = (ctx->npiv + 127) / 128 * 128;
+                const size_t pb = (size_t)ctx->u_limbs * D * ctx->ldk_piv;
+                CK(ctx->dMtPl.ensure(pb));
+                CK(ctx->dMtPscale.ensure((size_t)D * 8));
+                CK(cudaMemsetAsync(ctx->dMtPl.p, 0, pb, ctx->stream));
+                LAUNCH(qf_launch_fixed_rows_prepare(ctx->dMtP.as<double>(), ctx->ld_piv, (int)D, ctx->npiv, ctx->u_limbs, 1.0,
+                                                    ctx->dMtPscale.as<double>(), ctx->dMtPl.as<int8_t>(), D * ctx->ldk_piv,
+                                                    ctx->ldk_piv, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
         }
     }
     ctx->has_np = true;

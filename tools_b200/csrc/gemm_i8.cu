@@ -57,6 +57,7 @@ struct I8Params {
     // pairs lie below the error budget of the fixed-point update (out_kind 3 only, scale_mul = 256^d_lo)
     int d_lo;
     double scale_mul;
+    int overwrite;  // out_kind 3: out = -V * scale (no read of the old values) instead of out -= V * scale
     int acc_bufs;   // 2: the accumulators are double-buffered in TMEM (tile i+1's MMAs overlap tile i's epilogue)
     // conditional launch: the grid exits at once unless gate_lo <= *gate <= gate_hi (device-side choice between
     // variants of the same contraction compiled for different digit counts, no host round trip)
@@ -105,11 +106,12 @@ __device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const d
 // old values fetched before the accumulators are read.
 template <int NDT, int COLS>
 __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow, const double* __restrict__ scale, int n0,
-                                               int nt, int N, bool rv, int nd, int cbeg, int cend, double mul) {
+                                               int nt, int N, bool rv, int nd, int cbeg, int cend, double mul,
+                                               bool overwrite) {
     for (int c0 = cbeg; c0 < cend; c0 += COLS) {
         double told[COLS];
 #pragma unroll
-        for (int c = 0; c < COLS; ++c) told[c] = (rv && n0 + c0 + c < N) ? orow[n0 + c0 + c] : 0.0;
+        for (int c = 0; c < COLS; ++c) told[c] = (rv && !overwrite && n0 + c0 + c < N) ? orow[n0 + c0 + c] : 0.0;
         int32_t t[NDT][COLS];
 #pragma unroll
         for (int d = 0; d < NDT; ++d)
@@ -132,13 +134,21 @@ __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow,
 
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM and the barriers are set up
 // once; the TMA producer runs ahead into the next tile while the epilogue of the current one drains TMEM.
-template <int OK3>  // OK3 = 1: the scaled fp64 update epilogue (out_kind 3) only; 0: the integer epilogues
+// OK3 = 1: the scaled fp64 update epilogue (out_kind 3) only; 0: the integer epilogues.
+// PAIR: launched as clusters of two CTAs that own the two adjacent coordinate tiles (2p, 2p + 1) of the same 128 targets.
+// The x (target digit) tile is the same for both: each CTA fetches HALF of its rows and TMA-multicasts them into both
+// CTAs' operand rings, so every x block crosses L2 -> SM once per cluster instead of once per CTA (the x planes are the
+// larger operand: 16 KB per digit plane against nt x 128 bytes per w plane).  A stage is free again when BOTH tensor
+// cores have retired it (tcgen05.commit multicast onto both CTAs' empty barriers).  map_xh = map_x with 64-row boxes.
+template <int OK3, bool PAIR>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, I8Params p) {
-    if (p.gate != nullptr) {  // uniform over the grid: either every thread leaves here or none does
+gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_xh, I8Params p) {
+    if (p.gate != nullptr) {  // uniform over the grid (and over a cluster): either every thread leaves here or none does
         const int gv = *p.gate;
         if (gv < p.gate_lo || gv > p.gate_hi) return;
     }
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned operand ring
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -157,14 +167,17 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int ND = p.LX + p.LW - 1 - p.d_lo;   // accumulators per buffer: digit sums d_lo .. LX + LW - 2
     const int NB = p.acc_bufs;                 // accumulator buffers in TMEM (NB * ND * nt <= 512 columns)
     const uint32_t buf_cols = (uint32_t)(ND * p.nt);
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // PAIR: the walk is over tile PAIRS (n_tiles / 2 columns of pairs); this CTA takes coordinate tile 2 * pair + crank
+    const int n_cols = PAIR ? p.n_tiles / 2 : p.n_tiles;
+    const int total_tiles = p.m_tiles * n_cols;
+    const int walk0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, walk_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // tile rasterisation: consecutive tiles walk group_m target tiles for one n tile, then the next n tile
     auto tile_coords = [&](int t, int& tile_m, int& tile_n) {
-        const int per_group = p.group_m * p.n_tiles;
+        const int per_group = p.group_m * n_cols;
         const int g = t / per_group, r = t - g * per_group;
         const int gm = min(p.group_m, p.m_tiles - g * p.group_m);  // last group may be short
         tile_m = g * p.group_m + r % gm;
-        tile_n = r / gm;
+        tile_n = PAIR ? 2 * (r / gm) + (int)crank : r / gm;
     };
     // which x digit planes are non-zero in this (target tile, k block)? (bit j of the returned mask)
     auto plane_mask = [&](int tile_m, int kb) -> uint32_t {
@@ -178,7 +191,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIR ? 2 : 1);  // tcgen05.commit of this CTA (and of its peer)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
@@ -205,18 +218,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is multicast to / arrives at them
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int tile_m, tile_n;
-                tile_coords(tile, tile_m, tile_n);
-                const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const uint32_t mk = plane_mask(tile_m, kb);
+        // The zero-plane masks of 32 consecutive k blocks are fetched by the 32 lanes at once (one L2 round trip per 32
+        // k blocks instead of one per k block in front of every TMA issue) and handed out by shuffle.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = walk0; tile < total_tiles; tile += walk_step) {
+            int tile_m, tile_n;
+            tile_coords(tile, tile_m, tile_n);
+            const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
+            uint32_t mk_cache = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                if ((kb & 31) == 0) mk_cache = (kb + lane < num_kb) ? plane_mask(tile_m, kb + lane) : 0u;
+                const uint32_t mk = __shfl_sync(0xffffffffu, mk_cache, kb & 31);
+                if (lane == 0) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sx = smem + (size_t)stage * stage_bytes;
                     uint8_t* sw = sx + p.LX * x_tile;
@@ -224,12 +242,18 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         mbar_expect_tx(&full_bar[stage], 0);
                     } else {
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(__popc(mk) * x_tile + p.LW * w_tile));
-                        for (int j = 0; j < p.LX; ++j)
-                            if ((mk >> j) & 1u) tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BK, m0, j);
+                        for (int j = 0; j < p.LX; ++j) {
+                            if (!((mk >> j) & 1u)) continue;
+                            if (PAIR)  // rows [64 crank, 64 crank + 64) of the tile, into both CTAs
+                                tma_load_3d_mc(&map_xh, sx + j * x_tile + (int)crank * (x_tile / 2), &full_bar[stage], kb * BK,
+                                               m0 + (int)crank * (TILE_M / 2), j, (uint16_t)3);
+                            else tma_load_3d(&map_x, sx + j * x_tile, &full_bar[stage], kb * BK, m0, j);
+                        }
                         for (int i = 0; i < p.LW; ++i) tma_load_3d(&map_w, sw + i * w_tile, &full_bar[stage], kb * BK, n0, i);
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -244,7 +268,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         unsigned long long units = 0;  // executed (x digit, w digit, k block) products, for the profiler
         long long tw_empty = 0, tw_full = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = walk0; tile < total_tiles; tile += walk_step, ++it) {
             int tile_m, tile_n;
             tile_coords(tile, tile_m, tile_n);
             const int buf = NB == 2 ? (it & 1) : 0, use = NB == 2 ? (it >> 1) : it;
@@ -255,8 +279,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (p.tim) tw_empty += clock64() - t0_;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+            uint32_t mk_cache = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const uint32_t mk = plane_mask(tile_m, kb);
+                if ((kb & 31) == 0) mk_cache = (kb + lane < num_kb) ? plane_mask(tile_m, kb + lane) : 0u;  // as the producer
+                const uint32_t mk = __shfl_sync(0xffffffffu, mk_cache, kb & 31);
                 {
                     const long long t0_ = p.tim ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase);
@@ -280,7 +306,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             units += (unsigned long long)g;
                         }
                     }
-                    mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+                    // frees this smem stage (in both CTAs of a pair) when the MMAs above retire
+                    if (PAIR) mma_commit_mc(&empty_bar[stage], (uint16_t)3);
+                    else mma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) mma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
@@ -299,7 +327,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t lane_addr0 = tmem_base + ((uint32_t)(lg * 32) << 16);
         long long te_wait = 0, te_body = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = walk0; tile < total_tiles; tile += walk_step, ++it) {
             int tile_m, tile_n;
             tile_coords(tile, tile_m, tile_n);
             const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
@@ -314,7 +342,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                 (p.ldout & 1) == 0 && ((((uintptr_t)p.out) & 15) == 0);
             // per warp: 16 columns of a 32-column tile, 32 columns of a 64-column tile
             double2 pre[16];
-            if (OK3 && pre_ok) {
+            if (OK3 && pre_ok && p.overwrite) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pre[i] = make_double2(0.0, 0.0);
+            } else if (OK3 && pre_ok) {
                 const int ncw = p.nt >> 1;
                 const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0 + half * ncw);
 #pragma unroll
@@ -343,9 +374,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             } else if (OK3) {
                 // ragged / wider tiles
                 double* orow = (double*)p.out + (long)row * p.ldout;
-                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
-                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
-                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul);
+                if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
+                else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
+                else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
             } else if (!OK3) {
                 for (int c0 = cbeg; c0 < cend; c0 += 16) {
                     if (ND <= 4) {
@@ -427,7 +458,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
             if (p.tim) te_body += clock64() - te1_;
             // hand TMEM back: re-zero the accumulators for the next tile's accumulate-only MMAs
-            if (tile + NB * (int)gridDim.x < total_tiles) {  // this buffer is used again
+            if (tile + NB * walk_step < total_tiles) {  // this buffer is used again
                 // (each warp zeroes exactly the columns it has just read: the other warp of the lane group may still be
                 // reading its own)
                 for (int d = 0; d < ND; ++d)
@@ -446,6 +477,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+    // no CTA of a pair may exit while the peer can still multicast into its shared memory or arrive on its barriers
+    if (PAIR) cluster_sync_all();
 }
 
 // Ceiling of the int8 tensor pipe itself: every CTA loads ONE 128 x 128-byte x tile and ONE 256 x 128-byte w tile and then
@@ -537,6 +570,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     }
     I8Params p{};
     p.d_lo = a.d_lo;
+    p.overwrite = a.overwrite;
     p.scale_mul = 1.0;
     for (int i = 0; i < a.d_lo; ++i) p.scale_mul *= 256.0;
     p.acc_bufs = (2 * ND * nt <= 512) ? 2 : 1;
@@ -573,13 +607,16 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (stages > 8) stages = 8;
     p.stages = stages;
     const int smem = stages * stage_bytes + 1024 + 256;
-    CUtensorMap mx, mw;
+    CUtensorMap mx, mw, mxh;
     if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M, bk)) return cudaErrorInvalidValue;
     if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt, bk)) return cudaErrorInvalidValue;
+    if (!make_map(&mxh, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M / 2, bk)) return cudaErrorInvalidValue;
     static int configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -592,9 +629,32 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
     const int total_tiles = p.m_tiles * p.n_tiles;
+    // CTA pairs (x tile multicast) when the coordinate tiles pair up and there is enough work for every pair;
+    // QF_I8_PAIR=0 keeps single CTAs (experiments / tests)
+    static const bool pair_off = getenv("QF_I8_PAIR") && getenv("QF_I8_PAIR")[0] == '0';
+    const bool pair = !pair_off && (p.n_tiles % 2 == 0) && total_tiles >= 2 && bk == BLOCK_K;
+    if (pair) {
+        // group_m was chosen for single tiles; pairs halve the number of w-tile columns a wave touches: keep it
+        const int pairs = total_tiles / 2;
+        int ctas = 2 * (pairs < sm_count / 2 ? pairs : sm_count / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)ctas);
+        cfg.blockDim = dim3(I8_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (a.out_kind == 3) return cudaLaunchKernelEx(&cfg, gemm_i8_kernel<1, true>, mx, mw, mxh, p);
+        return cudaLaunchKernelEx(&cfg, gemm_i8_kernel<0, true>, mx, mw, mxh, p);
+    }
     dim3 grid((unsigned)(total_tiles < sm_count ? total_tiles : sm_count));  // persistent: one CTA per SM
-    if (a.out_kind == 3) gemm_i8_kernel<1><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
-    else gemm_i8_kernel<0><<<grid, I8_THREADS, smem, stream>>>(mx, mw, p);
+    if (a.out_kind == 3) gemm_i8_kernel<1, false><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
+    else gemm_i8_kernel<0, false><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
     return cudaGetLastError();
 }
 

@@ -178,6 +178,7 @@ struct I8GemmArgs {
     unsigned long long* tim;  // optional: 4 phase cycle counters (diagnostics)
     // out_kind 3 only: digit sums D_d with d < d_lo are not computed (their pairs lie below the error budget)
     int d_lo;
+    int overwrite;  // out_kind 3 only: out = -V * scale[n] (store) instead of out -= V * scale[n]
     // optional conditional launch: the grid runs only if gate_lo <= *gate <= gate_hi (device int)
     const int* gate;
     int gate_lo, gate_hi;

@@ -37,6 +37,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem, 
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// The same load delivered to the same shared-memory offset of every CTA in `mask` (cluster multicast); each destination's
+// mbarrier (same offset) receives the complete_tx for the bytes that land in it.
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
 // K-major swizzled operand tile: rows of bk bytes (bk = 128: SWIZZLE_128B, 8-row atoms of 1024 bytes;
 // bk = 64: SWIZZLE_64B, 8-row atoms of 512 bytes)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int bk = BLOCK_K) {
