@@ -155,6 +155,7 @@ struct qf_ctx {
     Dev dMtPl, dMtPscale;
     long ldk_piv = 0;
     int sol_limbs = 0;
+    bool np_fuse_split = true;  // the diagonal-block kernel writes the digit planes of z itself (no split pass over Z)
     bool np_fuse64 = true; // the rank-64 updates inside a 256-block run in the tail of the diagonal-block kernel
     int np_dlo = 2;        // digit sums below 256^np_dlo are dropped from the fixed-point updates (error budget: np_block)
     Dev dUl, dUscale, dNz, dMma;
@@ -680,17 +681,33 @@ static inline int np_block_index(long col, long D, long S) {
 // updates of every coordinate >= hi.  level 0 = one sequential diagonal block.  prop0 = first coordinate of the
 // enclosing 1024-level block (origin of the pre-generated proposals).
 qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, int level, long prop0, uint64_t seed,
-                   uint64_t first, long up_lo = -1) {
+                   uint64_t first) {
     const long D = ctx->dim, ldD = ctx->ld_dim;
     const double* U = ctx->dU.as<double>();
     if (level == 0) {
-        // up_lo >= 0: the diagonal-block kernel also applies this block's update to the columns [up_lo, lo) of the
-        // enclosing 256-block (fused: no K = 64 GEMM launch, no extra pass over Z)
+        // [lo, hi) wider than 64: a whole 256-block, the kernel walks its diagonal blocks and fuses the rank-64 updates
+        NpDigitOut dig{};
+        const bool fuse_digits = ctx->use_ozaki && ctx->np_fuse_split;
+        if (fuse_digits && (lo & 63)) return ctx->fail(QF_ERR_NUMERIC, "internal: diagonal block not 64-aligned");
+        if (fuse_digits) {  // the digit planes of this block of z, written by the kernel that produced it
+            const long ldk = ctx->ldk_dim;
+            int* gates = ctx->dGate.as<int>();
+            dig.planes = ctx->w[8].as<int8_t>(); dig.plane_stride = (long)ctx->chunk * ldk; dig.ldk = ldk; dig.L = ctx->z_limbs;
+            dig.nz = ctx->dNz.as<uint8_t>(); dig.nz_m_tiles = (int)((ctx->chunk + 127) / 128); dig.nz_kb_total = (int)(ldk / 128);
+            dig.gate[0] = gates + np_block_index(lo, D, NP_SIZES[1]);
+            dig.gate[1] = gates + ctx->gate_n256 + np_block_index(lo, D, NP_SIZES[2]);
+            dig.gate[2] = gates + ctx->gate_n256 + ctx->gate_n1024 + np_block_index(lo, D, NP_SIZES[3]);
+            dig.gate[3] = (ctx->gpv_struct && hi > ctx->nk) ? gates + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096 : nullptr;
+        }
         LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
-                                 ctx->w[9].as<float4>() + (lo - prop0) * ctx->chunk, ctx->chunk, Bc, (int)lo, (int)(hi - lo), (int)D,
-                                 seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream, (int)up_lo));
+                                 ctx->w[9].as<float4>(), ctx->chunk, Bc, (int)lo, (int)(hi - lo), (int)D,
+                                 seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream, (int)lo, fuse_digits ? &dig : nullptr,
+                                 (int)prop0));
         return QF_OK;
     }
+    if (level == 1 && ctx->np_fuse64 && (lo & 63) == 0)
+        // a whole 256-block in one launch: its diagonal blocks and the rank-64 updates between them (lattice.cu)
+        return np_block(ctx, T, Z, Bc, lo, hi, 0, prop0, seed, first);
     const long step = NP_SIZES[level - 1];
     const bool i8_level = level >= 2 && ctx->use_ozaki;
     for (long sub_hi = hi; sub_hi > lo;) {
@@ -706,12 +723,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                                         seed, first, ctx->stream));
             prop0 = sub_lo;
         }
-        const bool fused_update = level == 1 && ctx->np_fuse64 && (sub_lo - lo) % 16 == 0;
-        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, prop0, seed, first, fused_update ? lo : -1));
-        if (fused_update) {
-            sub_hi = sub_lo;
-            continue;
-        }
+        QF_TRY(np_block(ctx, T, Z, Bc, sub_lo, sub_hi, level - 1, prop0, seed, first));
         if (i8_level) {
             const long ldk = ctx->ldk_dim, plane = (long)ctx->chunk * ldk;
             const int nz_m = (int)((ctx->chunk + 127) / 128), nz_kb = (int)(ldk / 128);
@@ -721,7 +733,9 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             int* gate1 = gates + ctx->gate_n256 + np_block_index(sub_lo, D, NP_SIZES[2]);
             int* gate4 = gates + ctx->gate_n256 + ctx->gate_n1024 + np_block_index(sub_lo, D, NP_SIZES[3]);
             int* gate_z2 = gates + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096;
-            if (level == 2)  // digits of the finished 256-block of z (kept: the levels above and the final S z reuse them)
+            // digits of the finished 256-block of z (kept: the levels above and the final S z reuse them) -- unless the
+            // diagonal-block kernels have written them already
+            if (level == 2 && !ctx->np_fuse_split)
                 LAUNCH(qf_launch_split_f64_limbs(Z + sub_lo, ldD, zp + sub_lo, plane, ldk, Bc, (int)(sub_hi - sub_lo), ctx->z_limbs,
                                                  ctx->dFlag.as<int>(), ctx->dNz.as<uint8_t>(), nz_m, nz_kb, (int)sub_lo,
                                                  ctx->stream, gate0, gate1, gate4,
@@ -1332,6 +1346,8 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
         ctx->fused_fa = !(envf && envf[0] == '1');
         const char* envu = getenv("QF_DISABLE_NP_FUSE64");  // test switch: separate K = 64 GEMM launches as before
         ctx->np_fuse64 = !(envu && envu[0] == '1');
+        const char* envs = getenv("QF_DISABLE_NP_FUSE_SPLIT");  // test switch: separate digit-split launches
+        ctx->np_fuse_split = !(envs && envs[0] == '1');
         const char* envd = getenv("QF_NP_DLO");  // test switch: 0 = every digit pair of the fixed-point updates
         if (envd) ctx->np_dlo = std::max(0, std::min(3, atoi(envd)));
     }

@@ -206,3 +206,12 @@ __device__ __forceinline__ uint64_t mod_i64_barrett(long long v, uint64_t q, uin
 static inline uint64_t qf_barrett_magic(uint64_t q) { return q ? (uint64_t)((((unsigned __int128)1) << 64) / q) : 0; }
 
 static inline int qf_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Launcher-side caches (largest dynamic shared memory configured for a kernel, SM count) are kept PER DEVICE: function
+// attributes belong to the device context the launch runs in.
+#define QF_MAX_DEVICES 64
+static inline int qf_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= QF_MAX_DEVICES) dev = 0;
+    return dev;
+}

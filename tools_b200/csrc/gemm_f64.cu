@@ -157,7 +157,8 @@ cudaError_t qf_launch_gemm_f64(const double* X, long ldx, const double* W, long 
     if (B <= 0 || N <= 0) return cudaSuccess;
     // cp.async needs 16-byte aligned rows: even leading dimensions, aligned bases
     if ((ldx & 1) || (ldw & 1) || (((uintptr_t)X) & 15) || (((uintptr_t)W) & 15)) return cudaErrorMisalignedAddress;
-    static bool configured = false;
+    static bool configured_dev[QF_MAX_DEVICES] = {};
+    bool& configured = configured_dev[qf_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         if (e != cudaSuccess) return e;

@@ -564,7 +564,9 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (a.out_kind == 3 && (force_nt == 32 || force_nt == 64) && nt >= force_nt) nt = force_nt;
     }
     {   // two pipeline stages of LX x-planes + LW w-planes must fit in shared memory
-        const int bk0 = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
+        // test-only switch, read once per process: 64-byte K blocks (SWIZZLE_64B)
+        static const int bk_env = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
+        const int bk0 = bk_env;
         const int budget0 = 227 * 1024 - 1024 - 256;
         while (nt > 16 && 2 * (a.LX * TILE_M * bk0 + a.LW * nt * bk0) > budget0) nt = (a.out_kind == 3 && nt == 64) ? 32 : nt - 16;
     }
@@ -595,11 +597,8 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     // depth in the same shared memory, but measured 30 % slower on B200 (round-1 profile notes) -- the kernel is bound by
     // L2 -> shared-memory operand traffic, not by pipeline depth, and the 64-byte layout feeds the tensor core worse.
     const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;  // barriers + tmem slot + inited mask
-    int bk = BLOCK_K;
-    {
-        const char* env = getenv("QF_I8_BLOCK_K");
-        if (env && atoi(env) == 64) bk = 64;
-    }
+    static const int bk_env2 = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
+    const int bk = bk_env2;
     p.bk = bk;
     const int stage_bytes = a.LX * TILE_M * bk + a.LW * nt * bk;
     int stages = budget / stage_bytes;
@@ -611,7 +610,9 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M, bk)) return cudaErrorInvalidValue;
     if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt, bk)) return cudaErrorInvalidValue;
     if (!make_map(&mxh, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M / 2, bk)) return cudaErrorInvalidValue;
-    static int configured = 0;
+    const int dslot = qf_device_slot();
+    static int configured_dev[QF_MAX_DEVICES] = {};
+    int& configured = configured_dev[dslot];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -622,11 +623,10 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     }
     p.mma_units = a.mma_units;
     p.tim = a.tim;
-    static int sm_count = 0;
+    static int sm_count_dev[QF_MAX_DEVICES] = {};
+    int& sm_count = sm_count_dev[dslot];
     if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dslot) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
     const int total_tiles = p.m_tiles * p.n_tiles;
     // CTA pairs (x tile multicast) when the coordinate tiles pair up and there is enough work for every pair;

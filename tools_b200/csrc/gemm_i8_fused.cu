@@ -451,10 +451,11 @@ static cudaError_t launch_one(const FaFusedArgs& a, int LX, bool check, const in
     CUtensorMap mw;
     if (!tc05::make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt)) return cudaErrorInvalidValue;
     // CTA pairs (clusters of 2 along the coordinate tiles) whenever the tiles pair up; QF_FA_PAIR=0 keeps single CTAs
-    const char* pair_env = getenv("QF_FA_PAIR");
-    const bool pair = !(pair_env && pair_env[0] == '0') && (p.n_tiles % 2 == 0);
+    static const bool pair_off = getenv("QF_FA_PAIR") && getenv("QF_FA_PAIR")[0] == '0';  // test-only switch, read once
+    const bool pair = !pair_off && (p.n_tiles % 2 == 0);
     void (*kern)(const CUtensorMap, FusedParams) = pair ? pick_kernel<true>(LX, check) : pick_kernel<false>(LX, check);
-    static int configured[2][2][MAX_LX + 1] = {};
+    static int configured_dev[QF_MAX_DEVICES][2][2][MAX_LX + 1] = {};
+    auto& configured = configured_dev[qf_device_slot()];
     if (smem > configured[pair ? 1 : 0][check ? 1 : 0][LX]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -88,11 +88,21 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
 // writes Z[b][i].  dg: per-coordinate sampler parameters (length >= j0+nb).
 // *flag is set when |z| >= zlimit (exact-integer range check).
 // prop: this block's pre-generated proposals (np_propose), coordinate-major: prop[(i - j0) * ldprop + b]
-// up_lo (optional, -1 = none): the kernel also applies the block's update to the columns [up_lo, j0) of its own targets,
-//   T[b][j] -= sum_i Z[b][j0 + i] U[j][j0 + i]   (the rank-nb update inside the enclosing 256-block)
+// dig (optional): the kernel also writes the balanced base-256 digit planes of its block of z (L planes of B x ldk bytes,
+// planes already offset to column 0), marks the zero-tile map and raises the digit-count gates, like qf_launch_split_f64_limbs
+struct NpDigitOut {
+    int8_t* planes; long plane_stride, ldk; int L;
+    uint8_t* nz; int nz_m_tiles, nz_kb_total;
+    int* gate[4];
+};
+// nb <= 64: one diagonal block [j0, j0 + nb).  nb > 64 (j0 a multiple of 64, up_lo = j0): the whole block range, its
+// 64-wide diagonal blocks from the top down, each followed by the rank-64 update of the columns of the range below it,
+//   T[b][j] -= sum_i Z[b][j0' + i] U[j][j0' + i]   for this CTA's own targets (no cross-CTA dependence: one launch).
+// prop: proposals of coordinate prop0 onwards (prop0 = -1: j0)
 cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
-                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo = -1);
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo = -1,
+                              const NpDigitOut* dig = nullptr, int prop0 = -1);
 // two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[(i - j_lo) * ldo + b]
 cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
                                  uint64_t first_target, cudaStream_t stream);

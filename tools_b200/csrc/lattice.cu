@@ -119,15 +119,23 @@ constexpr int NP_UST_DOUBLES = NP_NB_MAX * NP_PANEL_LD;  // mu block (64 x 65), 
 __global__ void __launch_bounds__(NP_TPB, 2)
 np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
-               int j0, int nb, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag, int up_lo) {
+               int j_lo, int j_hi, int prop0, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag,
+               int fuse_update, NpDigitOut dig) {
     extern __shared__ __align__(16) double np_sm[];
-    const int us_ld = nb + 1;                             // padded: the transposing store is (almost) conflict-free
     double* ust = np_sm;                                  // ust[c * us_ld + r] = U[j0+r][j0+c], c > r
     double* ts = ust + NP_UST_DOUBLES;                    // ts[t * NP_TS + i]  (16-byte aligned)
     DGaussParams* dgs = reinterpret_cast<DGaussParams*>(ts + ((NP_TARGETS * NP_TS + 1) & ~1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbe = min(nb, dim - j0);
     const long b0 = (long)blockIdx.x * NP_TARGETS;
+    const float4* const prop_base = prop;
+    // The diagonal blocks of [j_lo, j_hi) from the top down: with the fused rank-64 update every block only touches this
+    // CTA's own targets, so the whole 256-block is ONE launch (the CTAs never wait for each other between blocks).
+    for (int sub_hi = j_hi; sub_hi > j_lo;) {
+    const int j0 = max(j_lo, (sub_hi - 1) / NP_NB_MAX * NP_NB_MAX), nb = sub_hi - j0;
+    const int up_lo = fuse_update ? j_lo : j0;
+    const int us_ld = nb + 1;                             // padded: the transposing store is (almost) conflict-free
+    const int nbe = min(nb, dim - j0);
+    prop = prop_base + (long)(j0 - prop0) * ldprop;       // row of coordinate j0 in the coordinate-major proposal buffer
 #pragma unroll 8
     for (int i = tid; i < nb * nb; i += NP_TPB) {
         const int r = i / nb, c = i - r * nb;  // coalesced read along c
@@ -242,6 +250,45 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
         if (bb < B)
             for (int c = lane; c < nbe; c += 32) Z[bb * ldz + j0 + c] = ts[r * NP_TS + c];
     }
+    // phase 2b (optional): balanced base-256 digit planes of this block of z for the tensor-core updates that consume it
+    // (same planes, zero-tile map and digit-count gates as split_f64_limbs_kernel, without a second pass over Z):
+    // a warp per target row, two columns per lane.
+    if (dig.planes != nullptr) {
+        int top = -1;
+        for (int r = warp; r < NP_TARGETS; r += NP_TPB / 32) {
+            const long bb = b0 + r;
+            long long v0 = 0, v1 = 0;
+            if (bb < B) {
+                if (2 * lane < nbe) v0 = __double2ll_rn(ts[r * NP_TS + 2 * lane]);
+                if (2 * lane + 1 < nbe) v1 = __double2ll_rn(ts[r * NP_TS + 2 * lane + 1]);
+            }
+            for (int l = 0; l < dig.L; ++l) {
+                long long d0 = ((v0 + 128) & 255) - 128, d1 = ((v1 + 128) & 255) - 128;
+                if (l == dig.L - 1) { d0 = v0; d1 = v1; }  // |z| < zlimit <= capacity of L digits (checked in phase 2)
+                v0 = (v0 - d0) >> 8;
+                v1 = (v1 - d1) >> 8;
+                int8_t* dst = dig.planes + (long)l * dig.plane_stride + bb * dig.ldk + j0 + 2 * lane;
+                if (bb < B) {
+                    if (2 * lane + 1 < nbe) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)((d0 & 255) | ((d1 & 255) << 8));
+                    else if (2 * lane < nbe) dst[0] = (int8_t)d0;
+                }
+                if (__any_sync(0xffffffffu, (d0 | d1) != 0)) top = max(top, l);
+            }
+        }
+        // zero-tile map: this CTA's 64 targets lie in one 128-target tile, its columns in one 128-column block
+        if (lane == 0 && top >= 0) {
+            for (int l = 0; l <= top; ++l) {
+                // (planes below the top one may still be all zero in this warp's rows; marking them non-zero only costs
+                // an MMA that multiplies zeros -- but the exact map is cheap: recompute per plane is not worth it)
+                dig.nz[((long)l * dig.nz_m_tiles + (b0 >> 7)) * dig.nz_kb_total + (j0 >> 7)] = 1;
+            }
+            if (top > 0) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (dig.gate[g] && *(volatile int*)dig.gate[g] < top) atomicMax(dig.gate[g], top);
+            }
+        }
+    }
     // phase 3: the rank-nb update of the columns [up_lo, j0) that remain in the enclosing 256-block, for this CTA's own
     // targets:  T[b][j] -= sum_i z_i U[j][j0 + i].  The z tile is still in shared memory; the panel of U goes through
     // the (now free) mu buffer 64 columns at a time.  Lanes are targets (lane, lane + 32), warps are 16-column groups:
@@ -290,6 +337,9 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
             }
         }
     }
+    __syncthreads();  // the next block re-uses the mu buffer and the centre tile, and reads T columns updated above
+    sub_hi = j0;
+    }
 }
 
 }  // namespace
@@ -300,7 +350,8 @@ cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long 
     if (B <= 0) return cudaSuccess;
     if (k > KMAX) return cudaErrorInvalidValue;
     size_t smem = (size_t)(2 * k * k + k) * sizeof(double) + (size_t)k * sizeof(DGaussParams);
-    static size_t configured = 0;
+    static size_t configured_dev[QF_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[qf_device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gadget_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -326,22 +377,39 @@ cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int wid
 
 cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
-                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo) {
+                              uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo,
+                              const NpDigitOut* dig, int prop0) {
     if (B <= 0) return cudaSuccess;
-    if (nb > NP_NB_MAX || nb < 1) return cudaErrorInvalidValue;
+    // nb <= 64: one diagonal block; nb > 64 (whole 256-block, up_lo == j0 required): its diagonal blocks from the top
+    // down with the rank-64 updates fused
+    const bool multi = nb > NP_NB_MAX;
+    if (nb < 1 || (multi && (up_lo != j0 || (j0 % NP_NB_MAX) != 0))) return cudaErrorInvalidValue;
+    if (prop0 < 0) prop0 = j0;
     int grid = (B + NP_TARGETS - 1) / NP_TARGETS;
     if (up_lo < 0 || up_lo > j0) up_lo = j0;  // no fused update
     // the fused update needs 16-byte aligned rows and whole 16-column groups
-    if (up_lo < j0 && ((ldt & 1) || ((j0 - up_lo) & 15) || (up_lo & 1) || (((uintptr_t)T) & 15))) return cudaErrorInvalidValue;
+    if ((up_lo < j0 || multi) && ((ldt & 1) || ((j0 - up_lo) & 15) || (up_lo & 1) || (((uintptr_t)T) & 15))) return cudaErrorInvalidValue;
+    // single block with an update range below it: launched as the range [up_lo .. j0 + nb) restricted to its top block
+    // is not expressible -- the kernel walks [j_lo, j_hi) completely; a single block with up_lo < j0 therefore runs as
+    // j_lo = j0 with the update range passed through fuse_update = 0 ... (not needed any more: the host fuses whole
+    // 256-blocks or nothing)
+    if (!multi && up_lo < j0) return cudaErrorInvalidValue;
     size_t smem = (size_t)(NP_UST_DOUBLES + ((NP_TARGETS * NP_TS + 1) & ~1)) * sizeof(double) +
                   (size_t)NP_NB_MAX * sizeof(DGaussParams);
-    static size_t configured = 0;
+    static size_t configured_dev[QF_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[qf_device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(np_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0, nb, dim, seed,
-                                                   first_target, zlimit, flag, up_lo);
+    NpDigitOut d{};
+    if (dig) {
+        d = *dig;
+        // two-byte stores / one map cell per CTA: even column offsets, 64-aligned blocks inside one 128-column cell
+        if ((j0 & 63) || (d.ldk & 1) || (((uintptr_t)d.planes) & 1) || (d.plane_stride & 1)) return cudaErrorInvalidValue;
+    }
+    np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0, j0 + nb, prop0, dim, seed,
+                                                   first_target, zlimit, flag, multi ? 1 : 0, d);
     return cudaGetLastError();
 }

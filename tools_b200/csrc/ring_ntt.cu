@@ -257,7 +257,8 @@ cudaError_t qf_launch_ring_f_a(const int32_t* sigma, const uint64_t* a_hat, int6
     if (pp > 8) pp = 8;
     dim3 block(nh, pp);
     size_t smem = (size_t)2 * pp * n * 8;
-    static size_t configured = 0;
+    static size_t configured_dev[QF_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[qf_device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(ring_f_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
