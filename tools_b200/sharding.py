@@ -47,6 +47,8 @@ def gather_domain_i16(torch, dist, lib, ffi, e, u, rank, world, dev, stream, max
     with torch.cuda.stream(stream):
         e16 = torch.empty(e.shape, dtype=torch.int16, device=dev)
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        # untimed warm-up of the collective (NCCL sets up its NVLink channels lazily, on the first call of a kind)
+        gather_shards(dist, e16[: min(b, 128)].contiguous(), rank, world, dst)
         stream.synchronize()
         dist.barrier()
         ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
