@@ -560,11 +560,10 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (a.out_kind == 3 && nt > 64 && nt < 128) nt = 64;
     if (a.out_kind == 3 && nt > 32 && nt < 64) nt = 32;
     {
-        // Short contractions (a few k blocks per tile) are dominated by the read-modify-write epilogue, which is serial
-        // with the MMAs when TMEM holds one 64-column tile: 32-column tiles leave room for two accumulator sets, so tile
-        // i+1's MMAs overlap tile i's epilogue.  Long contractions amortise the epilogue and prefer the wider tile (less
-        // operand traffic per MAC).  QF_I8_NT32_MAX_KB / QF_I8_UPDATE_NT: experiment switches.
-        static const int nt32_max_kb = getenv("QF_I8_NT32_MAX_KB") ? atoi(getenv("QF_I8_NT32_MAX_KB")) : 4;
+        // Experiment switches (profiles/README_r2.md): 32-column tiles leave room for two accumulator sets in TMEM (tile
+        // i+1's MMAs overlap tile i's read-modify-write epilogue) -- measured SLOWER than one 64-column set for every
+        // contraction length of the C2 step (305 k/s against 311 k/s), so the wide tile is the default.
+        static const int nt32_max_kb = getenv("QF_I8_NT32_MAX_KB") ? atoi(getenv("QF_I8_NT32_MAX_KB")) : 0;
         static const int force_nt = getenv("QF_I8_UPDATE_NT") ? atoi(getenv("QF_I8_UPDATE_NT")) : 0;
         if (a.out_kind == 3 && nt == 64 && (a.K + BLOCK_K - 1) / BLOCK_K <= nt32_max_kb && 2 * ND * 32 <= 512) nt = 32;
         if (a.out_kind == 3 && (force_nt == 32 || force_nt == 64) && nt >= force_nt) nt = force_nt;
