@@ -97,8 +97,9 @@ __device__ __forceinline__ void epi_update16(uint32_t lane_addr, int cb, const d
             const double old = (c & 1) ? pre[(c0 + c) >> 1].y : pre[(c0 + c) >> 1].x;
             r[c] = fma(-dv, scale[cb + c0 + c] * mul, old);
         }
-        *reinterpret_cast<double2*>(orow + cb + c0) = make_double2(r[0], r[1]);
-        *reinterpret_cast<double2*>(orow + cb + c0 + 2) = make_double2(r[2], r[3]);
+        // streaming stores / loads for T: every value is touched once per launch; evict-first keeps the digit planes in L2
+        __stcs(reinterpret_cast<double2*>(orow + cb + c0), make_double2(r[0], r[1]));
+        __stcs(reinterpret_cast<double2*>(orow + cb + c0 + 2), make_double2(r[2], r[3]));
     }
 }
 
@@ -349,10 +350,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int ncw = p.nt >> 1;
                 const double2* src = reinterpret_cast<const double2*>((const double*)p.out + (long)row * p.ldout + n0 + half * ncw);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) pre[i] = src[i];
+                for (int i = 0; i < 8; ++i) pre[i] = __ldcs(src + i);
                 if (p.nt == 64) {
 #pragma unroll
-                    for (int i = 8; i < 16; ++i) pre[i] = src[i];
+                    for (int i = 8; i < 16; ++i) pre[i] = __ldcs(src + i);
                 }
             }
             const long long te0_ = p.tim ? clock64() : 0;
