@@ -963,13 +963,21 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
     s = float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))
     rng = np.random.default_rng(12)
     u = rng.integers(0, q, (2027, n), dtype=np.int64)  # ragged: the last 128-target tile and its last warp are partial
-    outs = []
+    outs = {}
     key = None
-    for mode in ("ozaki", "fp64"):
-        if mode == "ozaki":
-            monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
-            monkeypatch.delenv("QF_DISABLE_OZAKI", raising=False)
-        else:
+    # "two_phase": the default for a G-trapdoor basis at tensor-core dimensions (samp_p_np2_chunk; nk % 128 == 0);
+    # "two_phase_wide": the same with every fixed-point matrix at full width and no dropped digit sums;
+    # "ozaki": the one-pass recursion with tensor-core updates; "fp64": the one-pass recursion on DMMA
+    for mode in ("two_phase", "two_phase_wide", "ozaki", "fp64"):
+        monkeypatch.delenv("QF_DISABLE_OZAKI", raising=False)
+        monkeypatch.delenv("QF_DISABLE_TWO_PHASE", raising=False)
+        monkeypatch.delenv("QF_NP2_CFG", raising=False)
+        monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
+        if mode == "two_phase_wide":
+            monkeypatch.setenv("QF_NP2_CFG", "7,0,7,0,7,0")
+        elif mode == "ozaki":
+            monkeypatch.setenv("QF_DISABLE_TWO_PHASE", "1")
+        elif mode == "fp64":
             monkeypatch.setenv("QF_DISABLE_OZAKI", "1")
         psf = T.PSFGPV(gp, s)
         if key is None:
@@ -977,13 +985,19 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
         a, td = key
         psf._a_id = None
         e = psf.samp_p_batch(a, td, u, seed=77)
-        assert np.array_equal(O.f_a_classical_batch(a, e, q), u)
-        assert psf.check_domain_batch(e).all()
+        assert np.array_equal(O.f_a_classical_batch(a, e, q), u), mode
+        assert psf.check_domain_batch(e).all(), mode
         ratio = (e.astype(np.float64) ** 2).sum(1).mean() / (gp.m * s * s / (2 * math.pi))
-        assert abs(ratio - 1) < 0.02, ratio
-        outs.append(e)
-    same = (outs[0] == outs[1]).all(axis=1).mean()
+        assert abs(ratio - 1) < 0.02, (mode, ratio)
+        outs[mode] = e
+    same = (outs["ozaki"] == outs["fp64"]).all(axis=1).mean()
     assert same > 0.9, same
+    if (n * gp.k) % 128 == 0:  # the two-phase path ran: its digit budget changes (almost) no preimage
+        assert not np.array_equal(outs["two_phase"], outs["ozaki"])
+        same2 = (outs["two_phase"] == outs["two_phase_wide"]).all(axis=1).mean()
+        assert same2 > 0.9, same2
+    else:
+        assert np.array_equal(outs["two_phase"], outs["ozaki"])
 
 
 def test_full_size_c2_properties(T):

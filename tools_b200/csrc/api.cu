@@ -164,6 +164,15 @@ struct qf_ctx {
     // contraction launches
     Dev dGate;
     int gate_n256 = 0, gate_n1024 = 0, gate_n4096 = 0;
+    // Two-phase nearest plane for the G-trapdoor basis (samp_p_np2_chunk): the key is A = [A_bar | G - A_bar R] with the R
+    // recovered from S (verified when the trapdoor is installed).  Fixed-point digit planes of Mt_1 = rows [0, nk) of
+    // D^-1 B~^t with the columns permuted to [gadget block | top block], one scale per row; digit counts / windows of the
+    // three contractions (U_22 updates, the centre map, U_11 updates).
+    bool gadget_key_ok = false, two_phase = false;
+    Dev dMt1l, dMt1scale, dNz2;
+    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1;
+    // digits / window / smallest compiled digit count of z for the update launches of the phase that is running
+    int np_wdrop_cur = 0, np_dlo_cur = 2, np_lx_min = 3;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -655,17 +664,17 @@ static long np_last_block_start(long D, long S) {
 // conditional on the device-side gate (highest non-zero digit plane of the z block it consumes), so exactly one of them
 // runs -- the one compiled for the digits that are really there (fewer accumulators in TMEM = wider tiles, less operand
 // traffic per MAC).  Without a gate a single launch with all z_limbs digits.
-qf_status gemm_i8_gated(qf_ctx* ctx, I8GemmArgs g, const int* gate) {
+qf_status gemm_i8_gated(qf_ctx* ctx, I8GemmArgs g, const int* gate, int lx_min = 3) {
     const int Lmax = g.LX;
-    if (!gate || Lmax <= 3) {
+    if (!gate || Lmax <= lx_min) {
         LAUNCH(ctx_gemm_i8(ctx, g));
         return QF_OK;
     }
-    for (int lx = 3; lx <= Lmax; ++lx) {
+    for (int lx = lx_min; lx <= Lmax; ++lx) {
         I8GemmArgs v = g;
         v.LX = lx;
         v.gate = gate;
-        v.gate_lo = lx == 3 ? 0 : lx - 1;
+        v.gate_lo = lx == lx_min ? 0 : lx - 1;
         v.gate_hi = lx == Lmax ? 1 << 20 : lx - 1;
         LAUNCH(ctx_gemm_i8(ctx, v, lx == Lmax));
     }
@@ -749,8 +758,11 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
             } else if (sub_lo > lo) {
                 I8GemmArgs g{};
                 g.x = zp + sub_lo; g.ldx = ldk; g.x_plane = plane;
-                g.w = ctx->dUl.as<int8_t>() + lo * ldk + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;
-                g.LX = ctx->z_limbs; g.LW = ctx->u_limbs; g.w_signed = 1;
+                // (two-phase recursion: only the top planes of U that the phase's error budget needs)
+                const int wdrop = ctx->np_wdrop_cur;
+                g.w = ctx->dUl.as<int8_t>() + (size_t)wdrop * D * ldk + lo * ldk + sub_lo; g.ldw = ldk; g.w_plane = D * ldk;
+                g.LX = ctx->z_limbs; g.LW = ctx->u_limbs - wdrop; g.w_signed = 1;
+                g.scale_mul = std::ldexp(1.0, 8 * wdrop);
                 g.B = Bc; g.N = (int)(sub_lo - lo); g.K = (int)(sub_hi - sub_lo);
                 g.out_kind = 3; g.sign = 1; g.q = 0; g.base = nullptr; g.ldbase = 0; g.out = T + lo; g.ldout = ldD;
                 g.flag = ctx->dFlag.as<int>();
@@ -761,8 +773,8 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
                 // row maximum of |U| / (127 256^6)), i.e. < 2^-27 |U|max K^(1/2) typically at d_lo = 2 -- four orders
                 // below the 2^-12 the centres need (the widths s / ||b~_i|| are >= 2.3), and below the fp64 rounding of T
                 // at |T| ~ 2^24.
-                g.d_lo = ctx->np_dlo;
-                QF_TRY(gemm_i8_gated(ctx, g, level == 2 ? gate0 : level == 3 ? gate1 : gate4));
+                g.d_lo = ctx->np_dlo_cur;
+                QF_TRY(gemm_i8_gated(ctx, g, level == 2 ? gate0 : level == 3 ? gate1 : gate4, ctx->np_lx_min));
             }
         } else if (sub_lo > lo) {
             LAUNCH(ctx_gemm(ctx, Z + sub_lo, ldD, U + lo * ldD + sub_lo, ldD, T + lo, ldD, Bc, (int)(sub_lo - lo),
@@ -773,7 +785,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
     return QF_OK;
 }
 
-qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
+qf_status samp_p_np1_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
     const long D = ctx->dim, ldD = ctx->ld_dim, ldp = ctx->ld_piv, C = ctx->chunk;
     const int np = ctx->npiv;
     CK(ctx->w[0].ensure((size_t)C * ldp * 8));  // u as fp64
@@ -839,6 +851,7 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         CK(ctx->dGate.ensure(gb));
         CK(cudaMemsetAsync(ctx->dGate.p, 0, gb, ctx->stream));
     }
+    ctx->np_wdrop_cur = 0; ctx->np_dlo_cur = ctx->np_dlo; ctx->np_lx_min = 3;
     QF_TRY(np_block(ctx, T, Z, Bc, 0, D, NP_TOP, 0, seed, first));
     // e = sol + S z   (exact integers)
     if (ctx->use_i8) {
@@ -927,6 +940,132 @@ qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t see
         LAUNCH(qf_launch_combine_i32(ca, dE, D, Bc, (int)D, ctx->dFlag.as<int>(), ctx->stream));
     }
     return QF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PSFGPV::samp_p for the G-trapdoor basis S = [[R S', I + R W],[S', W]] of A = [A_bar | G - A_bar R], in two phases.
+//
+// The reference loop (gpv.rs:152-161, MatZ::sample_d_precomputed_gso) walks i = m-1 .. 0 with centre -sol.  Its output law
+// depends on the centre only modulo the lattice, and -- at step i -- only modulo the sub-lattice spanned by b_0 .. b_i
+// (a shift by such a vector moves c'_i .. c'_0 by integers and z by the same integers: the same e).  So
+//   phase 1 (i = m-1 .. nk): centre -x with the gadget preimage x = [R g; g], g = digits(u)  (A x = u).  x lies in the real
+//            span of the first nk basis vectors [R;I] S', hence its GSO coordinates vanish for i >= nk:
+//            c'_i = -sum_{j>i} U_ij z_j, block U_22 only.  z_2 = z[nk:] is large (the widths s/||b~_i|| are ~10^4-10^5).
+//   between: the residual centre -x - S[:, nk:] z_2 is reduced modulo L_1 = [R;I] S' Z^nk to
+//            c_1 = -[z_2 + R g3; g3],  g3 = digits((u - A_bar z_2) mod q)     (G W = -A_bar, G g = u mod q);
+//   phase 2 (i = nk-1 .. 0): T_1 = Mt_1 c_1 (one fixed-point contraction over m columns: three digits of z_2 + R g3, one
+//            of g3), then the recursion with block U_11 only; z_1 is small (|z_1| ~ s) because c_1 is reduced.
+//   output:  e = [z_2 + R e_bot; e_bot],  e_bot = g3 + S' z_1        (A e = A_bar z_2 + G g3 = u).
+// Against the one-pass form this never forms sol = A_P^-1 u, never multiplies the nk x m_bar block U_12 by z_2 at 45-bit
+// precision against a 31-bit z_1, and replaces the nk x m_bar product W z_2 by the n x m_bar product A_bar z_2:
+// 9-12 digit-pair products per useful MAC instead of 18-25.
+// ---------------------------------------------------------------------------
+qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
+    const long D = ctx->dim, ldD = ctx->ld_dim, C = ctx->chunk, nk = ctx->nk, mb = ctx->m_bar, n = ctx->n;
+    const long ldk = ctx->ldk_dim, plane = C * ldk, ldnk = ctx->ld_nk, ldk_nk = ctx->ldk_nk;
+    const int nz_m = (int)((C + 127) / 128), nz_kb = (int)(ldk / 128);
+    const int L = ctx->z_limbs;
+    CK(ctx->w[0].ensure((size_t)C * n * 8));     // h = u - A_bar z2 mod q
+    CK(ctx->w[2].ensure((size_t)C * ldD * 8));   // T
+    CK(ctx->w[3].ensure((size_t)C * ldD * 8));   // Z  (columns >= nk become z2 + R g3 after phase 1)
+    CK(ctx->w[4].ensure((size_t)C * ldnk * 8));  // S' z1
+    CK(ctx->w[8].ensure((size_t)L * plane));     // digit planes of z
+    CK(ctx->w[10].ensure((size_t)L * plane));    // digit planes of y = [g3 | z2 + R g3]
+    const size_t nzb = (size_t)L * nz_m * nz_kb;
+    CK(ctx->dNz.ensure(nzb));
+    CK(ctx->dNz2.ensure(nzb));
+    CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dNz2.p, 0, nzb, ctx->stream));
+    ctx->gate_n256 = np_block_index(D - 1, D, NP_SIZES[1]) + 1;
+    ctx->gate_n1024 = np_block_index(D - 1, D, NP_SIZES[2]) + 1;
+    ctx->gate_n4096 = np_block_index(D - 1, D, NP_SIZES[3]) + 1;
+    const size_t gb = (size_t)(ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096 + 1) * sizeof(int);
+    CK(ctx->dGate.ensure(gb));
+    CK(cudaMemsetAsync(ctx->dGate.p, 0, gb, ctx->stream));
+    double* T = ctx->w[2].as<double>();
+    double* Z = ctx->w[3].as<double>();
+    int64_t* H = ctx->w[0].as<int64_t>();
+    int8_t* zp = ctx->w[8].as<int8_t>();
+    int8_t* yp = ctx->w[10].as<int8_t>();
+    int* flag = ctx->dFlag.as<int>();
+    int* gate_z2 = ctx->dGate.as<int>() + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096;
+
+    // ---- phase 1: coordinates m-1 .. nk, centres start at 0
+    CK(cudaMemset2DAsync(T + nk, (size_t)ldD * 8, 0, (size_t)mb * 8, (size_t)Bc, ctx->stream));
+    ctx->np_wdrop_cur = ctx->u_limbs - ctx->u22_limbs; ctx->np_dlo_cur = ctx->u22_dlo; ctx->np_lx_min = 3;
+    QF_TRY(np_block(ctx, T, Z, Bc, nk, D, NP_TOP, 0, seed, first));
+
+    // ---- h = (u - A_bar z2) mod q, exact (A_bar = the first m_bar columns of the installed digit planes of A)
+    {
+        I8GemmArgs g{};
+        g.x = zp + nk; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dAl.p; g.ldw = ldk; g.w_plane = n * ldk;
+        g.LX = L; g.LW = ctx->a_limbs; g.w_signed = 0;
+        g.B = Bc; g.N = (int)n; g.K = (int)mb;
+        g.out_kind = 0; g.sign = -1; g.q = ctx->prm.q; g.base = dUin; g.ldbase = n; g.out = H; g.ldout = n;
+        g.flag = flag;
+        g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = (int)(nk / 128);
+        QF_TRY(gemm_i8_gated(ctx, g, gate_z2));
+    }
+    // ---- g3 = digits(h) (one s8 plane, columns [0, nk) of y), then  z2 + R g3  in place of z2 and its digit planes
+    LAUNCH(qf_launch_gadget_digits(H, n, yp, ldk, Bc, (int)n, (int)ctx->k, (unsigned)ctx->prm.base, ctx->dNz2.as<uint8_t>(), nz_kb,
+                                   ctx->stream));
+    {
+        I8GemmArgs g{};
+        g.x = yp; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dRl.p; g.ldw = ldk_nk; g.w_plane = mb * ldk_nk;
+        g.LX = 1; g.LW = 1; g.w_signed = 1;
+        g.B = Bc; g.N = (int)mb; g.K = (int)nk;
+        g.out_kind = 2; g.sign = 1; g.q = 0; g.out = Z + nk; g.ldout = ldD;
+        g.flag = flag;
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    }
+    LAUNCH(qf_launch_split_f64_limbs(Z + nk, ldD, yp + nk, plane, ldk, Bc, (int)mb, L, flag, ctx->dNz2.as<uint8_t>(), nz_m, nz_kb,
+                                     (int)nk, ctx->stream));
+    // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -Mt_1 [g3 ; z2 + R g3]   (store-only epilogue)
+    {
+        const int wdrop = 0;
+        I8GemmArgs g{};
+        g.x = yp; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dMt1l.as<int8_t>() + (size_t)wdrop * nk * ldk; g.ldw = ldk; g.w_plane = nk * ldk;
+        g.LX = L; g.LW = ctx->mt1_limbs - wdrop; g.w_signed = 1;
+        g.B = Bc; g.N = (int)nk; g.K = (int)D;
+        g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
+        g.flag = flag;
+        g.scale = ctx->dMt1scale.as<double>();
+        g.d_lo = ctx->mt1_dlo; g.overwrite = 1;
+        g.x_nz = ctx->dNz2.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = 0;
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    }
+    // ---- phase 2: coordinates nk-1 .. 0
+    ctx->np_wdrop_cur = ctx->u_limbs - ctx->u11_limbs; ctx->np_dlo_cur = ctx->u11_dlo; ctx->np_lx_min = 2;
+    QF_TRY(np_block(ctx, T, Z, Bc, 0, nk, NP_TOP, 0, seed, first));
+
+    // ---- e_bot = g3 + S' z1,  e_top = (z2 + R g3) + R (S' z1)
+    double* I2 = ctx->w[4].as<double>();
+    CK(cudaMemsetAsync(I2, 0, (size_t)Bc * ldnk * 8, ctx->stream));
+    LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev, ctx->stream));
+    const long plane2 = C * ldk_nk;
+    CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->i2_limbs * plane2, C * ldD * 8)));  // T is dead: digits of S' z1
+    int8_t* ip = ctx->w[2].as<int8_t>();
+    LAUNCH(qf_launch_split_f64_limbs(I2, ldnk, ip, plane2, ldk_nk, Bc, (int)nk, ctx->i2_limbs, flag, nullptr, 0, 0, 0,
+                                     ctx->stream));
+    {
+        I8GemmArgs h{};
+        h.x = ip; h.ldx = ldk_nk; h.x_plane = plane2;
+        h.w = ctx->dRl.p; h.ldw = ldk_nk; h.w_plane = mb * ldk_nk;
+        h.LX = ctx->i2_limbs; h.LW = 1; h.w_signed = 1;
+        h.B = Bc; h.N = (int)mb; h.K = (int)nk;
+        h.out_kind = 1; h.sign = 1; h.q = 0; h.out = dE; h.ldout = D;
+        h.flag = flag;
+        LAUNCH(ctx_gemm_i8(ctx, h));
+    }
+    LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, (int)nk, flag, ctx->stream, yp, ldk));
+    return QF_OK;
+}
+
+qf_status samp_p_np_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t seed, uint64_t first, int32_t* dE) {
+    return ctx->two_phase ? samp_p_np2_chunk(ctx, dUin, Bc, seed, first, dE) : samp_p_np1_chunk(ctx, dUin, Bc, seed, first, dE);
 }
 
 // find n columns of A (n x m) that form a matrix invertible over Z_q by unit pivoting and return
@@ -1260,6 +1399,40 @@ qf_status detect_gpv_structure(qf_ctx* ctx, const int64_t* s, const std::vector<
     for (int pc : piv) piv_low = piv_low || pc >= mb;
     ctx->i2_limbs = limbs_for(8.0 * ctx->prm.s + 64.0 + (piv_low ? (double)q : 0.0));
     ctx->gpv_struct = true;
+    // Does the installed key have the trapdoor form A = [A_bar | G - A_bar R] for this R (tag = identity,
+    // gadget_classical.rs:56-68)?  Then x = [R g; g] with g = digits(u) solves A x = u and the two-phase recursion applies.
+    // A_bar R on the tensor cores ("targets" = the columns of R, key matrix = the installed digit planes of A), compared
+    // exactly on the host.
+    ctx->gadget_key_ok = false;
+    if (base <= 128) {
+        std::vector<int64_t> rt((size_t)nk * mb);
+        for (long i = 0; i < mb; ++i)
+            for (long j = 0; j < nk; ++j) rt[(size_t)j * mb + i] = R[(size_t)i * nk + j];
+        Dev dRt, dAr;
+        QF_TRY(upload_limbs(ctx, rt.data(), nk, mb, ctx->ldk_mb, 1, true, dRt));
+        CK(dAr.ensure((size_t)nk * n * 8));
+        I8GemmArgs g{};
+        g.x = dRt.as<int8_t>(); g.ldx = ctx->ldk_mb; g.x_plane = nk * ctx->ldk_mb;
+        g.w = ctx->dAl.p; g.ldw = ctx->ldk_dim; g.w_plane = n * ctx->ldk_dim;
+        g.LX = 1; g.LW = ctx->a_limbs; g.w_signed = 0;
+        g.B = (int)nk; g.N = (int)n; g.K = (int)mb;
+        g.out_kind = 0; g.sign = 1; g.q = q; g.out = dAr.p; g.ldout = n;
+        g.flag = ctx->dFlag.as<int>();
+        LAUNCH(ctx_gemm_i8(ctx, g));
+        std::vector<int64_t> art((size_t)nk * n);
+        CK(cudaMemcpyAsync(art.data(), dAr.p, art.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<uint64_t> gpow(k);
+        u128 pwt = 1;
+        for (long t = 0; t < k; ++t) { gpow[t] = (uint64_t)(pwt % q); pwt *= base; }
+        bool ok = true;
+        for (long i = 0; i < n && ok; ++i)
+            for (long j = 0; j < nk; ++j) {
+                const uint64_t gij = (j / k == i) ? gpow[j % k] : 0;
+                if ((uint64_t)ctx->hA[(size_t)i * m + mb + j] != (gij + q - (uint64_t)art[(size_t)j * n + i]) % q) { ok = false; break; }
+            }
+        ctx->gadget_key_ok = ok;
+    }
     return QF_OK;
 }
 
@@ -1679,6 +1852,7 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     if (!ctx || !s) return QF_ERR_INVALID;
     if (ctx->prm.kind == QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a GPV context");
     ctx->has_np = false;  // stays false if anything below fails half-way (pivots / A^-1 / U are overwritten in place)
+    ctx->two_phase = false;
     CK(cudaSetDevice(ctx->device));
     const long D = ctx->dim, ld = ctx->ld_dim;
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
@@ -1770,7 +1944,25 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
         const char* env = getenv("QF_DISABLE_OZAKI");
         const char* envmin = getenv("QF_OZAKI_MIN_DIM");
         const long min_dim = envmin ? atol(envmin) : 2 * NP_SIZES[2];
+        // two-phase recursion (samp_p_np2_chunk): G-trapdoor basis of a key of the form [A_bar | G - A_bar R], tensor-core
+        // dimensions.  z then only has to hold the phase-1 coefficients (widths s/||b~_i||, centres of the same size).
+        const char* env2 = getenv("QF_DISABLE_TWO_PHASE");  // test switch: the one-pass recursion
+        ctx->two_phase = ctx->gpv_struct && ctx->gadget_key_ok && D > std::max(min_dim, NP_SIZES[2]) &&
+                         !(env && env[0] == '1') && !(env2 && env2[0] == '1');
+        if (ctx->two_phase) {
+            ctx->z_limbs = limbs_for(64.0 * ctx->prm.s / std::sqrt(dmin));
+            ctx->zlimit = std::min(std::ldexp(1.0, 52), limb_capacity(ctx->z_limbs));
+            if (const char* cfg = getenv("QF_NP2_CFG")) {  // experiments: "u22,dlo,u11,dlo,mt1,dlo"
+                int v[6] = {ctx->u22_limbs, ctx->u22_dlo, ctx->u11_limbs, ctx->u11_dlo, ctx->mt1_limbs, ctx->mt1_dlo};
+                sscanf(cfg, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+                auto lim = [&](int x, int lo, int hi) { return std::max(lo, std::min(hi, x)); };
+                ctx->u22_limbs = lim(v[0], 1, ctx->u_limbs); ctx->u22_dlo = lim(v[1], 0, ctx->u22_limbs - 1);
+                ctx->u11_limbs = lim(v[2], 1, ctx->u_limbs); ctx->u11_dlo = lim(v[3], 0, ctx->u11_limbs - 1);
+                ctx->mt1_limbs = lim(v[4], 1, 7); ctx->mt1_dlo = lim(v[5], 0, ctx->mt1_limbs - 1);
+            }
+        }
         ctx->use_ozaki = D > std::max(min_dim, NP_SIZES[2]) && ctx->z_limbs + ctx->u_limbs - 1 <= 16 && !(env && env[0] == '1');
+        if (ctx->two_phase && !ctx->use_ozaki) return ctx->fail(QF_ERR_NUMERIC, "internal: two-phase recursion without the tensor-core updates");
         if (ctx->use_ozaki) {
             const long nblk = (D + NP_SCALE_BLOCK - 1) / NP_SCALE_BLOCK;
             CK(ctx->dUscale.ensure((size_t)nblk * D * 8));
@@ -1782,12 +1974,30 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
                                            (int)np_last_block_start(D, NP_SIZES[1]), (int)np_last_block_start(D, NP_SCALE_BLOCK),
                                            ctx->u_limbs,
                                            ctx->dUscale.as<double>(), ctx->dUl.as<int8_t>(), D * ctx->ldk_dim, ctx->ldk_dim,
-                                           ctx->stream));
+                                           ctx->stream, ctx->two_phase ? (int)ctx->nk : 0));
             CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->two_phase) {
+                // Mt_1 = rows [0, nk) of D^-1 B~^t with the columns permuted to [gadget block (nk) | top block (m_bar)]
+                // (the order of the operand y = [g3 | z2 + R g3]), as fixed-point digit planes with one scale per row
+                const long nk = ctx->nk, mb = ctx->m_bar, ldk = ctx->ldk_dim;
+                double* perm = dSt.as<double>();  // S^t is dead after the U product
+                CK(cudaMemcpy2DAsync(perm, (size_t)ld * 8, dMt.as<double>() + mb, (size_t)ld * 8, (size_t)nk * 8, (size_t)nk,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpy2DAsync(perm + nk, (size_t)ld * 8, dMt.as<double>(), (size_t)ld * 8, (size_t)mb * 8, (size_t)nk,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+                const size_t pb = (size_t)ctx->mt1_limbs * nk * ldk;
+                CK(ctx->dMt1l.ensure(pb));
+                CK(ctx->dMt1scale.ensure((size_t)nk * 8));
+                CK(cudaMemsetAsync(ctx->dMt1l.p, 0, pb, ctx->stream));
+                LAUNCH(qf_launch_fixed_rows_prepare(perm, ld, (int)nk, (int)D, ctx->mt1_limbs, 1.0, ctx->dMt1scale.as<double>(),
+                                                    ctx->dMt1l.as<int8_t>(), nk * ldk, ldk, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->dMtP.release();
+            }
             // Mt_P as fixed-point digit planes (D rows x npiv columns, one scale per row): T = -Mt_P sol_P on tcgen05
             ctx->sol_limbs = limbs_for((double)ctx->prm.q);
             const char* envm = getenv("QF_DISABLE_MTP_I8");  // test switch: fp64 DMMA as before
-            ctx->mtp_i8 = !(envm && envm[0] == '1') && ctx->sol_limbs + ctx->u_limbs - 1 - ctx->np_dlo <= 9;
+            ctx->mtp_i8 = !ctx->two_phase && !(envm && envm[0] == '1') && ctx->sol_limbs + ctx->u_limbs - 1 - ctx->np_dlo <= 9;
             if (ctx->mtp_i8) {
                 ctx->ldk_piv = (ctx->npiv + 127) / 128 * 128;
                 const size_t pb = (size_t)ctx->u_limbs * D * ctx->ldk_piv;

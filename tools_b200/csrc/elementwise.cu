@@ -593,15 +593,17 @@ __global__ void sprime_apply_kernel(const double* __restrict__ Z, long ldz, doub
         I2[b * ldi + row] += acc;
     }
 }
-// e[b][i] += z2[b][i] (i < mb),  e[b][mb + row] = I2[b][row]: the structured form of e = S z
+// e[b][i] += z2[b][i] (i < mb),  e[b][mb + row] = I2[b][row] (+ g3[b][row], two-phase form): the structured form of e = S z
 __global__ void gpv_struct_finalize_kernel(int32_t* __restrict__ e, long lde, const double* __restrict__ Z2, long ldz,
-                                           const double* __restrict__ I2, long ldi, int B, int mb, int nk, int* flag) {
+                                           const double* __restrict__ I2, long ldi, int B, int mb, int nk, int* flag,
+                                           const int8_t* __restrict__ g3, long ldg) {
     const int m = mb + nk;
     const long total = (long)B * m;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long b = i / m;
         const int j = (int)(i - b * m);
-        double v = j < mb ? (double)e[b * lde + j] + Z2[b * ldz + j] : I2[b * ldi + (j - mb)];
+        double v = j < mb ? (double)e[b * lde + j] + Z2[b * ldz + j]
+                          : I2[b * ldi + (j - mb)] + (g3 ? (double)g3[b * ldg + (j - mb)] : 0.0);
         if (!(fabs(v) < 2147483647.0)) { if (flag) atomicOr(flag, 4); v = 0.0; }
         e[b * lde + j] = (int32_t)__double2ll_rn(v);
     }
@@ -614,10 +616,44 @@ cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long l
     return cudaGetLastError();
 }
 cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2, long ldz, const double* I2, long ldi, int B,
-                                          int mb, int nk, int* flag, cudaStream_t stream) {
+                                          int mb, int nk, int* flag, cudaStream_t stream, const int8_t* g3, long ldg) {
     if (B <= 0) return cudaSuccess;
     gpv_struct_finalize_kernel<<<grid_for((long long)B * (mb + nk), TPB), TPB, 0, stream>>>(e, lde, Z2, ldz, I2, ldi, B, mb, nk,
-                                                                                           flag);
+                                                                                           flag, g3, ldg);
+    return cudaGetLastError();
+}
+namespace {
+// g3[b][blk * k + t] = digit t (base `base`) of h[b][blk]: the gadget-lattice coset representative with G g3 = h
+// (gadget_classical.rs:169-182, find_solution_gadget_vec), one thread per (target, syndrome entry)
+__global__ void gadget_digits_kernel(const int64_t* __restrict__ h, long ldh, int8_t* __restrict__ plane, long ldk, int B,
+                                     int n, int k, unsigned base, uint8_t* __restrict__ nz, int nz_kb_total) {
+    const long total = (long)B * n;
+    const bool pow2 = (base & (base - 1)) == 0;
+    const int sh = 31 - __clz(base);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / n;
+        const int blk = (int)(i - b * n);
+        unsigned long long v = (unsigned long long)h[b * ldh + blk];
+        int8_t* dst = plane + b * ldk + (long)blk * k;
+        for (int t = 0; t < k; ++t) {
+            unsigned d;
+            if (pow2) { d = (unsigned)(v & (base - 1)); v >>= sh; }
+            else { d = (unsigned)(v % base); v /= base; }
+            dst[t] = (int8_t)d;
+        }
+    }
+    if (nz) {  // plane 0 of the zero-tile map: every (128-target, 128-column) tile of the digit block is live
+        const int kbn = (n * k + 127) >> 7, mt = (B + 127) >> 7;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)mt * kbn; i += (long)gridDim.x * blockDim.x)
+            nz[(i / kbn) * nz_kb_total + (i % kbn)] = 1;
+    }
+}
+}  // namespace
+cudaError_t qf_launch_gadget_digits(const int64_t* h, long ldh, int8_t* plane, long ldk, int B, int n, int k, unsigned base,
+                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    if (base < 2 || base > 128) return cudaErrorInvalidValue;
+    gadget_digits_kernel<<<grid_for((long long)B * n, TPB), TPB, 0, stream>>>(h, ldh, plane, ldk, B, n, k, base, nz, nz_kb_total);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,

@@ -579,7 +579,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     I8Params p{};
     p.d_lo = a.d_lo;
     p.overwrite = a.overwrite;
-    p.scale_mul = 1.0;
+    p.scale_mul = a.scale_mul > 0.0 ? a.scale_mul : 1.0;
     for (int i = 0; i < a.d_lo; ++i) p.scale_mul *= 256.0;
     p.acc_bufs = (2 * ND * nt <= 512) ? 2 : 1;
     p.gate = a.gate; p.gate_lo = a.gate_lo; p.gate_hi = a.gate_hi;

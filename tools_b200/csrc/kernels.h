@@ -59,7 +59,13 @@ cudaError_t qf_launch_dgauss(const double* center, long ldc, double* out_f64, lo
 cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long ldi, int B, int nk, int k, const double* sk,
                                    int reversed, cudaStream_t stream);
 cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2, long ldz, const double* I2, long ldi, int B,
-                                          int mb, int nk, int* flag, cudaStream_t stream);
+                                          int mb, int nk, int* flag, cudaStream_t stream, const int8_t* g3 = nullptr,
+                                          long ldg = 0);
+// two-phase nearest plane (api.cu samp_p_np2_chunk): base-b digits of the syndromes h (B x n, in [0,q)) in gadget order,
+// g3[b][blk*k + t] = digit t of h[b][blk], written as ONE s8 digit plane (B x ldk, columns [0, n*k)) and marked in
+// plane 0 of the zero-tile map (k blocks [0, ceil(n*k/128)) of every target tile)
+cudaError_t qf_launch_gadget_digits(const int64_t* h, long ldh, int8_t* plane, long ldk, int B, int n, int k, unsigned base,
+                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream);
 // structured perturbation (api.cu setup_structured_sigma2): X2[b][mb+j] = sqrt_beta * G[b][mb+j] and the balanced
 // base-256 digits of rint(that * fscale) into L planes of B x ldk bytes
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
@@ -192,6 +198,9 @@ struct I8GemmArgs {
     // optional conditional launch: the grid runs only if gate_lo <= *gate <= gate_hi (device int)
     const int* gate;
     int gate_lo, gate_hi;
+    // out_kind 3 only: extra factor on scale[n] (0 = 1): the caller passes the TOP planes of a fixed-point matrix
+    // (w advanced by `dropped` planes, LW reduced) and 256^dropped here
+    double scale_mul;
 };
 int qf_i8_tile_n(int LX, int LW, int N, int d_lo = 0);
 // gemm_i8_fused.cu: out = X W^t mod q with X read as int32 (digit split fused into the contraction) and the
@@ -230,8 +239,10 @@ cudaError_t qf_launch_split_i32_limbs(const int32_t* in, long ldin, int8_t* plan
 cudaError_t qf_launch_add_cols_i32(int32_t* e, long lde, const double* sol, long ldsol, const int* cols, int ncols,
                                    int B, cudaStream_t stream);
 // fixed-point digit planes of U for the tensor-core nearest-plane updates (see setup.cu)
+// split > 0: the entries U[i][j] with i < split <= j are left out (two-phase recursion: that block is never multiplied)
 cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int fs_last, int ss_last, int L,
-                                    double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream);
+                                    double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream,
+                                    int split = 0);
 
 // narrow boundary types (elementwise.cu): int16 Domain values, device-side range check of residues
 // narrow: *flag |= 64 when a value does not fit int16; range check: *flag |= 32 when a residue is outside [0, q)

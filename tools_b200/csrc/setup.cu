@@ -91,14 +91,15 @@ cudaError_t qf_launch_make_dg(const double* d, int count, double s, DGaussParams
 namespace {
 
 __global__ void ozaki_scale_kernel(const double* __restrict__ U, long ld, int D, int blk, int sblk, int fs_last, int ss_last,
-                                   int L, double* __restrict__ scale) {
+                                   int L, double* __restrict__ scale, int split) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int nblk = ss_last / sblk + 1;
     const long total = (long)D * nblk;
     for (long w = (long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total; w += (long)gridDim.x * wpb) {
         const int c = (int)(w / D), i = (int)(w - (long)c * D);
         double mx = 0.0;
-        const int j1 = (c == nblk - 1) ? D : (c + 1) * sblk;
+        int j1 = (c == nblk - 1) ? D : (c + 1) * sblk;
+        if (i < split) j1 = min(j1, split);  // two-phase recursion: rows below the split never meet columns above it
         // first column whose blk-block starts above row i (none if row i lies in the last block)
         const int j0 = i >= fs_last ? D : max(c * sblk, (i / blk + 1) * blk);
         for (int j = j0 + lane; j < j1; j += 32) mx = fmax(mx, fabs(U[(long)i * ld + j]));
@@ -114,13 +115,14 @@ __global__ void ozaki_scale_kernel(const double* __restrict__ U, long ld, int D,
 
 __global__ void ozaki_digits_kernel(const double* __restrict__ U, long ld, int D, int blk, int sblk, int fs_last, int ss_last,
                                     int L, const double* __restrict__ scale, int8_t* __restrict__ planes, long plane_stride,
-                                    long ldk) {
+                                    long ldk, int split) {
     const long total = (long)D * D;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const int i = (int)(t / D), j = (int)(t - (long)i * D);
         const int c = min(j, ss_last) / sblk;
         long long v = 0;
-        if (i < min((j / blk) * blk, fs_last)) v = __double2ll_rn(U[(long)i * ld + j] / scale[(long)c * D + i]);
+        if (i < min((j / blk) * blk, fs_last) && !(i < split && j >= split))
+            v = __double2ll_rn(U[(long)i * ld + j] / scale[(long)c * D + i]);
         for (int l = 0; l < L; ++l) {
             long long lo = ((v + 128) & 255) - 128;
             if (l == L - 1) lo = v;
@@ -133,16 +135,17 @@ __global__ void ozaki_digits_kernel(const double* __restrict__ U, long ld, int D
 }  // namespace
 
 cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, int sblk, int fs_last, int ss_last, int L,
-                                    double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream) {
+                                    double* scale, int8_t* planes, long plane_stride, long ldk, cudaStream_t stream, int split) {
     if (blk <= 0 || sblk % blk != 0 || fs_last % blk != 0 || ss_last % sblk != 0) return cudaErrorInvalidValue;
     const int nblk = ss_last / sblk + 1;
     long long warps = (long long)D * nblk;
     long long g = (warps + 7) / 8;
     if (g > 148 * 32) g = 148 * 32;
-    ozaki_scale_kernel<<<(int)g, 256, 0, stream>>>(U, ld, D, blk, sblk, fs_last, ss_last, L, scale);
+    ozaki_scale_kernel<<<(int)g, 256, 0, stream>>>(U, ld, D, blk, sblk, fs_last, ss_last, L, scale, split);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    ozaki_digits_kernel<<<148 * 16, 256, 0, stream>>>(U, ld, D, blk, sblk, fs_last, ss_last, L, scale, planes, plane_stride, ldk);
+    ozaki_digits_kernel<<<148 * 16, 256, 0, stream>>>(U, ld, D, blk, sblk, fs_last, ss_last, L, scale, planes, plane_stride, ldk,
+                                                      split);
     return cudaGetLastError();
 }
 
