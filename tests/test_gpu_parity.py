@@ -974,7 +974,7 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
         monkeypatch.delenv("QF_NP2_CFG", raising=False)
         monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
         if mode == "two_phase_wide":
-            monkeypatch.setenv("QF_NP2_CFG", "7,0,7,0,7,0")
+            monkeypatch.setenv("QF_NP2_CFG", "7,0,7,0,7,0,7")
         elif mode == "ozaki":
             monkeypatch.setenv("QF_DISABLE_TWO_PHASE", "1")
         elif mode == "fp64":
@@ -998,6 +998,33 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
         assert same2 > 0.9, same2
     else:
         assert np.array_equal(outs["two_phase"], outs["ozaki"])
+
+
+@pytest.mark.parametrize("n,q,s,B", [(64, 2**16, None, 1500), (24, 2**16, 300.0, 700), (8, 127, 70.0, 333), (5, 32, 10.0, 130)])
+def test_np_diag_kernels_bit_identical(T, monkeypatch, n, q, s, B):
+    """The diagonal-block kernel (one target per thread, 64 unrolled steps, lattice.cu np_diag2) against the
+    quad-per-two-targets kernel it replaced: same Philox counters, same order of floating-point operations per
+    (target, coordinate) => identical preimages.  Shapes: tensor-core recursion with fused digit planes (two-phase),
+    fp64 recursion with whole 256-blocks, dimensions that are not multiples of 64, a ragged last CTA."""
+    import math
+
+    gp = T.GadgetParameters.init_default(n, q)
+    if s is None:
+        s = float(math.ceil((math.sqrt(gp.m_bar) + 1.0) * math.sqrt(5.0) * math.log2(n)))
+    rng = np.random.default_rng(n)
+    u = rng.integers(0, q, (B, n), dtype=np.int64)
+    monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
+    outs, key = [], None
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("QF_NP_DIAG_V1", v1)
+        psf = T.PSFGPV(gp, s)
+        if key is None:
+            key = psf.trap_gen(seed=17)
+        a, td = key
+        psf._a_id = None
+        outs.append(psf.samp_p_batch(a, td, u, seed=21))
+        assert np.array_equal(O.f_a_classical_batch(a, outs[-1], q), u)
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_full_size_c2_properties(T):

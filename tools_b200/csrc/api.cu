@@ -170,9 +170,11 @@ struct qf_ctx {
     // three contractions (U_22 updates, the centre map, U_11 updates).
     bool gadget_key_ok = false, two_phase = false;
     Dev dMt1l, dMt1scale, dNz2;
-    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1;
+    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1, mt1g_limbs = 3;
     // digits / window / smallest compiled digit count of z for the update launches of the phase that is running
     int np_wdrop_cur = 0, np_dlo_cur = 2, np_lx_min = 3;
+    int np_diag_variant = 0;
+    long chunk_env = 0;
     // optional per-launch timing of the contraction kernels, CUDA events on ctx->stream
     bool prof = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; double issued; };
@@ -711,7 +713,7 @@ qf_status np_block(qf_ctx* ctx, double* T, double* Z, int Bc, long lo, long hi, 
         LAUNCH(qf_launch_np_diag(T, ldD, Z, ldD, U, ldD, ctx->dDg.as<DGaussParams>(),
                                  ctx->w[9].as<float4>(), ctx->chunk, Bc, (int)lo, (int)(hi - lo), (int)D,
                                  seed, first, ctx->zlimit, ctx->dFlag.as<int>(), ctx->stream, (int)lo, fuse_digits ? &dig : nullptr,
-                                 (int)prop0));
+                                 (int)prop0, ctx->np_diag_variant));
         return QF_OK;
     }
     if (level == 1 && ctx->np_fuse64 && (lo & 63) == 0)
@@ -1022,19 +1024,36 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
     }
     LAUNCH(qf_launch_split_f64_limbs(Z + nk, ldD, yp + nk, plane, ldk, Bc, (int)mb, L, flag, ctx->dNz2.as<uint8_t>(), nz_m, nz_kb,
                                      (int)nk, ctx->stream));
-    // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -Mt_1 [g3 ; z2 + R g3]   (store-only epilogue)
+    // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -Mt_1 [g3 ; z2 + R g3], two launches:
+    // (a) the gadget block: g3 is one digit of 0 .. base-1, three digits of Mt_1 are enough for it, and that block of Mt_1 is
+    //     block triangular (b~_i only involves the gadget coordinates of b_0 .. b_i): store-only epilogue, half the k blocks;
+    // (b) the top block: the three digits of z2 + R g3 against all digits of Mt_1, accumulated onto (a).
     {
-        const int wdrop = 0;
+        const int wdrop = std::max(0, ctx->mt1_limbs - ctx->mt1g_limbs);
         I8GemmArgs g{};
         g.x = yp; g.ldx = ldk; g.x_plane = plane;
         g.w = ctx->dMt1l.as<int8_t>() + (size_t)wdrop * nk * ldk; g.ldw = ldk; g.w_plane = nk * ldk;
-        g.LX = L; g.LW = ctx->mt1_limbs - wdrop; g.w_signed = 1;
-        g.B = Bc; g.N = (int)nk; g.K = (int)D;
+        g.LX = 1; g.LW = ctx->mt1_limbs - wdrop; g.w_signed = 1;
+        g.B = Bc; g.N = (int)nk; g.K = (int)nk;
         g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
         g.flag = flag;
         g.scale = ctx->dMt1scale.as<double>();
-        g.d_lo = ctx->mt1_dlo; g.overwrite = 1;
-        g.x_nz = ctx->dNz2.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = 0;
+        g.scale_mul = std::ldexp(1.0, 8 * wdrop);
+        g.d_lo = 0; g.overwrite = 1;
+        g.tri_mode = ctx->gpv_rev ? 2 : 1; g.tri_slack = (int)ctx->k;
+        LAUNCH(ctx_gemm_i8(ctx, g));
+    }
+    {
+        I8GemmArgs g{};
+        g.x = yp + nk; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dMt1l.as<int8_t>() + nk; g.ldw = ldk; g.w_plane = nk * ldk;
+        g.LX = L; g.LW = ctx->mt1_limbs; g.w_signed = 1;
+        g.B = Bc; g.N = (int)nk; g.K = (int)mb;
+        g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
+        g.flag = flag;
+        g.scale = ctx->dMt1scale.as<double>();
+        g.d_lo = ctx->mt1_dlo; g.overwrite = 0;
+        g.x_nz = ctx->dNz2.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = (int)(nk / 128);
         LAUNCH(ctx_gemm_i8(ctx, g));
     }
     // ---- phase 2: coordinates nk-1 .. 0
@@ -1521,15 +1540,20 @@ qf_status qf_ctx_create(const qf_params* p, int device, qf_ctx** out) {
         ctx->np_fuse64 = !(envu && envu[0] == '1');
         const char* envs = getenv("QF_DISABLE_NP_FUSE_SPLIT");  // test switch: separate digit-split launches
         ctx->np_fuse_split = !(envs && envs[0] == '1');
+        const char* envv = getenv("QF_NP_DIAG_V1");  // test switch: the quad-per-two-targets diagonal-block kernel
+        ctx->np_diag_variant = (envv && envv[0] == '1') ? 1 : 0;
+        if (const char* envc = getenv("QF_CHUNK")) ctx->chunk_env = atol(envc);  // experiments: targets per internal chunk
         const char* envd = getenv("QF_NP_DLO");  // test switch: 0 = every digit pair of the fixed-point updates
         if (envd) ctx->np_dlo = std::max(0, std::min(3, atoi(envd)));
     }
-    // default chunk: keep ~8 fp64-sized work matrices within ~16 GB; whole waves of 148 SMs x 128-target tiles
+    // default chunk: keep ~8 fp64-sized work matrices within ~32 GB (of 180 GB); whole waves of 148 SMs x 128-target tiles.
+    // Two waves (C2: 37 888 targets) give the per-target sequential kernel two CTAs per SM and halve the number of
+    // latency-bound short-K launches per target: 384 k/s against 344 k/s at one wave.
     long per_target = ctx->ld_dim * 8 * 8;
-    long c = (long)((16LL << 30) / std::max(1L, per_target));
+    long c = (long)((32LL << 30) / std::max(1L, per_target));
     c = std::max(128L, std::min(75776L, c / 128 * 128));
     if (c >= 148 * 128) c = c / (148 * 128) * (148 * 128);
-    ctx->chunk = c;
+    ctx->chunk = ctx->chunk_env > 0 ? ctx->chunk_env : c;
     if (ctx->dFlag.ensure(sizeof(int)) != cudaSuccess || cudaMemset(ctx->dFlag.p, 0, sizeof(int)) != cudaSuccess) {
         delete ctx;
         return QF_ERR_CUDA;
@@ -1952,9 +1976,10 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
         if (ctx->two_phase) {
             ctx->z_limbs = limbs_for(64.0 * ctx->prm.s / std::sqrt(dmin));
             ctx->zlimit = std::min(std::ldexp(1.0, 52), limb_capacity(ctx->z_limbs));
-            if (const char* cfg = getenv("QF_NP2_CFG")) {  // experiments: "u22,dlo,u11,dlo,mt1,dlo"
-                int v[6] = {ctx->u22_limbs, ctx->u22_dlo, ctx->u11_limbs, ctx->u11_dlo, ctx->mt1_limbs, ctx->mt1_dlo};
-                sscanf(cfg, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+            if (const char* cfg = getenv("QF_NP2_CFG")) {  // experiments: "u22,dlo,u11,dlo,mt1,dlo[,mt1g]"
+                int v[7] = {ctx->u22_limbs, ctx->u22_dlo, ctx->u11_limbs, ctx->u11_dlo, ctx->mt1_limbs, ctx->mt1_dlo, ctx->mt1g_limbs};
+                sscanf(cfg, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+                ctx->mt1g_limbs = std::max(1, std::min(7, v[6]));
                 auto lim = [&](int x, int lo, int hi) { return std::max(lo, std::min(hi, x)); };
                 ctx->u22_limbs = lim(v[0], 1, ctx->u_limbs); ctx->u22_dlo = lim(v[1], 0, ctx->u22_limbs - 1);
                 ctx->u11_limbs = lim(v[2], 1, ctx->u_limbs); ctx->u11_dlo = lim(v[3], 0, ctx->u11_limbs - 1);

@@ -62,6 +62,10 @@ struct I8Params {
     // conditional launch: the grid exits at once unless gate_lo <= *gate <= gate_hi (device-side choice between
     // variants of the same contraction compiled for different digit counts, no host round trip)
     const int* gate; int gate_lo, gate_hi;
+    // structured w: rows [n0, n0 + nt) of the key matrix only have non-zero columns k < n0 + nt + tri_slack (tri_mode 1,
+    // lower block-triangular) or k >= K - (n0 + nt) - tri_slack (tri_mode 2, the same with the columns reversed): the
+    // k blocks outside that range are neither loaded nor multiplied
+    int tri_mode, tri_slack;
     // optional diagnostics (QF_TRACE): cycles the MMA warp waited for [0] drained accumulators, [1] operand tiles, and the
     // epilogue spent [2] waiting for the accumulators, [3] draining them (summed over CTAs)
     unsigned long long* tim;
@@ -180,6 +184,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         tile_m = g * p.group_m + r % gm;
         tile_n = PAIR ? 2 * (r / gm) + (int)crank : r / gm;
     };
+    // k blocks [kb0, kb1) of a tile (structured w; a CTA pair walks the union of its two tiles' ranges in lockstep)
+    auto kb_range = [&](int tile_n, int& kb0, int& kb1) {
+        kb0 = 0; kb1 = num_kb;
+        if (p.tri_mode == 0) return;
+        const int nlo = (PAIR ? (tile_n & ~1) : tile_n) * p.nt, nhi = min(p.N, nlo + (PAIR ? 2 : 1) * p.nt);
+        if (p.tri_mode == 1) kb1 = min(num_kb, (min(p.K, nhi + p.tri_slack) + BK - 1) / BK);
+        else kb0 = max(0, p.K - nhi - p.tri_slack) / BK;
+    };
     // which x digit planes are non-zero in this (target tile, k block)? (bit j of the returned mask)
     auto plane_mask = [&](int tile_m, int kb) -> uint32_t {
         if (!p.x_nz) return (1u << p.LX) - 1u;
@@ -232,8 +244,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             tile_coords(tile, tile_m, tile_n);
             const int n0 = tile_n * p.nt, m0 = tile_m * TILE_M;
             uint32_t mk_cache = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if ((kb & 31) == 0) mk_cache = (kb + lane < num_kb) ? plane_mask(tile_m, kb + lane) : 0u;
+            int kb0, kb1;
+            kb_range(tile_n, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (kb == kb0 || (kb & 31) == 0) mk_cache = ((kb & ~31) + lane < num_kb) ? plane_mask(tile_m, (kb & ~31) + lane) : 0u;
                 const uint32_t mk = __shfl_sync(0xffffffffu, mk_cache, kb & 31);
                 if (lane == 0) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -281,8 +295,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             uint32_t mk_cache = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if ((kb & 31) == 0) mk_cache = (kb + lane < num_kb) ? plane_mask(tile_m, kb + lane) : 0u;  // as the producer
+            int kb0, kb1;
+            kb_range(tile_n, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (kb == kb0 || (kb & 31) == 0)  // as the producer
+                    mk_cache = ((kb & ~31) + lane < num_kb) ? plane_mask(tile_m, (kb & ~31) + lane) : 0u;
                 const uint32_t mk = __shfl_sync(0xffffffffu, mk_cache, kb & 31);
                 {
                     const long long t0_ = p.tim ? clock64() : 0;
@@ -310,7 +327,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     // frees this smem stage (in both CTAs of a pair) when the MMAs above retire
                     if (PAIR) mma_commit_mc(&empty_bar[stage], (uint16_t)3);
                     else mma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) mma_commit(&tmem_full[buf]);
+                    if (kb == kb1 - 1) mma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -558,6 +575,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     const int ND = a.LX + a.LW - 1 - a.d_lo;
     // the fast read-modify-write epilogue of the fixed-point update exists for 32- and 64-column tiles
     // (wider tiles, ND <= 4, keep their width and take the generic epilogue)
+    if (a.out_kind == 3 && nt > 128) nt = 128;
     if (a.out_kind == 3 && nt > 64 && nt < 128) nt = 64;
     if (a.out_kind == 3 && nt > 32 && nt < 64) nt = 32;
     {
@@ -583,6 +601,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     for (int i = 0; i < a.d_lo; ++i) p.scale_mul *= 256.0;
     p.acc_bufs = (2 * ND * nt <= 512) ? 2 : 1;
     p.gate = a.gate; p.gate_lo = a.gate_lo; p.gate_hi = a.gate_hi;
+    p.tri_mode = a.tri_mode; p.tri_slack = a.tri_slack;
     p.B = a.B; p.N = a.N; p.K = a.K; p.LX = a.LX; p.LW = a.LW; p.nt = nt; p.w_signed = a.w_signed;
     p.out_kind = a.out_kind; p.sign = a.sign; p.q = a.q; p.qmagic = qf_barrett_magic(a.q); p.base = a.base; p.ldbase = a.ldbase; p.out = a.out;
     p.ldout = a.ldout; p.flag = a.flag; p.scale = a.scale;

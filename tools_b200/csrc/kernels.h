@@ -108,7 +108,7 @@ struct NpDigitOut {
 cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
                               uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo = -1,
-                              const NpDigitOut* dig = nullptr, int prop0 = -1);
+                              const NpDigitOut* dig = nullptr, int prop0 = -1, int variant = 0);
 // two proposals per (target, coordinate) for coordinates [j_lo, j_lo + width): out[(i - j_lo) * ldo + b]
 cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int width, int dim, uint64_t seed,
                                  uint64_t first_target, cudaStream_t stream);
@@ -201,6 +201,9 @@ struct I8GemmArgs {
     // out_kind 3 only: extra factor on scale[n] (0 = 1): the caller passes the TOP planes of a fixed-point matrix
     // (w advanced by `dropped` planes, LW reduced) and 256^dropped here
     double scale_mul;
+    // structured key matrix: 1 = rows [n0, n0 + nt) are zero in the columns k >= n0 + nt + tri_slack; 2 = zero in the
+    // columns k < K - (n0 + nt) - tri_slack.  Those k blocks are skipped.
+    int tri_mode, tri_slack;
 };
 int qf_i8_tile_n(int LX, int LW, int N, int d_lo = 0);
 // gemm_i8_fused.cu: out = X W^t mod q with X read as int32 (digit split fused into the contraction) and the

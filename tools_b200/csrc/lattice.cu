@@ -12,6 +12,8 @@
 //    One thread per target, the nb x nb block of mu-coefficients broadcast from
 //    shared memory, target rows staged through shared memory so that global
 //    traffic is coalesced.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -342,6 +344,251 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// np_diag2: the same diagonal-block walk with ONE TARGET PER THREAD.
+// A thread owns one target; the 64 centres of the block live in its column of a shared-memory tile
+// (cs[i * 128 + tid]: conflict-free).  The block is walked in groups of 8 coordinates: the 8 centres of the group
+// are in registers for the 8 sequential steps (accept / reject arithmetic done once per target -- the quad formulation
+// above repeats it in four lanes and serves 16 targets per warp-instruction where this one serves 32), then the rank-8
+// update of the lower coordinates streams their centres through registers once (8 FMAs per load / store pair, the
+// mu values as warp-wide 16-byte broadcasts from the row-major block in shared memory).  The loop over groups stays
+// rolled: ~600 instructions of loop body (a fully unrolled 64-step recursion is 200 KB of code and runs out of the
+// instruction cache at 4 warps per SM -- measured slower than the quad kernel).  Draw order, Philox counters and the
+// order of every floating-point operation per (target, coordinate) are those of np_diag_kernel: the two kernels
+// produce bit-identical output (tested).  One CTA = 128 targets = one 128-target tile of the zero-tile map.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ND2_TPB = 128;
+constexpr int ND2_LD = 66;  // row stride (doubles) of the mu block / update panel in shared memory: even (16-byte rows)
+
+__global__ void __launch_bounds__(ND2_TPB, 2)
+np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
+                long ldu, const DGaussParams* __restrict__ dg_g, const float4* __restrict__ prop, long ldprop, int B,
+                int j_lo, int j_hi, int prop0, int dim, uint64_t seed, uint64_t first_target, double zlimit, int* flag,
+                int fuse_update, NpDigitOut dig) {
+    extern __shared__ __align__(16) double nd2_sm[];
+    double* ur = nd2_sm;             // ur[j * ND2_LD + i] = U[j0 + j][j0 + i] (i > j), later the panel pan[i * ND2_LD + c]
+    double* cs = ur + 64 * ND2_LD;   // cs[i * ND2_TPB + tid]: centres, overwritten by z as the recursion proceeds
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(cs + 64 * ND2_TPB);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long b0 = (long)blockIdx.x * ND2_TPB, b = b0 + tid;
+    const bool live = b < B;
+    double* const cst = cs + tid;
+    for (int sub_hi = j_hi; sub_hi > j_lo;) {
+        const int j0 = max(j_lo, (sub_hi - 1) / 64 * 64), nb = sub_hi - j0;
+        const int up_lo = fuse_update ? j_lo : j0;
+        const int nbe = min(nb, dim - j0);
+        {
+            // the 64 x 64 block of mu: 32 independent loads per thread in flight, then the stores
+            const int mr = tid >> 6, mc = tid & 63;  // rows mr + 2 r, column mc (coalesced along the column index)
+            double mv[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int row = mr + 2 * r;
+                mv[r] = (row < nbe && mc < nbe && mc > row) ? U[(long)(j0 + row) * ldu + (j0 + mc)] : 0.0;
+            }
+            __syncthreads();  // the previous block's panel reads are done
+#pragma unroll
+            for (int r = 0; r < 32; ++r) ur[(mr + 2 * r) * ND2_LD + mc] = mv[r];
+        }
+        for (int i = tid; i < 64; i += ND2_TPB) dgs[i] = i < nbe ? dg_g[j0 + i] : DGaussParams{0.f, 0.f, 0.f, 0.f};
+        // this target's centres -> its column of the tile
+        {
+            const double* tr = T + b * ldt + j0;
+            if (live && nbe == 64 && ((((uintptr_t)tr) & 15) == 0)) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const double2 v = reinterpret_cast<const double2*>(tr)[i];
+                    cst[(2 * i) * ND2_TPB] = v.x;
+                    cst[(2 * i + 1) * ND2_TPB] = v.y;
+                }
+            } else {
+                for (int i = 0; i < 64; ++i) cst[i * ND2_TPB] = (live && i < nbe) ? tr[i] : 0.0;
+            }
+        }
+        const float4* pq = prop + (long)(j0 - prop0) * ldprop + b;
+        const uint64_t index0 = (first_target + (uint64_t)b) * (uint64_t)dim + (uint64_t)j0;
+        float4 pcur[8], pnxt[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pcur[t] = (live && 56 + t < nbe) ? pq[(long)(56 + t) * ldprop] : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+#pragma unroll 1
+        for (int g = 7; g >= 0; --g) {
+            const int ig = 8 * g;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)  // proposals of the next group, in flight during the eight steps of this one
+                pnxt[t] = (live && g > 0 && ig - 8 + t < nbe) ? pq[(long)(ig - 8 + t) * ldprop] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ig < nbe) {  // uniform
+                double c8[8], z8[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) c8[t] = cst[(ig + t) * ND2_TPB];
+#pragma unroll
+                for (int t = 7; t >= 0; --t) {
+                    double zz = 0.0;
+                    if (ig + t < nbe) {  // uniform
+                        const DGaussParams dgp = dgs[ig + t];
+                        const float4 p4 = pcur[t];
+                        const double cp = c8[t];
+                        const double c_int = rint(cp);
+                        const float c_frac = (float)(cp - c_int);
+                        bool done = false;
+                        {
+                            float x = rintf(fmaf(dgp.sigma_p, p4.x, c_frac));
+                            float d = x - c_frac;
+                            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * p4.x, p4.x, -dgp.emax));
+                            if (fabsf(d) <= dgp.tail && p4.z < e) { zz = c_int + (double)x; done = true; }
+                        }
+                        if (!done) {
+                            float x = rintf(fmaf(dgp.sigma_p, p4.y, c_frac));
+                            float d = x - c_frac;
+                            float e = fmaf(-d * d, dgp.inv2s2, fmaf(0.5f * p4.y, p4.y, -dgp.emax));
+                            if (fabsf(d) <= dgp.tail && p4.w < e) { zz = c_int + (double)x; done = true; }
+                        }
+                        if (!done && live)  // both pre-generated proposals rejected: continue the stream from its second block
+                            zz = np_sample_slow(dgp, cp, seed, index0 + (uint64_t)(ig + t), flag);
+                        if (live && !(fabs(zz) < zlimit) && flag) atomicOr(flag, 2);
+                        const double* ucol = ur + ig * ND2_LD + ig + t;  // ucol[t' * ND2_LD] = U[ig + t'][ig + t]
+#pragma unroll
+                        for (int tp = 0; tp < t; ++tp) c8[tp] = fma(-ucol[tp * ND2_LD], zz, c8[tp]);
+                    }
+                    z8[t] = zz;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) cst[(ig + t) * ND2_TPB] = z8[t];
+                // rank-8 update of the lower coordinates, in the order of the one-step-at-a-time recursion (t descending)
+#pragma unroll 8
+                for (int j = 0; j < ig; ++j) {
+                    double cj = cst[j * ND2_TPB];
+                    const double2* up = reinterpret_cast<const double2*>(ur + j * ND2_LD + ig);  // warp-wide broadcasts
+                    const double2 u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
+                    cj = fma(-u67.y, z8[7], cj);
+                    cj = fma(-u67.x, z8[6], cj);
+                    cj = fma(-u45.y, z8[5], cj);
+                    cj = fma(-u45.x, z8[4], cj);
+                    cj = fma(-u23.y, z8[3], cj);
+                    cj = fma(-u23.x, z8[2], cj);
+                    cj = fma(-u01.y, z8[1], cj);
+                    cj = fma(-u01.x, z8[0], cj);
+                    cst[j * ND2_TPB] = cj;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) pcur[t] = pnxt[t];
+        }
+        // the tile now holds z: Z, digit planes
+        double c[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) c[i] = cst[i * ND2_TPB];
+        if (live) {
+            double* zr = Z + b * ldz + j0;
+            if (nbe == 64 && ((((uintptr_t)zr) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) reinterpret_cast<double2*>(zr)[i] = make_double2(c[2 * i], c[2 * i + 1]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i < nbe) zr[i] = c[i];
+            }
+        }
+        // balanced base-256 digit planes, zero-tile map and digit-count gates of this block of z
+        if (dig.planes != nullptr) {
+            int top = -1;
+            // digit l of v: v_l = floor((v + 128 (256^l - 1) / 255) / 256^l) (the balanced carries of the lower digits,
+            // nested floors collapsed), d_l = ((v_l + 128) mod 256) - 128, the top plane keeps all of v_{L-1}
+            long long bias = 0;
+            for (int l = 0; l < dig.L; ++l) {
+                int8_t* dst = dig.planes + (long)l * dig.plane_stride + b * dig.ldk + j0;
+                unsigned any = 0;
+                unsigned w[16];
+                const bool last = l == dig.L - 1;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const long long v = (live && i < nbe) ? __double2ll_rn(c[i]) : 0ll;
+                    const long long vl = (v + bias) >> (8 * l);
+                    const long long d = last ? vl : (((vl + 128) & 255) - 128);  // |z| < zlimit <= capacity of L digits
+                    const unsigned byte = (unsigned)(d & 255);
+                    any |= byte;
+                    if ((i & 3) == 0) w[i >> 2] = byte; else w[i >> 2] |= byte << (8 * (i & 3));
+                }
+                if (live) {
+                    if (nbe == 64) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < nbe; ++i) dst[i] = (int8_t)((w[i >> 2] >> (8 * (i & 3))) & 255);
+                    }
+                }
+                if (any) top = l;
+                bias += 128ll << (8 * l);
+            }
+            top = __reduce_max_sync(0xffffffffu, top);
+            if (lane == 0 && top >= 0) {
+                for (int l = 0; l <= top; ++l) dig.nz[((long)l * dig.nz_m_tiles + (b0 >> 7)) * dig.nz_kb_total + (j0 >> 7)] = 1;
+                if (top > 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (dig.gate[g] && *(volatile int*)dig.gate[g] < top) atomicMax(dig.gate[g], top);
+                }
+            }
+        }
+        // rank-nb update of the columns [up_lo, j0) of the enclosing block for this CTA's own targets:
+        //   T[b][col] -= sum_i z_i U[col][j0 + i],  the panel of U through shared memory 64 columns at a time
+        // (the next panel is fetched into registers while the current one is being multiplied, and the old values of T are
+        // requested before the 64-step accumulation: with 4-8 warps per SM nothing else would hide those latencies)
+        const int pj = tid >> 6, pi = tid & 63;  // this thread's panel elements: columns pj + 2 r, row pi (coalesced along i)
+        double pv[32];
+        auto load_panel = [&](int c0, int ncol) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int j = pj + 2 * r;
+                pv[r] = (j < ncol && pi < nbe) ? U[(long)(c0 + j) * ldu + j0 + pi] : 0.0;
+            }
+        };
+        if (up_lo < j0) load_panel(up_lo, min(64, j0 - up_lo));
+        for (int c0 = up_lo; c0 < j0; c0 += 64) {
+            const int ncol = min(64, j0 - c0);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) ur[pi * ND2_LD + pj + 2 * r] = pv[r];
+            __syncthreads();
+            if (c0 + 64 < j0) load_panel(c0 + 64, min(64, j0 - c0 - 64));
+            for (int cg = 0; cg < ncol; cg += 16) {
+                double2* tr = reinterpret_cast<double2*>(T + b * ldt + c0 + cg);
+                double2 told[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) told[t] = (live && cg + 2 * t < ncol) ? tr[t] : make_double2(0.0, 0.0);
+                double acc[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+                const double2* pan = reinterpret_cast<const double2*>(ur + cg);
+#pragma unroll 4
+                for (int i = 0; i < 64; ++i) {
+                    const double zi = cst[i * ND2_TPB];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const double2 u = pan[i * (ND2_LD / 2) + t];  // warp-wide broadcast, two columns per load
+                        acc[2 * t] = fma(zi, u.x, acc[2 * t]);
+                        acc[2 * t + 1] = fma(zi, u.y, acc[2 * t + 1]);
+                    }
+                }
+                if (live) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (cg + 2 * t < ncol) {
+                            double2 v = told[t];
+                            v.x -= acc[2 * t];
+                            v.y -= acc[2 * t + 1];
+                            tr[t] = v;
+                        }
+                    }
+                }
+            }
+        }
+        sub_hi = j0;
+    }
+}
+
 }  // namespace
 
 cudaError_t qf_launch_gadget_sample(const int64_t* V, long ldv, double* Z, long ldz, int B, int n, int k, int base,
@@ -378,7 +625,7 @@ cudaError_t qf_launch_np_propose(float4* out, long ldo, int B, int j_lo, int wid
 cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const double* U, long ldu,
                               const DGaussParams* dg, const float4* prop, long ldprop, int B, int j0, int nb, int dim,
                               uint64_t seed, uint64_t first_target, double zlimit, int* flag, cudaStream_t stream, int up_lo,
-                              const NpDigitOut* dig, int prop0) {
+                              const NpDigitOut* dig, int prop0, int variant) {
     if (B <= 0) return cudaSuccess;
     // nb <= 64: one diagonal block; nb > 64 (whole 256-block, up_lo == j0 required): its diagonal blocks from the top
     // down with the rank-64 updates fused
@@ -408,6 +655,25 @@ cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const do
         d = *dig;
         // two-byte stores / one map cell per CTA: even column offsets, 64-aligned blocks inside one 128-column cell
         if ((j0 & 63) || (d.ldk & 1) || (((uintptr_t)d.planes) & 1) || (d.plane_stride & 1)) return cudaErrorInvalidValue;
+    }
+    // variant 1 (test switch QF_NP_DIAG_V1, read at context creation): the quad-per-two-targets kernel (bit-identical output)
+    const bool v1 = variant == 1;
+    // np_diag2 stores digits 16 bytes at a time and T two doubles at a time
+    const bool v2_ok = (!dig || (((d.ldk & 15) == 0) && ((((uintptr_t)d.planes) & 15) == 0) && ((d.plane_stride & 15) == 0))) &&
+                       (ldt & 1) == 0 && ((((uintptr_t)T) & 15) == 0) && ((up_lo & 1) == 0);
+    if (!v1 && v2_ok) {
+        const size_t smem2 = (size_t)(64 * ND2_LD + 64 * ND2_TPB) * sizeof(double) + 64 * sizeof(DGaussParams);
+        static size_t configured2_dev[QF_MAX_DEVICES] = {};
+        size_t& configured2 = configured2_dev[qf_device_slot()];
+        if (smem2 > configured2) {
+            cudaError_t e2 = cudaFuncSetAttribute(np_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e2 != cudaSuccess) return e2;
+            configured2 = smem2;
+        }
+        np_diag2_kernel<<<(B + ND2_TPB - 1) / ND2_TPB, ND2_TPB, smem2, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0,
+                                                                                 j0 + nb, prop0, dim, seed, first_target, zlimit,
+                                                                                 flag, multi ? 1 : 0, d);
+        return cudaGetLastError();
     }
     np_diag_kernel<<<grid, NP_TPB, smem, stream>>>(T, ldt, Z, ldz, U, ldu, dg, prop, ldprop, B, j0, j0 + nb, prop0, dim, seed,
                                                    first_target, zlimit, flag, multi ? 1 : 0, d);
