@@ -66,6 +66,10 @@ struct I8Params {
     // lower block-triangular) or k >= K - (n0 + nt) - tri_slack (tri_mode 2, the same with the columns reversed): the
     // k blocks outside that range are neither loaded nor multiplied
     int tri_mode, tri_slack;
+    // out_kind 3, full 32 / 64-column tiles: the read-modify-write of T goes through a per-warp shared-memory staging tile
+    // (coalesced 128-byte row segments on the global side, lane = row on the TMEM side) instead of 16-byte accesses to
+    // 32 different rows per instruction; epi_stage = byte offset of the staging area behind the barriers (0: none)
+    int epi_stage;
     // optional diagnostics (QF_TRACE): cycles the MMA warp waited for [0] drained accumulators, [1] operand tiles, and the
     // epilogue spent [2] waiting for the accumulators, [3] draining them (summed over CTAs)
     unsigned long long* tim;
@@ -137,6 +141,34 @@ __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow,
     }
 }
 
+// 16 columns of the scaled fp64 update for one row (lane = TMEM lane): v <- v - V * scale[n] * mul, in registers.
+template <int NDT>
+__device__ __forceinline__ void epi_cols16(uint32_t lane_addr, int cb, double2 (&v)[8], const double* __restrict__ scale,
+                                           int nd, int nt, double mul) {
+#pragma unroll
+    for (int c0 = 0; c0 < 16; c0 += 4) {
+        double sc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sc[c] = __ldg(scale + c0 + c) * mul;
+        int32_t t[NDT][4];
+#pragma unroll
+        for (int d = 0; d < NDT; ++d)
+            if (d < nd) tmem_ld4(lane_addr + (uint32_t)(d * nt + cb + c0), t[d]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double dv = 0.0;  // Horner in fp64 from the top digit
+#pragma unroll
+            for (int d = NDT - 1; d >= 0; --d)
+                if (d < nd) dv = fma(dv, 256.0, s32_to_f64(t[d][c]));
+            double& o = (c & 1) ? v[(c0 + c) >> 1].y : v[(c0 + c) >> 1].x;
+            o = fma(-dv, sc[c], o);
+        }
+    }
+}
+constexpr int EPI_STG_LD = 18;  // doubles per staged row: 16 columns + 2 (rows stay 16-byte aligned, lane = row reads are conflict free)
+constexpr int EPI_STG_BYTES = EPI_WARPS * 32 * EPI_STG_LD * 8;
+
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM and the barriers are set up
 // once; the TMA producer runs ahead into the next tile while the epilogue of the current one drains TMEM.
 // OK3 = 1: the scaled fp64 update epilogue (out_kind 3) only; 0: the integer epilogues.
@@ -145,7 +177,7 @@ __device__ __forceinline__ void epi_update_any(uint32_t lane_addr, double* orow,
 // CTAs' operand rings, so every x block crosses L2 -> SM once per cluster instead of once per CTA (the x planes are the
 // larger operand: 16 KB per digit plane against nt x 128 bytes per w plane).  A stage is free again when BOTH tensor
 // cores have retired it (tcgen05.commit multicast onto both CTAs' empty barriers).  map_xh = map_x with 64-row boxes.
-template <int OK3, bool PAIR>
+template <int OK3, bool PAIR, bool STG = false>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_xh, I8Params p) {
@@ -358,9 +390,30 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // (warp-uniform: tcgen05.ld is .aligned, every lane of the warp must take the same path)
             const bool pre_ok = OK3 && (p.nt == 32 || p.nt == 64) && m0 + lg * 32 + 31 < p.B && n0 + p.nt <= p.N &&
                                 (p.ldout & 1) == 0 && ((((uintptr_t)p.out) & 15) == 0);
+            // staged epilogue: the old values of this warp's 32 rows x 16-column halves are requested as coalesced 128-byte row
+            // segments (lane -> row lane / 8 + 4 it, 16-byte chunk lane % 8) while the tile's MMAs are still running
+            const bool stg_ok = STG && OK3 && pre_ok;
+            const int ncw_s = p.nt >> 1, r4 = lane >> 3, ch = lane & 7;
+            // (first half: cp.async straight into the staging tile, no registers; second half: registers until the first is done)
+            double2 ldh1[8];
+            if (stg_ok && !p.overwrite) {
+                const double* gb = (const double*)p.out + (long)(m0 + lg * 32) * p.ldout + n0 + half * ncw_s;
+                const uint32_t stg_s = smem_u32(smem + (size_t)p.epi_stage) + (uint32_t)((warp - 2) * (32 * EPI_STG_LD * 8));
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_s + (uint32_t)(((r4 + 4 * it) * EPI_STG_LD + 2 * ch) * 8)),
+                                 "l"(gb + (long)(r4 + 4 * it) * p.ldout + 2 * ch) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (ncw_s > 16) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        ldh1[it] = __ldcs(reinterpret_cast<const double2*>(gb + (long)(r4 + 4 * it) * p.ldout + 16 + 2 * ch));
+                }
+            }
             // per warp: 16 columns of a 32-column tile, 32 columns of a 64-column tile
             double2 pre[16];
-            if (OK3 && pre_ok && p.overwrite) {
+            if (STG) {
+            } else if (OK3 && pre_ok && p.overwrite) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pre[i] = make_double2(0.0, 0.0);
             } else if (OK3 && pre_ok) {
@@ -378,12 +431,47 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const long long te1_ = p.tim ? clock64() : 0;
             te_wait += te1_ - te0_;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (OK3 && pre_ok && p.nt == 64) {
+            if (stg_ok) {
+                double* stg = reinterpret_cast<double*>(smem + (size_t)p.epi_stage) + (warp - 2) * (32 * EPI_STG_LD);
+                double* gb = (double*)p.out + (long)(m0 + lg * 32) * p.ldout + n0 + half * ncw_s;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (16 * h < ncw_s) {  // warp-uniform
+                        double2 v[8];
+                        if (!p.overwrite) {
+                            if (h == 0) {
+                                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            } else {
+#pragma unroll
+                                for (int it = 0; it < 8; ++it)
+                                    *reinterpret_cast<double2*>(stg + (r4 + 4 * it) * EPI_STG_LD + 2 * ch) = ldh1[it];
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const double2*>(stg + lane * EPI_STG_LD + 2 * i);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = make_double2(0.0, 0.0);
+                        }
+                        const int cb = half * ncw_s + 16 * h;
+                        if (ND <= 6) epi_cols16<6>(lane_addr, cb, v, p.scale + n0 + cb, ND, p.nt, p.scale_mul);
+                        else epi_cols16<8>(lane_addr, cb, v, p.scale + n0 + cb, ND, p.nt, p.scale_mul);  // ND <= 8 (launcher)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *reinterpret_cast<double2*>(stg + lane * EPI_STG_LD + 2 * i) = v[i];
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            __stcs(reinterpret_cast<double2*>(gb + (long)(r4 + 4 * it) * p.ldout + 16 * h + 2 * ch),
+                                   *reinterpret_cast<const double2*>(stg + (r4 + 4 * it) * EPI_STG_LD + 2 * ch));
+                        __syncwarp();  // the next half (or tile) overwrites the staged rows
+                    }
+                }
+            } else if (!STG && OK3 && pre_ok && p.nt == 64) {
                 double* orow = (double*)p.out + (long)row * p.ldout + n0;
                 if (ND == 7) epi_update16<7, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, 7, 64, p.scale_mul);
                 else if (ND == 8) epi_update16<8, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, 8, 64, p.scale_mul);
                 else epi_update16<8, 32>(lane_addr, half * 32, pre, orow, p.scale + n0, ND, 64, p.scale_mul);  // ND <= 8 at nt = 64
-            } else if (OK3 && pre_ok) {
+            } else if (!STG && OK3 && pre_ok) {
                 double* orow = (double*)p.out + (long)row * p.ldout + n0;
                 if (ND == 11) epi_update16<11>(lane_addr, half * 16, pre, orow, p.scale + n0, 11, 32, p.scale_mul);
                 else if (ND == 6) epi_update16<6>(lane_addr, half * 16, pre, orow, p.scale + n0, 6, 32, p.scale_mul);
@@ -394,6 +482,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 double* orow = (double*)p.out + (long)row * p.ldout;
                 if (ND <= 3) epi_update_any<3, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
                 else if (ND <= 6) epi_update_any<6, 8>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
+                else if (STG) epi_update_any<8, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
                 else epi_update_any<16, 4>(lane_addr, orow, p.scale, n0, p.nt, p.N, row < p.B, ND, cbeg, cend, p.scale_mul, p.overwrite != 0);
             } else if (!OK3) {
                 for (int c0 = cbeg; c0 < cend; c0 += 16) {
@@ -587,12 +676,18 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (a.out_kind == 3 && nt == 64 && (a.K + BLOCK_K - 1) / BLOCK_K <= nt32_max_kb && 2 * ND * 32 <= 512) nt = 32;
         if (a.out_kind == 3 && (force_nt == 32 || force_nt == 64) && nt >= force_nt) nt = force_nt;
     }
+    // staged (coalesced) read-modify-write epilogue of the fixed-point update: needs EPI_STG_BYTES behind two pipeline stages
+    // (QF_I8_EPI_STAGE=0: the register epilogue, for A/B measurements)
+    static const bool stage_off = getenv("QF_I8_EPI_STAGE") && getenv("QF_I8_EPI_STAGE")[0] == '0';
+    bool epi_stage = false;
     {   // two pipeline stages of LX x-planes + LW w-planes must fit in shared memory
         // test-only switch, read once per process: 64-byte K blocks (SWIZZLE_64B)
         static const int bk_env = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
         const int bk0 = bk_env;
         const int budget0 = 227 * 1024 - 1024 - 256;
         while (nt > 16 && 2 * (a.LX * TILE_M * bk0 + a.LW * nt * bk0) > budget0) nt = (a.out_kind == 3 && nt == 64) ? 32 : nt - 16;
+        epi_stage = !stage_off && a.out_kind == 3 && (nt == 32 || nt == 64) && ND <= 8 &&
+                    2 * (a.LX * TILE_M * bk0 + a.LW * nt * bk0) <= budget0 - EPI_STG_BYTES;
     }
     I8Params p{};
     p.d_lo = a.d_lo;
@@ -621,7 +716,7 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     // K block: 128-byte rows (SWIZZLE_128B).  QF_I8_BLOCK_K=64 selects 64-byte rows (SWIZZLE_64B): twice the pipeline
     // depth in the same shared memory, but measured 30 % slower on B200 (round-1 profile notes) -- the kernel is bound by
     // L2 -> shared-memory operand traffic, not by pipeline depth, and the 64-byte layout feeds the tensor core worse.
-    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;  // barriers + tmem slot + inited mask
+    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - (epi_stage ? EPI_STG_BYTES : 0);  // barriers + tmem slot
     static const int bk_env2 = (getenv("QF_I8_BLOCK_K") && atoi(getenv("QF_I8_BLOCK_K")) == 64) ? 64 : BLOCK_K;
     const int bk = bk_env2;
     p.bk = bk;
@@ -630,7 +725,8 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
     if (stages < 2) return cudaErrorInvalidValue;
     if (stages > 8) stages = 8;
     p.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + 1024 + 256 + (epi_stage ? EPI_STG_BYTES : 0);
+    p.epi_stage = epi_stage ? stages * stage_bytes + 256 : 0;
     CUtensorMap mx, mw, mxh;
     if (!make_map(&mx, a.x, a.K, a.B, a.LX, a.ldx, a.x_plane, TILE_M, bk)) return cudaErrorInvalidValue;
     if (!make_map(&mw, a.w, a.K, a.N, a.LW, a.ldw, a.w_plane, nt, bk)) return cudaErrorInvalidValue;
@@ -643,6 +739,8 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_i8_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -674,11 +772,13 @@ cudaError_t qf_launch_gemm_i8(const I8GemmArgs& a, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (a.out_kind == 3 && epi_stage) return cudaLaunchKernelEx(&cfg, gemm_i8_kernel<1, true, true>, mx, mw, mxh, p);
         if (a.out_kind == 3) return cudaLaunchKernelEx(&cfg, gemm_i8_kernel<1, true>, mx, mw, mxh, p);
         return cudaLaunchKernelEx(&cfg, gemm_i8_kernel<0, true>, mx, mw, mxh, p);
     }
     dim3 grid((unsigned)(total_tiles < sm_count ? total_tiles : sm_count));  // persistent: one CTA per SM
-    if (a.out_kind == 3) gemm_i8_kernel<1, false><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
+    if (a.out_kind == 3 && epi_stage) gemm_i8_kernel<1, false, true><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
+    else if (a.out_kind == 3) gemm_i8_kernel<1, false><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
     else gemm_i8_kernel<0, false><<<grid, I8_THREADS, smem, stream>>>(mx, mw, mxh, p);
     return cudaGetLastError();
 }
