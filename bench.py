@@ -42,7 +42,7 @@ def pert_s_for(m_bar, nk):
 WORKLOADS = {
     "c1": dict(kind="pert", n=8, q=64, r=3.0, s=25.0, batch=262144,
                desc="C1 README PSFPerturbation init_default(8, 64), r=3, s=25 (m=105), uniform synthetic targets"),
-    "c2": dict(kind="gpv", n=256, q=2**24, batch=151552,  # four internal chunks of 2 x 148 SMs x 128 targets
+    "c2": dict(kind="gpv", n=256, q=2**24, batch=227328,  # six internal chunks of 2 x 148 SMs x 128 targets
                desc="C2 PSFGPV n=256 q=2^24 classical gadget (m=12352), uniform synthetic targets"),
     "c2small": dict(kind="gpv", n=64, q=2**24, batch=65536,
                     desc="reduced PSFGPV n=64 q=2^24 (m=3108) -- smoke-size variant, not the headline"),

@@ -165,12 +165,13 @@ struct qf_ctx {
     Dev dGate;
     int gate_n256 = 0, gate_n1024 = 0, gate_n4096 = 0;
     // Two-phase nearest plane for the G-trapdoor basis (samp_p_np2_chunk): the key is A = [A_bar | G - A_bar R] with the R
-    // recovered from S (verified when the trapdoor is installed).  Fixed-point digit planes of Mt_1 = rows [0, nk) of
-    // D^-1 B~^t with the columns permuted to [gadget block | top block], one scale per row; digit counts / windows of the
-    // three contractions (U_22 updates, the centre map, U_11 updates).
+    // recovered from S (verified when the trapdoor is installed).  Fixed-point digit planes (one scale per row) of
+    // Mt_1 = rows [0, nk) x columns [0, m_bar) of D^-1 B~^t (GSO coordinates of a centre -[z; 0]) and of
+    // M' = Mt_1 [R; I] = U_11 S'^-1 (GSO coordinates of a centre -[R; I] g, g in gadget coordinates: block triangular);
+    // digit counts / windows of the contractions (U_22 updates, the two centre maps, U_11 updates).
     bool gadget_key_ok = false, two_phase = false;
-    Dev dMt1l, dMt1scale, dNz2;
-    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1, mt1g_limbs = 3;
+    Dev dMt1l, dMt1scale, dMpl, dMpscale;
+    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1, mt1g_limbs = 4;
     // digits / window / smallest compiled digit count of z for the update launches of the phase that is running
     int np_wdrop_cur = 0, np_dlo_cur = 2, np_lx_min = 3;
     int np_diag_variant = 0;
@@ -954,9 +955,10 @@ qf_status samp_p_np1_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
 //            span of the first nk basis vectors [R;I] S', hence its GSO coordinates vanish for i >= nk:
 //            c'_i = -sum_{j>i} U_ij z_j, block U_22 only.  z_2 = z[nk:] is large (the widths s/||b~_i|| are ~10^4-10^5).
 //   between: the residual centre -x - S[:, nk:] z_2 is reduced modulo L_1 = [R;I] S' Z^nk to
-//            c_1 = -[z_2 + R g3; g3],  g3 = digits((u - A_bar z_2) mod q)     (G W = -A_bar, G g = u mod q);
-//   phase 2 (i = nk-1 .. 0): T_1 = Mt_1 c_1 (one fixed-point contraction over m columns: three digits of z_2 + R g3, one
-//            of g3), then the recursion with block U_11 only; z_1 is small (|z_1| ~ s) because c_1 is reduced.
+//            c_1 = -[z_2; 0] - [R; I] g3,  g3 = digits((u - A_bar z_2) mod q)     (G W = -A_bar, G g = u mod q);
+//   phase 2 (i = nk-1 .. 0): its GSO coordinates T_1 = -Mt_1 z_2 - M' g3 (Mt_1 = the first m_bar columns of rows [0, nk) of
+//            D^-1 B~^t; M' = Mt [R; I] = U_11 S'^-1 is block triangular with entries <= 1/2), then the recursion with block
+//            U_11 only; z_1 is small (|z_1| ~ s) because c_1 is reduced.
 //   output:  e = [z_2 + R e_bot; e_bot],  e_bot = g3 + S' z_1        (A e = A_bar z_2 + G g3 = u).
 // Against the one-pass form this never forms sol = A_P^-1 u, never multiplies the nk x m_bar block U_12 by z_2 at 45-bit
 // precision against a 31-bit z_1, and replaces the nk x m_bar product W z_2 by the n x m_bar product A_bar z_2:
@@ -969,15 +971,13 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
     const int L = ctx->z_limbs;
     CK(ctx->w[0].ensure((size_t)C * n * 8));     // h = u - A_bar z2 mod q
     CK(ctx->w[2].ensure((size_t)C * ldD * 8));   // T
-    CK(ctx->w[3].ensure((size_t)C * ldD * 8));   // Z  (columns >= nk become z2 + R g3 after phase 1)
-    CK(ctx->w[4].ensure((size_t)C * ldnk * 8));  // S' z1
+    CK(ctx->w[3].ensure((size_t)C * ldD * 8));   // Z
+    CK(ctx->w[4].ensure((size_t)C * ldnk * 8));  // e_bot = g3 + S' z1
     CK(ctx->w[8].ensure((size_t)L * plane));     // digit planes of z
-    CK(ctx->w[10].ensure((size_t)L * plane));    // digit planes of y = [g3 | z2 + R g3]
+    CK(ctx->w[10].ensure((size_t)C * ldk_nk));   // g3 (one digit plane)
     const size_t nzb = (size_t)L * nz_m * nz_kb;
     CK(ctx->dNz.ensure(nzb));
-    CK(ctx->dNz2.ensure(nzb));
     CK(cudaMemsetAsync(ctx->dNz.p, 0, nzb, ctx->stream));
-    CK(cudaMemsetAsync(ctx->dNz2.p, 0, nzb, ctx->stream));
     ctx->gate_n256 = np_block_index(D - 1, D, NP_SIZES[1]) + 1;
     ctx->gate_n1024 = np_block_index(D - 1, D, NP_SIZES[2]) + 1;
     ctx->gate_n4096 = np_block_index(D - 1, D, NP_SIZES[3]) + 1;
@@ -988,7 +988,7 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
     double* Z = ctx->w[3].as<double>();
     int64_t* H = ctx->w[0].as<int64_t>();
     int8_t* zp = ctx->w[8].as<int8_t>();
-    int8_t* yp = ctx->w[10].as<int8_t>();
+    int8_t* gp = ctx->w[10].as<int8_t>();
     int* flag = ctx->dFlag.as<int>();
     int* gate_z2 = ctx->dGate.as<int>() + ctx->gate_n256 + ctx->gate_n1024 + ctx->gate_n4096;
 
@@ -1009,63 +1009,48 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
         g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = (int)(nk / 128);
         QF_TRY(gemm_i8_gated(ctx, g, gate_z2));
     }
-    // ---- g3 = digits(h) (one s8 plane, columns [0, nk) of y), then  z2 + R g3  in place of z2 and its digit planes
-    LAUNCH(qf_launch_gadget_digits(H, n, yp, ldk, Bc, (int)n, (int)ctx->k, (unsigned)ctx->prm.base, ctx->dNz2.as<uint8_t>(), nz_kb,
-                                   ctx->stream));
+    // ---- g3 = digits(h): one s8 plane (the x operand of its centre map) and, as fp64, the start of e_bot = g3 + S' z1
+    double* I2 = ctx->w[4].as<double>();
+    LAUNCH(qf_launch_gadget_digits(H, n, gp, ldk_nk, Bc, (int)n, (int)ctx->k, (unsigned)ctx->prm.base, nullptr, 0, ctx->stream, I2,
+                                   ldnk));
+    // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -M' g3 - Mt_1 z2, two launches:
+    // (a) M' g3 (M' = U_11 S'^-1, entries <= 1/2, block triangular: the k blocks outside the triangle are skipped
+    //     in-kernel), one digit of 0 .. base-1 against four digits: store-only epilogue;
+    // (b) Mt_1 z2: the three digit planes of z2 written by phase 1 against all digits of Mt_1, accumulated onto (a).
     {
         I8GemmArgs g{};
-        g.x = yp; g.ldx = ldk; g.x_plane = plane;
-        g.w = ctx->dRl.p; g.ldw = ldk_nk; g.w_plane = mb * ldk_nk;
-        g.LX = 1; g.LW = 1; g.w_signed = 1;
-        g.B = Bc; g.N = (int)mb; g.K = (int)nk;
-        g.out_kind = 2; g.sign = 1; g.q = 0; g.out = Z + nk; g.ldout = ldD;
-        g.flag = flag;
-        LAUNCH(ctx_gemm_i8(ctx, g));
-    }
-    LAUNCH(qf_launch_split_f64_limbs(Z + nk, ldD, yp + nk, plane, ldk, Bc, (int)mb, L, flag, ctx->dNz2.as<uint8_t>(), nz_m, nz_kb,
-                                     (int)nk, ctx->stream));
-    // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -Mt_1 [g3 ; z2 + R g3], two launches:
-    // (a) the gadget block: g3 is one digit of 0 .. base-1, three digits of Mt_1 are enough for it, and that block of Mt_1 is
-    //     block triangular (b~_i only involves the gadget coordinates of b_0 .. b_i): store-only epilogue, half the k blocks;
-    // (b) the top block: the three digits of z2 + R g3 against all digits of Mt_1, accumulated onto (a).
-    {
-        const int wdrop = std::max(0, ctx->mt1_limbs - ctx->mt1g_limbs);
-        I8GemmArgs g{};
-        g.x = yp; g.ldx = ldk; g.x_plane = plane;
-        g.w = ctx->dMt1l.as<int8_t>() + (size_t)wdrop * nk * ldk; g.ldw = ldk; g.w_plane = nk * ldk;
-        g.LX = 1; g.LW = ctx->mt1_limbs - wdrop; g.w_signed = 1;
+        g.x = gp; g.ldx = ldk_nk; g.x_plane = C * ldk_nk;
+        g.w = ctx->dMpl.p; g.ldw = ldk_nk; g.w_plane = nk * ldk_nk;
+        g.LX = 1; g.LW = ctx->mt1g_limbs; g.w_signed = 1;
         g.B = Bc; g.N = (int)nk; g.K = (int)nk;
         g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
         g.flag = flag;
-        g.scale = ctx->dMt1scale.as<double>();
-        g.scale_mul = std::ldexp(1.0, 8 * wdrop);
+        g.scale = ctx->dMpscale.as<double>();
         g.d_lo = 0; g.overwrite = 1;
-        g.tri_mode = ctx->gpv_rev ? 2 : 1; g.tri_slack = (int)ctx->k;
+        g.tri_mode = ctx->gpv_rev ? 3 : 4; g.tri_slack = (int)ctx->k;
         LAUNCH(ctx_gemm_i8(ctx, g));
     }
     {
         I8GemmArgs g{};
-        g.x = yp + nk; g.ldx = ldk; g.x_plane = plane;
-        g.w = ctx->dMt1l.as<int8_t>() + nk; g.ldw = ldk; g.w_plane = nk * ldk;
+        g.x = zp + nk; g.ldx = ldk; g.x_plane = plane;
+        g.w = ctx->dMt1l.p; g.ldw = ctx->ldk_mb; g.w_plane = nk * ctx->ldk_mb;
         g.LX = L; g.LW = ctx->mt1_limbs; g.w_signed = 1;
         g.B = Bc; g.N = (int)nk; g.K = (int)mb;
         g.out_kind = 3; g.sign = 1; g.q = 0; g.out = T; g.ldout = ldD;
         g.flag = flag;
         g.scale = ctx->dMt1scale.as<double>();
         g.d_lo = ctx->mt1_dlo; g.overwrite = 0;
-        g.x_nz = ctx->dNz2.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = (int)(nk / 128);
-        LAUNCH(ctx_gemm_i8(ctx, g));
+        g.x_nz = ctx->dNz.as<uint8_t>(); g.nz_m_tiles = nz_m; g.nz_kb_total = nz_kb; g.nz_kb_off = (int)(nk / 128);
+        QF_TRY(gemm_i8_gated(ctx, g, gate_z2));
     }
     // ---- phase 2: coordinates nk-1 .. 0
     ctx->np_wdrop_cur = ctx->u_limbs - ctx->u11_limbs; ctx->np_dlo_cur = ctx->u11_dlo; ctx->np_lx_min = 2;
     QF_TRY(np_block(ctx, T, Z, Bc, 0, nk, NP_TOP, 0, seed, first));
 
-    // ---- e_bot = g3 + S' z1,  e_top = (z2 + R g3) + R (S' z1)
-    double* I2 = ctx->w[4].as<double>();
-    CK(cudaMemsetAsync(I2, 0, (size_t)Bc * ldnk * 8, ctx->stream));
+    // ---- e_bot = g3 + S' z1,  e_top = z2 + R e_bot
     LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev, ctx->stream));
     const long plane2 = C * ldk_nk;
-    CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->i2_limbs * plane2, C * ldD * 8)));  // T is dead: digits of S' z1
+    CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->i2_limbs * plane2, C * ldD * 8)));  // T is dead: digits of e_bot
     int8_t* ip = ctx->w[2].as<int8_t>();
     LAUNCH(qf_launch_split_f64_limbs(I2, ldnk, ip, plane2, ldk_nk, Bc, (int)nk, ctx->i2_limbs, flag, nullptr, 0, 0, 0,
                                      ctx->stream));
@@ -1079,7 +1064,7 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
         h.flag = flag;
         LAUNCH(ctx_gemm_i8(ctx, h));
     }
-    LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, (int)nk, flag, ctx->stream, yp, ldk));
+    LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, (int)nk, flag, ctx->stream));
     return QF_OK;
 }
 
@@ -2002,21 +1987,63 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
                                            ctx->stream, ctx->two_phase ? (int)ctx->nk : 0));
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->two_phase) {
-                // Mt_1 = rows [0, nk) of D^-1 B~^t with the columns permuted to [gadget block (nk) | top block (m_bar)]
-                // (the order of the operand y = [g3 | z2 + R g3]), as fixed-point digit planes with one scale per row
-                const long nk = ctx->nk, mb = ctx->m_bar, ldk = ctx->ldk_dim;
-                double* perm = dSt.as<double>();  // S^t is dead after the U product
-                CK(cudaMemcpy2DAsync(perm, (size_t)ld * 8, dMt.as<double>() + mb, (size_t)ld * 8, (size_t)nk * 8, (size_t)nk,
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
-                CK(cudaMemcpy2DAsync(perm + nk, (size_t)ld * 8, dMt.as<double>(), (size_t)ld * 8, (size_t)mb * 8, (size_t)nk,
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
-                const size_t pb = (size_t)ctx->mt1_limbs * nk * ldk;
-                CK(ctx->dMt1l.ensure(pb));
-                CK(ctx->dMt1scale.ensure((size_t)nk * 8));
-                CK(cudaMemsetAsync(ctx->dMt1l.p, 0, pb, ctx->stream));
-                LAUNCH(qf_launch_fixed_rows_prepare(perm, ld, (int)nk, (int)D, ctx->mt1_limbs, 1.0, ctx->dMt1scale.as<double>(),
-                                                    ctx->dMt1l.as<int8_t>(), nk * ldk, ldk, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
+                const long nk = ctx->nk, mb = ctx->m_bar, k = ctx->k;
+                // Mt_1 = rows [0, nk) x columns [0, m_bar) of D^-1 B~^t as fixed-point digit planes, one scale per row
+                {
+                    const long ldk = ctx->ldk_mb;
+                    const size_t pb = (size_t)ctx->mt1_limbs * nk * ldk;
+                    CK(ctx->dMt1l.ensure(pb));
+                    CK(ctx->dMt1scale.ensure((size_t)nk * 8));
+                    CK(cudaMemsetAsync(ctx->dMt1l.p, 0, pb, ctx->stream));
+                    LAUNCH(qf_launch_fixed_rows_prepare(dMt.as<double>(), ld, (int)nk, (int)mb, ctx->mt1_limbs, 1.0,
+                                                        ctx->dMt1scale.as<double>(), ctx->dMt1l.as<int8_t>(), nk * ldk, ldk,
+                                                        ctx->stream));
+                }
+                // M' = U_11 S'^-1 (nk x nk): S_k^-1 by Gauss-Jordan on the host (k <= 64), the product on the device
+                {
+                    std::vector<double> a((size_t)k * 2 * k, 0.0), ski((size_t)k * k);
+                    const uint64_t base = (uint64_t)ctx->prm.base, q = ctx->prm.q;
+                    u128 pw = 1;
+                    for (long i = 0; i < k; ++i) pw *= base;
+                    for (long j = 0; j < k; ++j) { a[j * 2 * k + j] = (double)base; a[j * 2 * k + k + j] = 1.0; }
+                    for (long i = 0; i + 1 < k; ++i) a[(i + 1) * 2 * k + i] = -1.0;
+                    if (pw != (u128)q) {
+                        uint64_t qq = q;
+                        for (long i = 0; i < k; ++i) { a[i * 2 * k + (k - 1)] = (double)(qq % base); qq /= base; }
+                    }
+                    for (long c = 0; c < k; ++c) {
+                        long pv = c;
+                        for (long r = c + 1; r < k; ++r)
+                            if (std::fabs(a[r * 2 * k + c]) > std::fabs(a[pv * 2 * k + c])) pv = r;
+                        if (!(std::fabs(a[pv * 2 * k + c]) > 0)) return ctx->fail(QF_ERR_NUMERIC, "internal: singular gadget block");
+                        if (pv != c)
+                            for (long j = 0; j < 2 * k; ++j) std::swap(a[c * 2 * k + j], a[pv * 2 * k + j]);
+                        const double inv = 1.0 / a[c * 2 * k + c];
+                        for (long j = 0; j < 2 * k; ++j) a[c * 2 * k + j] *= inv;
+                        for (long r = 0; r < k; ++r) {
+                            if (r == c) continue;
+                            const double f = a[r * 2 * k + c];
+                            if (f != 0.0)
+                                for (long j = 0; j < 2 * k; ++j) a[r * 2 * k + j] -= f * a[c * 2 * k + j];
+                        }
+                    }
+                    for (long i = 0; i < k; ++i)
+                        for (long j = 0; j < k; ++j) ski[i * k + j] = a[i * 2 * k + k + j];
+                    Dev dSki;
+                    CK(dSki.ensure(ski.size() * 8));
+                    CK(cudaMemcpyAsync(dSki.p, ski.data(), ski.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+                    double* mp = dSt.as<double>();  // S^t is dead after the U product
+                    LAUNCH(qf_launch_gadget_to_gso(ctx->dU.as<double>(), ld, (int)nk, (int)k, ctx->gpv_rev, dSki.as<double>(), mp, ld,
+                                                   ctx->stream));
+                    const long ldk = ctx->ldk_nk;
+                    const size_t pb = (size_t)ctx->mt1g_limbs * nk * ldk;
+                    CK(ctx->dMpl.ensure(pb));
+                    CK(ctx->dMpscale.ensure((size_t)nk * 8));
+                    CK(cudaMemsetAsync(ctx->dMpl.p, 0, pb, ctx->stream));
+                    LAUNCH(qf_launch_fixed_rows_prepare(mp, ld, (int)nk, (int)nk, ctx->mt1g_limbs, 1.0, ctx->dMpscale.as<double>(),
+                                                        ctx->dMpl.as<int8_t>(), nk * ldk, ldk, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                }
                 ctx->dMtP.release();
             }
             // Mt_P as fixed-point digit planes (D rows x npiv columns, one scale per row): T = -Mt_P sol_P on tcgen05

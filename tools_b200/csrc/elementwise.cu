@@ -626,7 +626,8 @@ namespace {
 // g3[b][blk * k + t] = digit t (base `base`) of h[b][blk]: the gadget-lattice coset representative with G g3 = h
 // (gadget_classical.rs:169-182, find_solution_gadget_vec), one thread per (target, syndrome entry)
 __global__ void gadget_digits_kernel(const int64_t* __restrict__ h, long ldh, int8_t* __restrict__ plane, long ldk, int B,
-                                     int n, int k, unsigned base, uint8_t* __restrict__ nz, int nz_kb_total) {
+                                     int n, int k, unsigned base, uint8_t* __restrict__ nz, int nz_kb_total,
+                                     double* __restrict__ I2, long ldi) {
     const long total = (long)B * n;
     const bool pow2 = (base & (base - 1)) == 0;
     const int sh = 31 - __clz(base);
@@ -640,6 +641,7 @@ __global__ void gadget_digits_kernel(const int64_t* __restrict__ h, long ldh, in
             if (pow2) { d = (unsigned)(v & (base - 1)); v >>= sh; }
             else { d = (unsigned)(v % base); v /= base; }
             dst[t] = (int8_t)d;
+            if (I2) I2[b * ldi + (long)blk * k + t] = (double)d;
         }
     }
     if (nz) {  // plane 0 of the zero-tile map: every (128-target, 128-column) tile of the digit block is live
@@ -650,10 +652,11 @@ __global__ void gadget_digits_kernel(const int64_t* __restrict__ h, long ldh, in
 }
 }  // namespace
 cudaError_t qf_launch_gadget_digits(const int64_t* h, long ldh, int8_t* plane, long ldk, int B, int n, int k, unsigned base,
-                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream) {
+                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream, double* I2, long ldi) {
     if (B <= 0) return cudaSuccess;
     if (base < 2 || base > 128) return cudaErrorInvalidValue;
-    gadget_digits_kernel<<<grid_for((long long)B * n, TPB), TPB, 0, stream>>>(h, ldh, plane, ldk, B, n, k, base, nz, nz_kb_total);
+    gadget_digits_kernel<<<grid_for((long long)B * n, TPB), TPB, 0, stream>>>(h, ldh, plane, ldk, B, n, k, base, nz, nz_kb_total,
+                                                                              I2, ldi);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,

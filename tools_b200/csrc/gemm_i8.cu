@@ -63,7 +63,8 @@ struct I8Params {
     // variants of the same contraction compiled for different digit counts, no host round trip)
     const int* gate; int gate_lo, gate_hi;
     // structured w: rows [n0, n0 + nt) of the key matrix only have non-zero columns k < n0 + nt + tri_slack (tri_mode 1,
-    // lower block-triangular) or k >= K - (n0 + nt) - tri_slack (tri_mode 2, the same with the columns reversed): the
+    // lower block-triangular), k >= K - (n0 + nt) - tri_slack (2, the same with the columns reversed), k < K - n0 + tri_slack
+    // (3, upper block-triangular with the columns reversed) or k >= n0 - tri_slack (4, upper block-triangular): the
     // k blocks outside that range are neither loaded nor multiplied
     int tri_mode, tri_slack;
     // out_kind 3, full 32 / 64-column tiles: the read-modify-write of T goes through a per-warp shared-memory staging tile
@@ -222,7 +223,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (p.tri_mode == 0) return;
         const int nlo = (PAIR ? (tile_n & ~1) : tile_n) * p.nt, nhi = min(p.N, nlo + (PAIR ? 2 : 1) * p.nt);
         if (p.tri_mode == 1) kb1 = min(num_kb, (min(p.K, nhi + p.tri_slack) + BK - 1) / BK);
-        else kb0 = max(0, p.K - nhi - p.tri_slack) / BK;
+        else if (p.tri_mode == 2) kb0 = max(0, p.K - nhi - p.tri_slack) / BK;
+        else if (p.tri_mode == 3) kb1 = min(num_kb, (min(p.K, max(1, p.K - nlo + p.tri_slack)) + BK - 1) / BK);
+        else kb0 = max(0, min(p.K - 1, nlo - p.tri_slack)) / BK;
     };
     // which x digit planes are non-zero in this (target tile, k block)? (bit j of the returned mask)
     auto plane_mask = [&](int tile_m, int kb) -> uint32_t {

@@ -65,7 +65,12 @@ cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2
 // g3[b][blk*k + t] = digit t of h[b][blk], written as ONE s8 digit plane (B x ldk, columns [0, n*k)) and marked in
 // plane 0 of the zero-tile map (k blocks [0, ceil(n*k/128)) of every target tile)
 cudaError_t qf_launch_gadget_digits(const int64_t* h, long ldh, int8_t* plane, long ldk, int B, int n, int k, unsigned base,
-                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream);
+                                    uint8_t* nz, int nz_kb_total, cudaStream_t stream, double* I2 = nullptr, long ldi = 0);
+// M'[i][bc k + t] = sum_t' U[i][col(bc, t')] Skinv[t'][t] over the upper unitriangular part of U (col = the basis column
+// of gadget coordinate bc k + t', reversed when `rev`): the map from a gadget-coordinate vector g (centre -[R;I] g) to
+// GSO coordinates of the first nk basis vectors (api.cu samp_p_np2_chunk)
+cudaError_t qf_launch_gadget_to_gso(const double* U, long ldu, int nk, int k, int rev, const double* skinv, double* out,
+                                    long ldo, cudaStream_t stream);
 // structured perturbation (api.cu setup_structured_sigma2): X2[b][mb+j] = sqrt_beta * G[b][mb+j] and the balanced
 // base-256 digits of rint(that * fscale) into L planes of B x ldk bytes
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,
@@ -201,8 +206,8 @@ struct I8GemmArgs {
     // out_kind 3 only: extra factor on scale[n] (0 = 1): the caller passes the TOP planes of a fixed-point matrix
     // (w advanced by `dropped` planes, LW reduced) and 256^dropped here
     double scale_mul;
-    // structured key matrix: 1 = rows [n0, n0 + nt) are zero in the columns k >= n0 + nt + tri_slack; 2 = zero in the
-    // columns k < K - (n0 + nt) - tri_slack.  Those k blocks are skipped.
+    // structured key matrix: rows [n0, n0 + nt) are zero in the columns  1: k >= n0 + nt + tri_slack;
+    // 2: k < K - (n0 + nt) - tri_slack;  3: k >= K - n0 + tri_slack;  4: k < n0 - tri_slack.  Those k blocks are skipped.
     int tri_mode, tri_slack;
 };
 int qf_i8_tile_n(int LX, int LW, int N, int d_lo = 0);

@@ -149,6 +149,30 @@ cudaError_t qf_launch_ozaki_prepare(const double* U, long ld, int D, int blk, in
     return cudaGetLastError();
 }
 
+namespace {
+__global__ void gadget_to_gso_kernel(const double* __restrict__ U, long ldu, int nk, int k, int rev,
+                                     const double* __restrict__ skinv, double* __restrict__ out, long ldo) {
+    const long total = (long)nk * nk;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / nk), c = (int)(idx - (long)i * nk);
+        const int bc = c / k, t = c - bc * k;
+        double acc = 0.0;
+        for (int tp = 0; tp < k; ++tp) {
+            const int cc = bc * k + tp, col = rev ? nk - 1 - cc : cc;
+            if (col < i) continue;  // U is upper unitriangular (the computed lower part is rounding noise)
+            const double u = col == i ? 1.0 : U[(long)i * ldu + col];
+            acc = fma(u, skinv[tp * k + t], acc);
+        }
+        out[(long)i * ldo + c] = acc;
+    }
+}
+}  // namespace
+cudaError_t qf_launch_gadget_to_gso(const double* U, long ldu, int nk, int k, int rev, const double* skinv, double* out,
+                                    long ldo, cudaStream_t stream) {
+    gadget_to_gso_kernel<<<148 * 16, 256, 0, stream>>>(U, ldu, nk, k, rev, skinv, out, ldo);
+    return cudaGetLastError();
+}
+
 // ---- blocked Cholesky (per key): compute_sqrt_sigma_2, mp_perturbation.rs:111-139 --------------------
 // One diagonal block (nb <= 64) in shared memory: A_jj = L L^t in place (strict upper part zeroed) and
 // Linv = L^-1 (row-major nb x 64, lower triangular) for the panel solve  L_ij = A_ij L_jj^-t  as a GEMM.
