@@ -1001,11 +1001,14 @@ def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
 
 
 @pytest.mark.parametrize("n,q,s,B", [(64, 2**16, None, 1500), (24, 2**16, 300.0, 700), (8, 127, 70.0, 333), (5, 32, 10.0, 130)])
-def test_np_diag_kernels_bit_identical(T, monkeypatch, n, q, s, B):
-    """The diagonal-block kernel (one target per thread, 64 unrolled steps, lattice.cu np_diag2) against the
-    quad-per-two-targets kernel it replaced: same Philox counters, same order of floating-point operations per
-    (target, coordinate) => identical preimages.  Shapes: tensor-core recursion with fused digit planes (two-phase),
-    fp64 recursion with whole 256-blocks, dimensions that are not multiples of 64, a ragged last CTA."""
+def test_np_diag_kernels_agree(T, monkeypatch, n, q, s, B):
+    """The diagonal-block kernel (one target per thread, groups of 8 steps, lattice.cu np_diag2) against the
+    quad-per-two-targets kernel it replaced: same Philox counters and the same sequence of floating-point operations in
+    the recursion itself => the same preimages.  The rank-64 update of np_diag2 runs on the fp64 tensor path (DMMA), whose
+    summation order differs in the last bit of a centre: a rounding decision may flip for a handful of targets (each flip
+    changes the rest of that target's draws), so the requirement is >= 99 % identical preimages, all of them exact.
+    Shapes: tensor-core recursion with fused digit planes (two-phase), fp64 recursion with whole 256-blocks, dimensions
+    that are not multiples of 64, a ragged last CTA."""
     import math
 
     gp = T.GadgetParameters.init_default(n, q)
@@ -1024,7 +1027,8 @@ def test_np_diag_kernels_bit_identical(T, monkeypatch, n, q, s, B):
         psf._a_id = None
         outs.append(psf.samp_p_batch(a, td, u, seed=21))
         assert np.array_equal(O.f_a_classical_batch(a, outs[-1], q), u)
-    assert np.array_equal(outs[0], outs[1])
+    same = (outs[0] == outs[1]).all(axis=1).mean()
+    assert same >= 0.99, same
 
 
 def test_full_size_c2_properties(T):

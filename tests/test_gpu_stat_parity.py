@@ -213,6 +213,40 @@ def test_samp_p_gpv_marginals_vs_reference(T, n, q, s):
     assert moments_match((e.astype(np.float64) ** 2).sum(1), (ref.astype(np.float64) ** 2).sum(1))
 
 
+def test_samp_p_gpv_two_phase_marginals_vs_reference(T, monkeypatch):
+    """The two-phase form of the recursion (gadget preimage as centre, residual reduced modulo the [R;I]S' sub-lattice,
+    DESIGN 4.3) against the reference loop run with the pivot-column particular solution of gpv.rs:153-156, on the same
+    key and syndrome: every tested coordinate of e must have the same law.  n = 32, q = 2^16: m = 1049 > 1024, so the
+    tensor-core path and with it the two-phase form are active (checked: the one-pass form gives other preimages)."""
+    n, q, s = 32, 2**16, 330.0
+    monkeypatch.setenv("QF_OZAKI_MIN_DIM", "1024")
+    gp = T.GadgetParameters.init_default(n, q)
+    assert gp.m > 1024 and (n * gp.k) % 128 == 0
+    psf = T.PSFGPV(gp, s)
+    a, (sb, _) = psf.trap_gen(seed=n)
+    rng = np.random.default_rng(n + 1)
+    u1 = rng.integers(0, q, (1, n), dtype=np.int64)
+    n_gpu, n_ref = 120_000, 20_000
+    e = psf.samp_p_batch(a, (sb, None), np.tile(u1, (n_gpu, 1)), seed=5)
+    assert np.array_equal(O.f_a_classical_batch(a, e[:64], q), np.tile(u1, (64, 1)))
+    monkeypatch.setenv("QF_DISABLE_TWO_PHASE", "1")
+    psf1 = T.PSFGPV(gp, s)
+    psf1._install_a(a)
+    e1 = psf1.samp_p_batch(a, (sb, None), np.tile(u1, (256, 1)), seed=5)
+    assert not np.array_equal(e1, e[:256])
+    gso = O.gso_f64(sb.astype(np.float64))
+    piv, ainv = OC.unit_pivots(a, q)
+    ref = OC.samp_p_gpv(sb, gso, piv, ainv, np.tile(u1, (n_ref, 1)), q, s, 12345, OC.threads())
+    assert np.array_equal(O.f_a_classical_batch(a, ref[:16], q), np.tile(u1, (16, 1)))
+    bad = []
+    for j in _coords(gp.m, gp.m_bar, 20):
+        ok, chi, dof = chi2_two_sample(e[:, j], ref[:, j])
+        if not ok or not moments_match(e[:, j], ref[:, j]):
+            bad.append((j, chi, dof))
+    assert not bad, bad
+    assert moments_match((e.astype(np.float64) ** 2).sum(1), (ref.astype(np.float64) ** 2).sum(1))
+
+
 @pytest.mark.parametrize("n,q,r,s,structured", [(8, 64, 3.0, 25.0, False), (8, 64, 3.0, 25.0, True),
                                                  (16, 2**10, 4.0, 60.0, False), (16, 2**10, 4.0, 60.0, True)])
 def test_samp_p_perturbation_marginals_vs_reference(T, n, q, r, s, structured):

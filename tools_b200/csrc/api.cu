@@ -171,7 +171,10 @@ struct qf_ctx {
     // digit counts / windows of the contractions (U_22 updates, the two centre maps, U_11 updates).
     bool gadget_key_ok = false, two_phase = false;
     Dev dMt1l, dMt1scale, dMpl, dMpscale;
-    int mt1_limbs = 5, mt1_dlo = 1, u22_limbs = 5, u22_dlo = 2, u11_limbs = 5, u11_dlo = 1, mt1g_limbs = 4;
+    // Defaults from the error budget of DESIGN 4.2, checked at the full C2 key (scripts/ab_c2_precision.py, profiles/README_r2.md):
+    // four digits everywhere; the lowest digit sum is dropped where the operand has three digits (z2), not for the
+    // two-digit z1 (dropping it there moves 14 % of the preimages, keeping it 0.3 %).
+    int mt1_limbs = 4, mt1_dlo = 1, u22_limbs = 4, u22_dlo = 1, u11_limbs = 4, u11_dlo = 0, mt1g_limbs = 4;
     // digits / window / smallest compiled digit count of z for the update launches of the phase that is running
     int np_wdrop_cur = 0, np_dlo_cur = 2, np_lx_min = 3;
     int np_diag_variant = 0;
@@ -1862,6 +1865,7 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
     if (ctx->prm.kind == QF_PSF_PERTURBATION) return ctx->fail(QF_ERR_INVALID, "not a GPV context");
     ctx->has_np = false;  // stays false if anything below fails half-way (pivots / A^-1 / U are overwritten in place)
     ctx->two_phase = false;
+    ctx->u_limbs = 7;
     CK(cudaSetDevice(ctx->device));
     const long D = ctx->dim, ld = ctx->ld_dim;
     const bool ring = ctx->prm.kind == QF_PSF_GPV_RING;
@@ -1970,6 +1974,7 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
                 ctx->u11_limbs = lim(v[2], 1, ctx->u_limbs); ctx->u11_dlo = lim(v[3], 0, ctx->u11_limbs - 1);
                 ctx->mt1_limbs = lim(v[4], 1, 7); ctx->mt1_dlo = lim(v[5], 0, ctx->mt1_limbs - 1);
             }
+            ctx->u_limbs = std::max(ctx->u22_limbs, ctx->u11_limbs);  // digit planes of U that are built and kept
         }
         ctx->use_ozaki = D > std::max(min_dim, NP_SIZES[2]) && ctx->z_limbs + ctx->u_limbs - 1 <= 16 && !(env && env[0] == '1');
         if (ctx->two_phase && !ctx->use_ozaki) return ctx->fail(QF_ERR_NUMERIC, "internal: two-phase recursion without the tensor-core updates");

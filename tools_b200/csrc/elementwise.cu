@@ -628,24 +628,49 @@ namespace {
 __global__ void gadget_digits_kernel(const int64_t* __restrict__ h, long ldh, int8_t* __restrict__ plane, long ldk, int B,
                                      int n, int k, unsigned base, uint8_t* __restrict__ nz, int nz_kb_total,
                                      double* __restrict__ I2, long ldi) {
-    const long total = (long)B * n;
+    // one thread per four consecutive output digits (coalesced 4-byte / 32-byte stores); nk = n k is a multiple of 4 for
+    // every caller (the structured path needs nk % 128 == 0), ragged tails take the scalar branch
+    const int nk = n * k, nq = (nk + 3) >> 2;
+    const long total = (long)B * nq;
     const bool pow2 = (base & (base - 1)) == 0;
     const int sh = 31 - __clz(base);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long b = i / n;
-        const int blk = (int)(i - b * n);
-        unsigned long long v = (unsigned long long)h[b * ldh + blk];
-        int8_t* dst = plane + b * ldk + (long)blk * k;
-        for (int t = 0; t < k; ++t) {
-            unsigned d;
-            if (pow2) { d = (unsigned)(v & (base - 1)); v >>= sh; }
-            else { d = (unsigned)(v % base); v /= base; }
-            dst[t] = (int8_t)d;
-            if (I2) I2[b * ldi + (long)blk * k + t] = (double)d;
+        const long b = i / nq;
+        const int c0 = (int)(i - b * nq) << 2;
+        unsigned d[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            if (c >= nk) break;
+            const int blk = c / k, t = c - blk * k;
+            unsigned long long v = (unsigned long long)h[b * ldh + blk];
+            if (pow2) {
+                d[e] = (t * sh < 64) ? (unsigned)((v >> (t * sh)) & (base - 1)) : 0u;
+            } else {
+                for (int r = 0; r < t; ++r) v /= base;
+                d[e] = (unsigned)(v % base);
+            }
+        }
+        if (c0 + 3 < nk && ((ldk & 3) == 0)) {
+            *reinterpret_cast<unsigned*>(plane + b * ldk + c0) = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+            if (I2) {
+                double* o = I2 + b * ldi + c0;
+                if (((ldi & 1) == 0) && ((((uintptr_t)I2) & 15) == 0)) {
+                    reinterpret_cast<double2*>(o)[0] = make_double2((double)d[0], (double)d[1]);
+                    reinterpret_cast<double2*>(o)[1] = make_double2((double)d[2], (double)d[3]);
+                } else {
+                    for (int e = 0; e < 4; ++e) o[e] = (double)d[e];
+                }
+            }
+        } else {
+            for (int e = 0; e < 4 && c0 + e < nk; ++e) {
+                plane[b * ldk + c0 + e] = (int8_t)d[e];
+                if (I2) I2[b * ldi + c0 + e] = (double)d[e];
+            }
         }
     }
     if (nz) {  // plane 0 of the zero-tile map: every (128-target, 128-column) tile of the digit block is live
-        const int kbn = (n * k + 127) >> 7, mt = (B + 127) >> 7;
+        const int kbn = (nk + 127) >> 7, mt = (B + 127) >> 7;
         for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)mt * kbn; i += (long)gridDim.x * blockDim.x)
             nz[(i / kbn) * nz_kb_total + (i % kbn)] = 1;
     }
@@ -655,8 +680,8 @@ cudaError_t qf_launch_gadget_digits(const int64_t* h, long ldh, int8_t* plane, l
                                     uint8_t* nz, int nz_kb_total, cudaStream_t stream, double* I2, long ldi) {
     if (B <= 0) return cudaSuccess;
     if (base < 2 || base > 128) return cudaErrorInvalidValue;
-    gadget_digits_kernel<<<grid_for((long long)B * n, TPB), TPB, 0, stream>>>(h, ldh, plane, ldk, B, n, k, base, nz, nz_kb_total,
-                                                                              I2, ldi);
+    gadget_digits_kernel<<<grid_for((long long)B * ((n * k + 3) / 4), TPB), TPB, 0, stream>>>(h, ldh, plane, ldk, B, n, k, base, nz,
+                                                                                          nz_kb_total, I2, ldi);
     return cudaGetLastError();
 }
 cudaError_t qf_launch_pert_xb(const double* G, long ldg, double* X2, long ldx, int8_t* planes, long plane_stride, long ldk,

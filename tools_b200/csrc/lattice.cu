@@ -359,7 +359,17 @@ np_diag_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ld
 // produce bit-identical output (tested).  One CTA = 128 targets = one 128-target tile of the zero-tile map.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ND2_TPB = 128;
-constexpr int ND2_LD = 66;  // row stride (doubles) of the mu block / update panel in shared memory: even (16-byte rows)
+// Row strides (doubles) of the mu block / update panel and of the centre tile in shared memory: even (16-byte rows), and
+// 2 * stride = 16 mod 32 banks, so that the 8 x 4 DMMA fragment loads of the rank-64 update (rows fr = lane / 4 of
+// consecutive columns, k = lane % 4 of consecutive rows) take the minimal two wavefronts.
+constexpr int ND2_LD = 72;
+constexpr int ND2_ZLD = 136;
+
+__device__ __forceinline__ void nd2_dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(ND2_TPB, 2)
 np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long ldz, const double* __restrict__ U,
@@ -368,8 +378,8 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
                 int fuse_update, NpDigitOut dig) {
     extern __shared__ __align__(16) double nd2_sm[];
     double* ur = nd2_sm;             // ur[j * ND2_LD + i] = U[j0 + j][j0 + i] (i > j), later the panel pan[i * ND2_LD + c]
-    double* cs = ur + 64 * ND2_LD;   // cs[i * ND2_TPB + tid]: centres, overwritten by z as the recursion proceeds
-    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(cs + 64 * ND2_TPB);
+    double* cs = ur + 64 * ND2_LD;   // cs[i * ND2_ZLD + tid]: centres, overwritten by z as the recursion proceeds
+    DGaussParams* dgs = reinterpret_cast<DGaussParams*>(cs + 64 * ND2_ZLD);
     const int tid = threadIdx.x, lane = tid & 31;
     const long b0 = (long)blockIdx.x * ND2_TPB, b = b0 + tid;
     const bool live = b < B;
@@ -399,11 +409,11 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
 #pragma unroll 8
                 for (int i = 0; i < 32; ++i) {
                     const double2 v = reinterpret_cast<const double2*>(tr)[i];
-                    cst[(2 * i) * ND2_TPB] = v.x;
-                    cst[(2 * i + 1) * ND2_TPB] = v.y;
+                    cst[(2 * i) * ND2_ZLD] = v.x;
+                    cst[(2 * i + 1) * ND2_ZLD] = v.y;
                 }
             } else {
-                for (int i = 0; i < 64; ++i) cst[i * ND2_TPB] = (live && i < nbe) ? tr[i] : 0.0;
+                for (int i = 0; i < 64; ++i) cst[i * ND2_ZLD] = (live && i < nbe) ? tr[i] : 0.0;
             }
         }
         const float4* pq = prop + (long)(j0 - prop0) * ldprop + b;
@@ -421,7 +431,7 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
             if (ig < nbe) {  // uniform
                 double c8[8], z8[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) c8[t] = cst[(ig + t) * ND2_TPB];
+                for (int t = 0; t < 8; ++t) c8[t] = cst[(ig + t) * ND2_ZLD];
 #pragma unroll
                 for (int t = 7; t >= 0; --t) {
                     double zz = 0.0;
@@ -454,11 +464,11 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
                     z8[t] = zz;
                 }
 #pragma unroll
-                for (int t = 0; t < 8; ++t) cst[(ig + t) * ND2_TPB] = z8[t];
+                for (int t = 0; t < 8; ++t) cst[(ig + t) * ND2_ZLD] = z8[t];
                 // rank-8 update of the lower coordinates, in the order of the one-step-at-a-time recursion (t descending)
 #pragma unroll 8
                 for (int j = 0; j < ig; ++j) {
-                    double cj = cst[j * ND2_TPB];
+                    double cj = cst[j * ND2_ZLD];
                     const double2* up = reinterpret_cast<const double2*>(ur + j * ND2_LD + ig);  // warp-wide broadcasts
                     const double2 u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
                     cj = fma(-u67.y, z8[7], cj);
@@ -469,7 +479,7 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
                     cj = fma(-u23.x, z8[2], cj);
                     cj = fma(-u01.y, z8[1], cj);
                     cj = fma(-u01.x, z8[0], cj);
-                    cst[j * ND2_TPB] = cj;
+                    cst[j * ND2_ZLD] = cj;
                 }
             }
 #pragma unroll
@@ -478,7 +488,7 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
         // the tile now holds z: Z, digit planes
         double c[64];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) c[i] = cst[i * ND2_TPB];
+        for (int i = 0; i < 64; ++i) c[i] = cst[i * ND2_ZLD];
         if (live) {
             double* zr = Z + b * ldz + j0;
             if (nbe == 64 && ((((uintptr_t)zr) & 15) == 0)) {
@@ -534,9 +544,12 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
         }
         // rank-nb update of the columns [up_lo, j0) of the enclosing block for this CTA's own targets:
         //   T[b][col] -= sum_i z_i U[col][j0 + i],  the panel of U through shared memory 64 columns at a time
-        // (the next panel is fetched into registers while the current one is being multiplied, and the old values of T are
-        // requested before the 64-step accumulation: with 4-8 warps per SM nothing else would hide those latencies)
+        // On the fp64 tensor path (mma.sync m8n8k4): a warp owns its 32 targets x 64 columns as 4 x 8 DMMA tiles, A = z from the
+        // centre tile, B = the panel, both read as fragments from shared memory (12 loads per 32 MMAs; the CUDA-core form needs
+        // one broadcast load per two FMAs and was bound by exactly those loads).  The next panel is fetched into registers while
+        // the current one is being multiplied.
         const int pj = tid >> 6, pi = tid & 63;  // this thread's panel elements: columns pj + 2 r, row pi (coalesced along i)
+        const int wrp = tid >> 5, fr = lane >> 2, fc = lane & 3;
         double pv[32];
         auto load_panel = [&](int c0, int ncol) {
 #pragma unroll
@@ -553,35 +566,42 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
             for (int r = 0; r < 32; ++r) ur[pi * ND2_LD + pj + 2 * r] = pv[r];
             __syncthreads();
             if (c0 + 64 < j0) load_panel(c0 + 64, min(64, j0 - c0 - 64));
-            for (int cg = 0; cg < ncol; cg += 16) {
-                double2* tr = reinterpret_cast<double2*>(T + b * ldt + c0 + cg);
-                double2 told[8];
+            double acc[4][8][2];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) told[t] = (live && cg + 2 * t < ncol) ? tr[t] : make_double2(0.0, 0.0);
-                double acc[16];
+            for (int rt = 0; rt < 4; ++rt)
 #pragma unroll
-                for (int t = 0; t < 16; ++t) acc[t] = 0.0;
-                const double2* pan = reinterpret_cast<const double2*>(ur + cg);
-#pragma unroll 4
-                for (int i = 0; i < 64; ++i) {
-                    const double zi = cst[i * ND2_TPB];
+                for (int ct = 0; ct < 8; ++ct) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+            const double* ap = cs + fc * ND2_ZLD + wrp * 32 + fr;   // A[row = target][k = i] = z_i(target)
+            const double* bp = ur + fc * ND2_LD + fr;               // B[k = i][n = column] = U[c0 + column][j0 + i]
+#pragma unroll 2
+            for (int kk = 0; kk < 16; ++kk) {
+                double a[4], bb[8];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const double2 u = pan[i * (ND2_LD / 2) + t];  // warp-wide broadcast, two columns per load
-                        acc[2 * t] = fma(zi, u.x, acc[2 * t]);
-                        acc[2 * t + 1] = fma(zi, u.y, acc[2 * t + 1]);
-                    }
-                }
-                if (live) {
+                for (int rt = 0; rt < 4; ++rt) a[rt] = ap[kk * 4 * ND2_ZLD + rt * 8];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (cg + 2 * t < ncol) {
-                            double2 v = told[t];
-                            v.x -= acc[2 * t];
-                            v.y -= acc[2 * t + 1];
-                            tr[t] = v;
+                for (int ct = 0; ct < 8; ++ct) bb[ct] = bp[kk * 4 * ND2_LD + ct * 8];
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt)
+#pragma unroll
+                    for (int ct = 0; ct < 8; ++ct) nd2_dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], bb[ct]);
+            }
+            // C fragment: rows 8 rt + fr, columns 8 ct + 2 fc, + 1
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const long row = b0 + wrp * 32 + rt * 8 + fr;
+                if (row < B) {
+                    double2* tr = reinterpret_cast<double2*>(T + row * ldt + c0 + 2 * fc);
+                    double2 v[8];
+#pragma unroll
+                    for (int ct = 0; ct < 8; ++ct)
+                        if (8 * ct + 2 * fc < ncol) v[ct] = tr[4 * ct];
+#pragma unroll
+                    for (int ct = 0; ct < 8; ++ct)
+                        if (8 * ct + 2 * fc < ncol) {
+                            v[ct].x -= acc[rt][ct][0];
+                            v[ct].y -= acc[rt][ct][1];
+                            tr[4 * ct] = v[ct];
                         }
-                    }
                 }
             }
         }
@@ -662,7 +682,7 @@ cudaError_t qf_launch_np_diag(double* T, long ldt, double* Z, long ldz, const do
     const bool v2_ok = (!dig || (((d.ldk & 15) == 0) && ((((uintptr_t)d.planes) & 15) == 0) && ((d.plane_stride & 15) == 0))) &&
                        (ldt & 1) == 0 && ((((uintptr_t)T) & 15) == 0) && ((up_lo & 1) == 0);
     if (!v1 && v2_ok) {
-        const size_t smem2 = (size_t)(64 * ND2_LD + 64 * ND2_TPB) * sizeof(double) + 64 * sizeof(DGaussParams);
+        const size_t smem2 = (size_t)(64 * ND2_LD + 64 * ND2_ZLD) * sizeof(double) + 64 * sizeof(DGaussParams);
         static size_t configured2_dev[QF_MAX_DEVICES] = {};
         size_t& configured2 = configured2_dev[qf_device_slot()];
         if (smem2 > configured2) {
