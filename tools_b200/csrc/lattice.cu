@@ -364,6 +364,7 @@ constexpr int ND2_TPB = 128;
 // consecutive columns, k = lane % 4 of consecutive rows) take the minimal two wavefronts.
 constexpr int ND2_LD = 72;
 constexpr int ND2_ZLD = 136;
+constexpr int ND2_PLD = 68;  // update panel, stored [column][i]: coalesced conflict-free staging stores, two-wavefront B fragments
 
 __device__ __forceinline__ void nd2_dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -563,23 +564,32 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
             const int ncol = min(64, j0 - c0);
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < 32; ++r) ur[pi * ND2_LD + pj + 2 * r] = pv[r];
+            for (int r = 0; r < 32; ++r) ur[(pj + 2 * r) * ND2_PLD + pi] = pv[r];
             __syncthreads();
             if (c0 + 64 < j0) load_panel(c0 + 64, min(64, j0 - c0 - 64));
+            // the accumulators START as the old values of T (requested here, 32 loads in flight per lane, and only needed when
+            // the first MMA of their tile issues) and A = -z: T - sum_i z_i U is what the MMAs leave behind, stored as is
             double acc[4][8][2];
 #pragma unroll
-            for (int rt = 0; rt < 4; ++rt)
+            for (int rt = 0; rt < 4; ++rt) {
+                const long row = b0 + wrp * 32 + rt * 8 + fr;
+                const double2* tr = reinterpret_cast<const double2*>(T + row * ldt + c0 + 2 * fc);
 #pragma unroll
-                for (int ct = 0; ct < 8; ++ct) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
-            const double* ap = cs + fc * ND2_ZLD + wrp * 32 + fr;   // A[row = target][k = i] = z_i(target)
-            const double* bp = ur + fc * ND2_LD + fr;               // B[k = i][n = column] = U[c0 + column][j0 + i]
+                for (int ct = 0; ct < 8; ++ct) {
+                    const double2 v = (row < B && 8 * ct + 2 * fc < ncol) ? tr[4 * ct] : make_double2(0.0, 0.0);
+                    acc[rt][ct][0] = v.x;
+                    acc[rt][ct][1] = v.y;
+                }
+            }
+            const double* ap = cs + fc * ND2_ZLD + wrp * 32 + fr;   // A[row = target][k = i] = -z_i(target)
+            const double* bp = ur + fr * ND2_PLD + fc;              // B[k = i][n = column] = U[c0 + column][j0 + i]
 #pragma unroll 2
             for (int kk = 0; kk < 16; ++kk) {
                 double a[4], bb[8];
 #pragma unroll
-                for (int rt = 0; rt < 4; ++rt) a[rt] = ap[kk * 4 * ND2_ZLD + rt * 8];
+                for (int rt = 0; rt < 4; ++rt) a[rt] = -ap[kk * 4 * ND2_ZLD + rt * 8];
 #pragma unroll
-                for (int ct = 0; ct < 8; ++ct) bb[ct] = bp[kk * 4 * ND2_LD + ct * 8];
+                for (int ct = 0; ct < 8; ++ct) bb[ct] = bp[ct * 8 * ND2_PLD + kk * 4];
 #pragma unroll
                 for (int rt = 0; rt < 4; ++rt)
 #pragma unroll
@@ -591,17 +601,9 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
                 const long row = b0 + wrp * 32 + rt * 8 + fr;
                 if (row < B) {
                     double2* tr = reinterpret_cast<double2*>(T + row * ldt + c0 + 2 * fc);
-                    double2 v[8];
 #pragma unroll
                     for (int ct = 0; ct < 8; ++ct)
-                        if (8 * ct + 2 * fc < ncol) v[ct] = tr[4 * ct];
-#pragma unroll
-                    for (int ct = 0; ct < 8; ++ct)
-                        if (8 * ct + 2 * fc < ncol) {
-                            v[ct].x -= acc[rt][ct][0];
-                            v[ct].y -= acc[rt][ct][1];
-                            tr[4 * ct] = v[ct];
-                        }
+                        if (8 * ct + 2 * fc < ncol) tr[4 * ct] = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
                 }
             }
         }
