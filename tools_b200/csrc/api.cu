@@ -127,9 +127,10 @@ struct qf_ctx {
     std::vector<int64_t> hAring;
     // workspace
     Dev w[12];  // (w[10]: digit planes of the particular solution)
-    Dev dNorm, dFlag, dRetry, io_a, io_b, io_c, io_a2, io_h[2];
+    Dev dNorm, dFlag, dRetry, io_a, io_b, io_b2, io_c, io_a2, io_h[2];
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_u_in[2] = {nullptr, nullptr}, ev_u_used[2] = {nullptr, nullptr};
     // tcgen05 int8 path for the exact integer contractions
     bool use_i8 = true;
     bool fused_fa = true;  // f_a: digit split fused into the contraction (gemm_i8_fused.cu)
@@ -1013,9 +1014,12 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
         QF_TRY(gemm_i8_gated(ctx, g, gate_z2));
     }
     // ---- g3 = digits(h): one s8 plane (the x operand of its centre map) and, as fp64, the start of e_bot = g3 + S' z1
+    // (fused tail: e_bot is formed in one pass from z1 and the g3 plane -- needs 16-byte aligned int32 rows; otherwise e_bot is
+    // accumulated in fp64 as in the one-pass form)
+    const bool fused_tail = (nk & 3) == 0 && (mb & 3) == 0 && (D & 3) == 0 && (ldk_nk & 3) == 0;
     double* I2 = ctx->w[4].as<double>();
-    LAUNCH(qf_launch_gadget_digits(H, n, gp, ldk_nk, Bc, (int)n, (int)ctx->k, (unsigned)ctx->prm.base, nullptr, 0, ctx->stream, I2,
-                                   ldnk));
+    LAUNCH(qf_launch_gadget_digits(H, n, gp, ldk_nk, Bc, (int)n, (int)ctx->k, (unsigned)ctx->prm.base, nullptr, 0, ctx->stream,
+                                   fused_tail ? nullptr : I2, ldnk));
     // ---- centres of phase 2 in GSO coordinates: T[:, 0:nk] = -M' g3 - Mt_1 z2, two launches:
     // (a) M' g3 (M' = U_11 S'^-1, entries <= 1/2, block triangular: the k blocks outside the triangle are skipped
     //     in-kernel), one digit of 0 .. base-1 against four digits: store-only epilogue;
@@ -1051,12 +1055,18 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
     QF_TRY(np_block(ctx, T, Z, Bc, 0, nk, NP_TOP, 0, seed, first));
 
     // ---- e_bot = g3 + S' z1,  e_top = z2 + R e_bot
-    LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev, ctx->stream));
     const long plane2 = C * ldk_nk;
     CK(ctx->w[2].ensure((size_t)std::max<long>(ctx->i2_limbs * plane2, C * ldD * 8)));  // T is dead: digits of e_bot
     int8_t* ip = ctx->w[2].as<int8_t>();
-    LAUNCH(qf_launch_split_f64_limbs(I2, ldnk, ip, plane2, ldk_nk, Bc, (int)nk, ctx->i2_limbs, flag, nullptr, 0, 0, 0,
-                                     ctx->stream));
+    if (fused_tail) {
+        LAUNCH(qf_launch_gpv_ebot(Z, ldD, gp, ldk_nk, dE, D, (int)mb, ip, plane2, ldk_nk, ctx->i2_limbs, Bc, (int)nk, (int)ctx->k,
+                                  ctx->dSkf.as<double>(), ctx->gpv_rev, flag, ctx->stream));
+    } else {
+        LAUNCH(qf_launch_sprime_apply(Z, ldD, I2, ldnk, Bc, (int)nk, (int)ctx->k, ctx->dSkf.as<double>(), ctx->gpv_rev,
+                                      ctx->stream));
+        LAUNCH(qf_launch_split_f64_limbs(I2, ldnk, ip, plane2, ldk_nk, Bc, (int)nk, ctx->i2_limbs, flag, nullptr, 0, 0, 0,
+                                         ctx->stream));
+    }
     {
         I8GemmArgs h{};
         h.x = ip; h.ldx = ldk_nk; h.x_plane = plane2;
@@ -1067,7 +1077,8 @@ qf_status samp_p_np2_chunk(qf_ctx* ctx, const int64_t* dUin, int Bc, uint64_t se
         h.flag = flag;
         LAUNCH(ctx_gemm_i8(ctx, h));
     }
-    LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, (int)nk, flag, ctx->stream));
+    // e_top += z2 (and, unfused, e_bot from its fp64 form)
+    LAUNCH(qf_launch_gpv_struct_finalize(dE, D, Z + nk, ldD, I2, ldnk, Bc, (int)mb, fused_tail ? 0 : (int)nk, flag, ctx->stream));
     return QF_OK;
 }
 
@@ -1559,6 +1570,8 @@ void qf_ctx_destroy(qf_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_u_in[i]) cudaEventDestroy(ctx->ev_u_in[i]);
+        if (ctx->ev_u_used[i]) cudaEventDestroy(ctx->ev_u_used[i]);
     }
     for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
@@ -2426,19 +2439,36 @@ static qf_status samp_p_host(qf_ctx* ctx, const int64_t* u, int64_t batch, uint6
     CK(ctx->io_b.ensure((size_t)C * ctx->n * 8));
     CK(ctx->io_a.ensure((size_t)C * ctx->dim * 4));
     if (i16) CK(ctx->io_h[0].ensure((size_t)C * ctx->dim * 2));
-    // results leave through a second stream: the device->host copy of chunk i overlaps the computation of
-    // chunk i+1 (two result buffers, events in both directions)
+    // Both directions of the host traffic run on a second stream: the device->host copy of chunk i and the host->device
+    // copy of the targets of chunk i+1 overlap the computation (two result buffers, two target buffers, events in both
+    // directions); only the first chunk's targets and the last chunk's results are exposed.
     const bool overlap = batch > C;
     if (overlap) {
         if (i16) CK(ctx->io_h[1].ensure((size_t)C * ctx->dim * 2));
         else CK(ctx->io_a2.ensure((size_t)C * ctx->dim * 4));
+        CK(ctx->io_b2.ensure((size_t)C * ctx->n * 8));
         if (!ctx->copy_stream) {
             CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) {
                 CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_u_in[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_u_used[i], cudaEventDisableTiming));
             }
         }
+    }
+    // chunk boundaries (the same balanced split as for_chunks)
+    const int64_t nch = std::max<int64_t>(1, (batch + C - 1) / C);
+    const int64_t per = std::min<int64_t>(C, ((batch + nch - 1) / nch + 127) / 128 * 128);
+    auto u_buf = [&](int64_t i) { return (overlap && (i & 1)) ? ctx->io_b2.as<int64_t>() : ctx->io_b.as<int64_t>(); };
+    auto copy_u = [&](int64_t i, cudaStream_t st) -> qf_status {
+        const int64_t b0 = i * per, Bc = std::min<int64_t>(per, batch - b0);
+        CK(cudaMemcpyAsync(u_buf(i), u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, st));
+        return QF_OK;
+    };
+    if (overlap) {
+        QF_TRY(copy_u(0, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_u_in[0], ctx->copy_stream));
     }
     int64_t idx = 0;
     QF_TRY(for_chunks(ctx, batch, [&](int64_t b0, int Bc) -> qf_status {
@@ -2447,13 +2477,23 @@ static qf_status samp_p_host(qf_ctx* ctx, const int64_t* u, int64_t batch, uint6
         // buffer serves both slots
         int32_t* dres = (!i16 && overlap && slot) ? ctx->io_a2.as<int32_t>() : ctx->io_a.as<int32_t>();
         if (overlap && idx >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));  // buffer free again?
-        CK(cudaMemcpyAsync(ctx->io_b.p, u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (overlap) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_u_in[slot], 0));  // this chunk's targets have arrived
+            if (b0 + Bc < batch) {  // the next chunk's targets, as soon as the computation that read that buffer is done
+                if (idx >= 1) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_u_used[slot ^ 1], 0));
+                QF_TRY(copy_u(idx + 1, ctx->copy_stream));
+                CK(cudaEventRecord(ctx->ev_u_in[slot ^ 1], ctx->copy_stream));
+            }
+        } else {
+            CK(cudaMemcpyAsync(u_buf(idx), u + b0 * ctx->n, (size_t)Bc * ctx->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        const int64_t* du = u_buf(idx);
         // the targets must be residues in [0, q): checked on the device (a host loop over batch x n values would sit in
         // front of every call), reported by check_flag as QF_ERR_INVALID
-        LAUNCH(qf_launch_range_check_i64(ctx->io_b.as<int64_t>(), (size_t)Bc * ctx->n, ctx->prm.q, ctx->dFlag.as<int>(), ctx->stream));
-        QF_TRY(ctx->prm.kind == QF_PSF_PERTURBATION
-                   ? samp_p_pert_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres)
-                   : samp_p_np_chunk(ctx, ctx->io_b.as<int64_t>(), Bc, seed, first + (uint64_t)b0, dres));
+        LAUNCH(qf_launch_range_check_i64(du, (size_t)Bc * ctx->n, ctx->prm.q, ctx->dFlag.as<int>(), ctx->stream));
+        QF_TRY(ctx->prm.kind == QF_PSF_PERTURBATION ? samp_p_pert_chunk(ctx, du, Bc, seed, first + (uint64_t)b0, dres)
+                                                    : samp_p_np_chunk(ctx, du, Bc, seed, first + (uint64_t)b0, dres));
+        if (overlap) CK(cudaEventRecord(ctx->ev_u_used[slot], ctx->stream));
         const void* src = dres;
         if (i16) {
             int16_t* d16 = ctx->io_h[overlap ? slot : 0].as<int16_t>();

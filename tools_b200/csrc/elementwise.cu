@@ -609,6 +609,67 @@ __global__ void gpv_struct_finalize_kernel(int32_t* __restrict__ e, long lde, co
     }
 }
 }  // namespace
+namespace {
+// e_bot = g3 + S' z1 in one pass (two-phase form, api.cu samp_p_np2_chunk): four consecutive gadget rows per thread;
+// writes the int32 values into e[b][mb + row] and their balanced base-256 digit planes (the x operand of R e_bot).
+__global__ void gpv_ebot_kernel(const double* __restrict__ Z, long ldz, const int8_t* __restrict__ g3, long ldg,
+                                int32_t* __restrict__ e, long lde, int mb, int8_t* __restrict__ planes, long plane_stride,
+                                long ldk, int L, int B, int nk, int k, const double* __restrict__ sk, int reversed, int* flag) {
+    const int nq = nk >> 2;
+    const long total = (long)B * nq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / nq;
+        const int r0 = (int)(i - b * nq) << 2;
+        const double* zr = Z + b * ldz;
+        const unsigned gw = *reinterpret_cast<const unsigned*>(g3 + b * ldg + r0);
+        long long v[4];
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+            const int row = r0 + t4, blk = row / k, t = row - blk * k;
+            double acc = (double)(int8_t)((gw >> (8 * t4)) & 255);
+            const int cand[3] = {t - 1, t, k - 1};
+#pragma unroll
+            for (int c3 = 0; c3 < 3; ++c3) {
+                const int c = cand[c3];
+                if (c < 0 || (c3 == 2 && (c == t || c == t - 1))) continue;
+                const double sv = sk[t * k + c];
+                if (sv == 0.0) continue;
+                const int cc = blk * k + c;
+                acc = fma(sv, zr[reversed ? nk - 1 - cc : cc], acc);
+            }
+            if (!(fabs(acc) < 2147483647.0)) { if (flag) atomicOr(flag, 4); acc = 0.0; }
+            v[t4] = __double2ll_rn(acc);
+        }
+        *reinterpret_cast<int4*>(e + b * lde + mb + r0) = make_int4((int)v[0], (int)v[1], (int)v[2], (int)v[3]);
+        for (int l = 0; l < L; ++l) {
+            unsigned pk = 0;
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+                long long d = ((v[t4] + 128) & 255) - 128;
+                if (l == L - 1) {
+                    d = v[t4];
+                    if (d > 127 || d < -128) { if (flag) atomicOr(flag, 8); d = 0; }
+                }
+                v[t4] = (v[t4] - d) >> 8;
+                pk |= (unsigned)(d & 255) << (8 * t4);
+            }
+            *reinterpret_cast<unsigned*>(planes + (long)l * plane_stride + b * ldk + r0) = pk;
+        }
+    }
+}
+}  // namespace
+cudaError_t qf_launch_gpv_ebot(const double* Z, long ldz, const int8_t* g3, long ldg, int32_t* e, long lde, int mb,
+                               int8_t* planes, long plane_stride, long ldk, int L, int B, int nk, int k, const double* sk,
+                               int reversed, int* flag, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    // four rows per thread, 16-byte int32 stores, 4-byte digit stores
+    if ((nk & 3) || (ldg & 3) || (ldk & 3) || (plane_stride & 3) || (lde & 3) || (mb & 3) || (((uintptr_t)e) & 15) ||
+        (((uintptr_t)g3) & 3) || (((uintptr_t)planes) & 3))
+        return cudaErrorInvalidValue;
+    gpv_ebot_kernel<<<grid_for((long long)B * (nk / 4), TPB), TPB, 0, stream>>>(Z, ldz, g3, ldg, e, lde, mb, planes, plane_stride,
+                                                                               ldk, L, B, nk, k, sk, reversed, flag);
+    return cudaGetLastError();
+}
 cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long ldi, int B, int nk, int k, const double* sk,
                                    int reversed, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;

@@ -61,6 +61,10 @@ cudaError_t qf_launch_sprime_apply(const double* Z, long ldz, double* I2, long l
 cudaError_t qf_launch_gpv_struct_finalize(int32_t* e, long lde, const double* Z2, long ldz, const double* I2, long ldi, int B,
                                           int mb, int nk, int* flag, cudaStream_t stream, const int8_t* g3 = nullptr,
                                           long ldg = 0);
+// two-phase form: e_bot = g3 + S' z1 written as int32 into e[b][mb + row] and as L balanced digit planes (one pass over z1)
+cudaError_t qf_launch_gpv_ebot(const double* Z, long ldz, const int8_t* g3, long ldg, int32_t* e, long lde, int mb,
+                               int8_t* planes, long plane_stride, long ldk, int L, int B, int nk, int k, const double* sk,
+                               int reversed, int* flag, cudaStream_t stream);
 // two-phase nearest plane (api.cu samp_p_np2_chunk): base-b digits of the syndromes h (B x n, in [0,q)) in gadget order,
 // g3[b][blk*k + t] = digit t of h[b][blk], written as ONE s8 digit plane (B x ldk, columns [0, n*k)) and marked in
 // plane 0 of the zero-tile map (k blocks [0, ceil(n*k/128)) of every target tile)
