@@ -1,5 +1,4 @@
 set -x
-python scripts/d2h_probe.py 2>&1 | tail -6
-QF_CHUNK=18944 timeout 900 python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/r2_np14_bench.json 2> gpurun_out/r2_np14_bench.log
-python -c "
-import json; d=json.load(open('gpurun_out/r2_np14_bench.json')); print('chunk18944', d['value'], d['e2e']['value'], d['ms_per_step'])"
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r2_final.csv python scripts/prof_step.py c2 37888 1 > gpurun_out/r2_prof_final.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:np_diag2 -s 30 -c 1 -o gpurun_out/prof_npdiag2_r2 -f python scripts/prof_step.py c2 37888 1 > gpurun_out/ncu_np2_r2.log 2>&1
+QF_TRACE=1 timeout 300 python scripts/prof_step.py c2 37888 1 > gpurun_out/r2_final_trace.log 2>&1
