@@ -73,7 +73,9 @@ void qf_ctx_destroy(qf_ctx* ctx);
 const char* qf_last_error(const qf_ctx* ctx);
 /* run on a caller-owned CUDA stream (cudaStream_t); NULL = the context's own stream */
 qf_status qf_set_stream(qf_ctx* ctx, void* cuda_stream);
-/* targets processed per internal chunk (bounds the workspace); 0 = default */
+/* targets processed per internal chunk (bounds the workspace); 0 = default.  The default keeps the work matrices of
+ * samp_p within ~32 GB of device memory (PSFGPV n = 256, q = 2^24: 37 888 targets = two waves of 148 SMs x 128 targets);
+ * smaller chunks trade throughput for memory (one wave: -9 % at that size). */
 qf_status qf_set_chunk(qf_ctx* ctx, int64_t targets_per_chunk);
 qf_status qf_synchronize(qf_ctx* ctx);
 /* number of kernels this context has launched so far */
