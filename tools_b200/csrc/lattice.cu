@@ -385,6 +385,7 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
     const long b0 = (long)blockIdx.x * ND2_TPB, b = b0 + tid;
     const bool live = b < B;
     double* const cst = cs + tid;
+    bool tile_on_chip = false;  // the centre tile of this block was left in shared memory by the previous block's update
     for (int sub_hi = j_hi; sub_hi > j_lo;) {
         const int j0 = max(j_lo, (sub_hi - 1) / 64 * 64), nb = sub_hi - j0;
         const int up_lo = fuse_update ? j_lo : j0;
@@ -404,7 +405,9 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
         }
         for (int i = tid; i < 64; i += ND2_TPB) dgs[i] = i < nbe ? dg_g[j0 + i] : DGaussParams{0.f, 0.f, 0.f, 0.f};
         // this target's centres -> its column of the tile
-        {
+        const bool have_tile = tile_on_chip;
+        tile_on_chip = false;
+        if (!have_tile) {
             const double* tr = T + b * ldt + j0;
             if (live && nbe == 64 && ((((uintptr_t)tr) & 15) == 0)) {
 #pragma unroll 8
@@ -596,14 +599,29 @@ np_diag2_kernel(double* __restrict__ T, long ldt, double* __restrict__ Z, long l
                     for (int ct = 0; ct < 8; ++ct) nd2_dmma884(acc[rt][ct][0], acc[rt][ct][1], a[rt], bb[ct]);
             }
             // C fragment: rows 8 rt + fr, columns 8 ct + 2 fc, + 1
+            if (c0 + 64 == j0) {
+                // the 64 columns just below this block ARE the next diagonal block: their updated centres go straight into
+                // the (now dead: every panel has been multiplied) centre tile instead of through HBM and back
+                __syncwarp();  // a warp only reads / writes the tile columns of its own 32 targets
 #pragma unroll
-            for (int rt = 0; rt < 4; ++rt) {
-                const long row = b0 + wrp * 32 + rt * 8 + fr;
-                if (row < B) {
-                    double2* tr = reinterpret_cast<double2*>(T + row * ldt + c0 + 2 * fc);
+                for (int rt = 0; rt < 4; ++rt)
 #pragma unroll
-                    for (int ct = 0; ct < 8; ++ct)
-                        if (8 * ct + 2 * fc < ncol) tr[4 * ct] = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
+                    for (int ct = 0; ct < 8; ++ct) {
+                        double* dst = cs + (8 * ct + 2 * fc) * ND2_ZLD + wrp * 32 + rt * 8 + fr;
+                        dst[0] = acc[rt][ct][0];
+                        dst[ND2_ZLD] = acc[rt][ct][1];
+                    }
+                tile_on_chip = true;
+            } else {
+#pragma unroll
+                for (int rt = 0; rt < 4; ++rt) {
+                    const long row = b0 + wrp * 32 + rt * 8 + fr;
+                    if (row < B) {
+                        double2* tr = reinterpret_cast<double2*>(T + row * ldt + c0 + 2 * fc);
+#pragma unroll
+                        for (int ct = 0; ct < 8; ++ct)
+                            if (8 * ct + 2 * fc < ncol) tr[4 * ct] = make_double2(acc[rt][ct][0], acc[rt][ct][1]);
+                    }
                 }
             }
         }
