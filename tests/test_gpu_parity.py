@@ -949,13 +949,14 @@ def test_device_entry_points_and_midsize(T):
     assert psf.ctx.launch_count() > 0
 
 
-@pytest.mark.parametrize("n,q", [(40, 2**16), (64, 2**16), (128, 2**12)])
+@pytest.mark.parametrize("n,q", [(40, 2**16), (64, 2**16), (128, 2**12), (64, 4093)])
 def test_gpv_tensor_core_updates_match_fp64_path(T, monkeypatch, n, q):
     """The fixed-point (int8 tcgen05) nearest-plane updates against the fp64 DMMA path on the same key and
     seed: both must give exact preimages with the same second moment; with identical Philox streams almost
     every preimage is identical (centres agree to ~2^-40).  m = 1316: digits and S z only; m = 2084 = 2 * 1024 + 36:
     one tensor-core update whose block has absorbed the thin ragged top (K = 1060); m = 3121 = 3 * 1024 + 49: two
-    updates (K = 1073 with the merged top, then K = 1024)."""
+    updates (K = 1073 with the merged top, then K = 1024); q = 4093 (not a power of the base): the gadget block S_k carries
+    the digits of q, S' is not column-reversed and the gadget centre map M' is triangular the other way round."""
     import math
 
     gp = T.GadgetParameters.init_default(n, q)
