@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""A/B of the two diagonal-block kernels (np_diag2 against the quad kernel, QF_NP_DIAG_V1=1) on a few shapes: prints the
+number of targets whose preimages differ (same key, same seed): python scripts/ab_np_diag.py"""
 import os, sys, math
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
