@@ -504,6 +504,26 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                             for (int c = 0; c < 16; ++c) v[c] += (long long)t[c] * (1ll << (8 * d));
                         }
+                        // int32 store of a whole 16-column group: four 16-byte stores per row instead of sixteen 4-byte ones
+                        // (a thread owns a ROW: every store instruction of the warp touches 32 different lines, so the
+                        // instruction count is what the LSU sees)
+                        if (row < p.B && p.out_kind == 1 && n0 + c0 + 16 <= p.N && (p.ldout & 3) == 0 &&
+                            ((((uintptr_t)p.out) & 15) == 0)) {
+                            int o[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                long long val = p.sign < 0 ? -v[c] : v[c];
+                                if (val > 2147483647 || val < -2147483647) {
+                                    if (p.flag) atomicOr(p.flag, 4);
+                                    val = 0;
+                                }
+                                o[c] = (int)val;
+                            }
+                            int4* dst = reinterpret_cast<int4*>((int32_t*)p.out + (long)row * p.ldout + n0 + c0);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) dst[c] = make_int4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                            continue;
+                        }
                         if (row < p.B) {
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
