@@ -1976,6 +1976,8 @@ qf_status qf_set_trapdoor_gpv(qf_ctx* ctx, const int64_t* s, const double* sg) {
         ctx->two_phase = ctx->gpv_struct && ctx->gadget_key_ok && D > std::max(min_dim, NP_SIZES[2]) &&
                          !(env && env[0] == '1') && !(env2 && env2[0] == '1');
         if (ctx->two_phase) {
+            // the gadget digits g3 reach base - 1: one more digit of M' for bases above 4 (its error scales with |g3|)
+            ctx->mt1g_limbs = ctx->prm.base > 4 ? 5 : 4;
             ctx->z_limbs = limbs_for(64.0 * ctx->prm.s / std::sqrt(dmin));
             ctx->zlimit = std::min(std::ldexp(1.0, 52), limb_capacity(ctx->z_limbs));
             if (const char* cfg = getenv("QF_NP2_CFG")) {  // experiments: "u22,dlo,u11,dlo,mt1,dlo[,mt1g]"
