@@ -93,3 +93,27 @@ def test_two_phase_identities_and_equivalence_under_common_random_numbers(n, q):
         assert np.array_equal((a @ e) % q, u)
         # the same preimage
         assert np.array_equal(e, e_ref), (trial, np.abs(e - e_ref).max())
+
+
+def test_balanced_digit_bias_identity():
+    """np_diag2 extracts digit plane l of z directly: v_l = floor((v + 128 (256^l - 1) / 255) / 256^l), d_l = ((v_l + 128) mod
+    256) - 128, the top plane keeping all of v_{L-1} (lattice.cu).  Must equal the sequential balanced base-256 split
+    (carry from plane to plane) used everywhere else, and recombine to v."""
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.integers(-2**40, 2**40, 4000), np.arange(-70000, 70000, 37), [127, 128, -128, -129, 32639, -32640]])
+    for L in (1, 2, 3, 4, 5):
+        for v in vals.tolist():
+            if abs(v) > sum(127 * 256**i for i in range(L)):
+                continue
+            seq, w = [], v
+            for l in range(L):
+                d = ((w + 128) & 255) - 128 if l < L - 1 else w
+                seq.append(d)
+                w = (w - d) >> 8
+            direct, bias = [], 0
+            for l in range(L):
+                vl = (v + bias) >> (8 * l)
+                direct.append(vl if l == L - 1 else ((vl + 128) & 255) - 128)
+                bias += 128 << (8 * l)
+            assert direct == seq and all(-128 <= d <= 127 for d in seq), (v, L, seq, direct)
+            assert sum(d * 256**i for i, d in enumerate(seq)) == v
